@@ -1,0 +1,163 @@
+/*
+ * pygpr_b200 — C ABI of the B200-native (sm_100a) PyGPR hot path.
+ *
+ * The reference (sarath-srinivas/PyGPR) has NO FFI layer: its hot path is torch-CPU calls made
+ * from Python classes.  Each entry point below replaces one group of those call sites; the
+ * reference file:line it stands in for is cited on every declaration.  A maintainer binds them
+ * with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major FP64 unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it;
+ *   - the library never allocates or frees persistent device memory: workspaces are passed in;
+ *   - return value: 0 on success, negative gpr_status on failure (gpr_last_error() has the text);
+ *     numerical failure of a factorisation is reported LAPACK-style through info[B]
+ *     (0 = ok, k>0 = leading minor of order k is not positive definite), never as a return code;
+ *   - matrices that are factorised are stored PADDED to a multiple of GPR_TILE (=128) in both
+ *     dimensions (`npad`); the padding block is the identity, so factors of the padded matrix
+ *     equal the padded factors.  Inputs are stored pre-scaled by the ARD length-scales
+ *     (a = x * ls, covar.py:137-140) with the feature dimension zero-padded to `dpad`
+ *     (a multiple of 4, the DMMA k-step).
+ */
+#ifndef PYGPR_B200_H
+#define PYGPR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPR_TILE 128
+#define GPR_ABI_VERSION 1
+
+typedef enum {
+    GPR_OK = 0,
+    GPR_ERR_BAD_ARG = -1,
+    GPR_ERR_CUDA = -2,
+    GPR_ERR_UNSUPPORTED = -3
+} gpr_status;
+
+int gpr_abi_version(void);
+const char* gpr_last_error(void);
+/* number of SMs / max opt-in shared memory of the current device (0 on error) */
+int gpr_device_sm_count(void);
+
+/* bytes of scratch gpr_predict needs for a given padded order (per launch, independent of B, m) */
+long long gpr_predict_scratch_bytes(int npad);
+/* bytes of scratch gpr_lml_grad needs */
+long long gpr_lml_grad_scratch_bytes(int B, int npad, int d);
+
+/*
+ * a[b,i,:] = x[b,i,:] * ls[b,:]   (zero padded to [npad, dpad]),   nrm[b,i] = sum_k a[b,i,k]^2
+ * Replaces covar.py:137-140 (x.mul(ls)) and covar.py:106 (x.square().sum) — call sites C1.
+ *   x        [B or 1, n, d]   x_bstride = n*d, or 0 when one x is shared by all experts
+ *   hp       row b at hp + b*hp_stride (hp_stride = 0 shares one row); ls = hp[1..d]
+ */
+int gpr_se_scale(const double* x, long long x_bstride, const double* hp, int hp_stride,
+                 int B, int n, int d, int npad, int dpad, double* a, double* nrm, void* stream);
+
+/*
+ * K[b] = sig_b^2 exp(-(|a_i|^2 + |a_j|^2 - 2 a_i.a_j)) + diag_add_b * I      (GEMM form, DMMA cross term)
+ * Replaces Squared_exponential.kernel covar.py:129-167 (+ White_noise covar.py:227-240 and the
+ * jitter gpr.py:68 through diag_add) — call sites C1-C3.
+ *   a,nrm     from gpr_se_scale ([B,npad,dpad], [B,npad])
+ *   hp        sig = hp[b*hp_stride + 0]
+ *   diag_add  [B] or NULL
+ *   K         [B, ldk, ldk] with ldk >= n.  rows/cols >= n (up to ldk) are written as identity
+ *             when pad_identity != 0, left untouched otherwise.
+ *   lower_only != 0 writes only tiles on or below the block diagonal.
+ */
+int gpr_se_build(const double* a, const double* nrm, const double* hp, int hp_stride,
+                 const double* diag_add, int B, int n, int npad, int dpad,
+                 double* K, int ldk, int pad_identity, int lower_only, void* stream);
+
+/*
+ * Ks[b,i,j] = sig_b^2 exp(-|as_i - a_j|^2)   rows = test points, cols = training points
+ * Replaces the xp branch of Squared_exponential.kernel covar.py:151-160 — call site C4.
+ *   as,nrms  [B, mpad, dpad],[B, mpad] scaled test points;  a,nrm [B, npad, dpad],[B,npad]
+ *   Ks       [B, m, n] dense (no padding)
+ */
+int gpr_se_cross(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
+                 const double* hp, int hp_stride, int B, int m, int n, int dpad, double* Ks, void* stream);
+
+/*
+ * dK[b,0] = 2 K_se/sig ; dK[b,1+k] = -2 ls_k (x_ik - x_jk)^2 K_se      (covar.py:169-206)
+ * Materialises the gradient tensor for API parity of kernel_and_grad only; MLE never calls it.
+ *   Kse [B,n,n] dense, x [B,n,d], dK [B,d+1,n,n]
+ */
+int gpr_se_kernel_grad(const double* Kse, const double* x, const double* hp, int hp_stride,
+                       int B, int n, int d, double* dK, void* stream);
+
+/*
+ * Batched lower Cholesky, blocked left-looking, trailing products on FP64 tensor cores (DMMA).
+ * Replaces tc.cholesky gpr.py:69 / loss.py:39,64,97 (call site C5) and, through y/z, the forward
+ * half of tc.cholesky_solve gpr.py:70-72 / loss.py:44 (C6) and the NLML scalar loss.py:49-51 (C14).
+ *
+ *   L        [B, npad, npad] in: see `gen`; out: lower factor (strict upper triangle of each
+ *            diagonal block zeroed; blocks above the block diagonal are NOT touched)
+ *   gen == 0 the lower triangle of K (+ identity padding) is already in L (in-place factorisation)
+ *   gen != 0 K is generated on the fly from (a, nrm, hp, diag_add) — L is write-only
+ *   invdiag  [B, npad/128, 128, 128] out: inverses of the diagonal blocks of L (lower triangular)
+ *   y        [B, npad] or NULL (zero padded).  If given:  z = L^-1 y  is written to z [B, npad]
+ *   logdet_half [B] out: sum_i log L_ii          (NULL allowed)
+ *   zz       [B] out: z.z = y^T K^-1 y            (NULL allowed; needs y)
+ *   info     [B] int32 out
+ */
+int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
+                      const double* diag_add, int B, int n, int npad, int dpad,
+                      double* invdiag, const double* y, double* z, double* logdet_half, double* zz,
+                      int* info, void* stream);
+
+/*
+ * alpha = L^-T z  (backward half of cholesky_solve, gpr.py:70-72).  HBM-bound: reads L once.
+ *   z [B,npad] in, alpha [B,npad] out (may alias z)
+ */
+int gpr_trsv_backward(const double* L, const double* invdiag, int B, int npad,
+                      const double* z, double* alpha, void* stream);
+
+/*
+ * Batched prediction: mean and variance of every expert at m test points, in one persistent kernel.
+ *   V^T = K* L^-T  by blocked forward substitution (DMMA), K* tiles generated on the fly (never in HBM)
+ *   mean[b,c] = sum_j K*[c,j] alpha[b,j]                                   gpr.py:79-85   (C4, C7)
+ *   var[b,c]  = prior_b - sum_j V[j,c]^2 ,  prior_b = sig_b^2 + noise_prior_b   gpr.py:96-106 (C8, C9)
+ *   xs       [m, d] raw test points shared by all experts;  hp as above (sig, ls)
+ *   prior    [B] prior variance at a test point (sig^2 + sig_n^2: K** includes the noise, gpr.py:98)
+ *   want_var == 0 skips the triangular solve (SK_WRAP path, scikit_model.py:34)
+ *   scratch  >= gpr_predict_scratch_bytes(npad)
+ */
+int gpr_predict(const double* L, const double* invdiag, const double* a, const double* nrm,
+                const double* alpha, const double* hp, int hp_stride, const double* prior,
+                const double* xs, int B, int n, int npad, int d, int dpad, int m,
+                double* mean, double* var, int want_var, void* scratch, void* stream);
+
+/*
+ * Negative log marginal likelihood gradient without forming dK:
+ *   U = L^-T (blocked, DMMA) written into the strict block-upper part of L's buffer, then
+ *   K^-1 = U U^T tile by tile with a fused epilogue reducing  W = K^-1 - alpha alpha^T  against
+ *   K_se generated on the fly:   loss.py:59-128 (C11-C13)
+ *     grad[b,0]     = (1/sig)  sum_ij W_ij Kse_ij
+ *     grad[b,1+k]   = -ls_k    sum_ij W_ij Kse_ij (x_ik - x_jk)^2
+ *     grad[b,d+1]   = sig_n tr(W)                       (only when has_noise)
+ *   L, invdiag, a, nrm, alpha from the calls above; grad [B, d+1+has_noise]
+ */
+int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                 const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                 double* grad, void* scratch, void* stream);
+
+/*
+ * GRBCM aggregation (diag), gr_bcm.py:116-149 (C15), split for expert sharding:
+ *   partial : S[0,c] = sum_i beta_i, S[1,c] = sum_i beta_i/var_i, S[2,c] = sum_i beta_i mean_i/var_i
+ *             over the nc_local experts held here; beta_i = 1 for global expert index 0
+ *             (first_global_index + i == 0), else 0.5 (log var_g - log var_i).
+ *             Optionally writes beta/prec rows (row stride m) for the reference's self.beta/self.prec.
+ *   finalize: var_A = 1/(S1 + (1-S0)/var_g),  mu_A = var_A (S2 + (1-S0) mean_g/var_g)
+ */
+int grbcm_partial(const double* mean_l, const double* var_l, const double* var_g,
+                  int nc_local, int first_global_index, int m, double* S,
+                  double* beta_rows, double* prec_rows, void* stream);
+int grbcm_finalize(const double* S, const double* mean_g, const double* var_g, int m,
+                   double* mu, double* var, double* beta0, double* prec0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

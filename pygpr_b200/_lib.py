@@ -1,0 +1,71 @@
+"""ctypes binding of libpygpr_b200.so (the C ABI in include/pygpr_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  The library is
+built in-tree by ``pygpr_b200/csrc/build.py`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpygpr_b200.so")
+
+TILE = 128
+ABI_VERSION = 1
+
+# name -> (restype, argtypes).  Pointers are passed as integers (tensor.data_ptr()).
+_P, _I, _LL = c_void_p, c_int, c_longlong
+SIGNATURES = {
+    "gpr_abi_version": (c_int, []),
+    "gpr_last_error": (c_char_p, []),
+    "gpr_device_sm_count": (c_int, []),
+    "gpr_predict_scratch_bytes": (c_longlong, [_I]),
+    "gpr_lml_grad_scratch_bytes": (c_longlong, [_I, _I, _I]),
+    "gpr_se_scale": (c_int, [_P, _LL, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "gpr_se_build": (c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "gpr_se_cross": (c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "gpr_se_kernel_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
+    "gpr_predict": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "gpr_lml_grad": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "grbcm_partial": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "grbcm_finalize": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class GprError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "pygpr_b200: %s not found. Build it with `python pygpr_b200/csrc/build.py` "
+            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gpr_abi_version() != ABI_VERSION:
+        raise ImportError("pygpr_b200: ABI version mismatch, rebuild the library")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point; raise GprError on a negative status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.gpr_last_error()
+        raise GprError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else ""))

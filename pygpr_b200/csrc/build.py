@@ -1,0 +1,40 @@
+"""Build libpygpr_b200.so (sm_100a) in-tree with nvcc.  Usage: python pygpr_b200/csrc/build.py [--force]"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+ROOT = os.path.dirname(PKG)
+OUT = os.path.join(PKG, "libpygpr_b200.so")
+SOURCES = [os.path.join(HERE, "gpr_kernels.cu")]
+DEPS = SOURCES + [os.path.join(HERE, "gpr_core.cuh"), os.path.join(ROOT, "include", "pygpr_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

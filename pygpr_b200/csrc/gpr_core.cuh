@@ -1,0 +1,231 @@
+// pygpr_b200 — shared device code: the FP64 tensor-core (DMMA) tile engine.
+//
+// Every O(N^3) step of the hot path (Cholesky trailing products, the triangular solves of the
+// predictive variance, L^-T and K^-1 = U U^T for the LML gradient) is expressed as the SAME
+// 128x128 "NT" tile product
+//        acc[r][c] += sum_k A[r][k] * B[c][k]        A, B row-major, k contiguous
+// so one software-pipelined mainloop serves all of them.  FP64 on sm_100a has no tcgen05 kind;
+// the tensor path is warp-level mma.sync (SASS DMMA.8x8x4), measured at 37.0 TFLOP/s on B200
+// (profiles/r01_fp64_issue_rates.log) = 1 DMMA / 16 clk / SM sub-partition, so the design goal is
+// simply to keep one DMMA issuing every 16 clocks per scheduler: 8 warps x (32x64) register tiles,
+// 12 LDS.64 per 32 DMMA, cp.async (LDGSTS, L2-only) 4-stage pipeline, conflict-free padded smem.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpr {
+
+constexpr int TILE = 128;                      // CTA tile edge
+constexpr int KC = 16;                         // k-chunk (doubles) per pipeline stage = 128 B rows
+constexpr int SLD = 20;                        // smem row stride of a chunk tile; 20 mod 16 = 4 -> conflict-free 64-bit fragment loads
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;                  // 8 warps: 4 (rows) x 2 (cols), warp tile 32 x 64
+constexpr int STAGE_DOUBLES = 2 * TILE * SLD;  // A chunk tile + B chunk tile
+constexpr int MAIN_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163,840 B
+constexpr int XLD = 132;                       // row stride of a full 128x128 smem tile (132 mod 16 = 4)
+static_assert(TILE * XLD * 8 <= MAIN_SMEM_BYTES, "full tile must overlay the pipeline stages");
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// D(8x8) += A(8x4, row) * B(4x8, col):  lane (g=lane/4, t=lane%4) holds A[g][t], B[t][g], C[g][2t..2t+1]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
+}
+
+// One contiguous run of k-chunks: A rows at A + r*lda, B rows at B + c*ldb, both advancing 16 doubles per chunk.
+struct Seg {
+    const double* A;
+    long long lda;
+    const double* B;
+    long long ldb;
+    int nchunks;
+};
+
+struct NoHook {
+    __device__ __forceinline__ void pre(int) {}
+    __device__ __forceinline__ void post(const double*, int) {}
+};
+
+__device__ __forceinline__ void zero_acc(double (&acc)[4][8][2]) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+}
+
+// acc += A * B^T over the chunks of s0 then s1.  SAME_AB: the B tile is the A tile (diagonal blocks) and is
+// loaded once.  HOOK gets every landed A chunk tile (used to fuse the forward solve into the Cholesky).
+// Ends with all copies drained and a __syncthreads(), so the caller may reuse `smem` immediately.
+template <bool SAME_AB, typename HOOK>
+__device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, const Seg& s1, double* smem, HOOK& hook) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int total = s0.nchunks + s1.nchunks;
+
+    auto issue = [&](int c) {
+        if (c < total) {
+            const bool first = c < s0.nchunks;
+            const Seg& s = first ? s0 : s1;
+            const int lc = first ? c : c - s0.nchunks;
+            double* sA = smem + (c % STAGES) * STAGE_DOUBLES;
+            double* sB = sA + TILE * SLD;
+            const double* gA = s.A + (long long)lc * KC;
+            const double* gB = s.B + (long long)lc * KC;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int id = tid + q * NTHREADS;
+                const int row = id >> 3, cc = (id & 7) * 2;
+                cp_async16(sA + row * SLD + cc, gA + row * s.lda + cc);
+                if (!SAME_AB) cp_async16(sB + row * SLD + cc, gB + row * s.ldb + cc);
+            }
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int c = 0; c < STAGES - 1; ++c) issue(c);
+
+    const int aoff = (wm * 32 + g) * SLD + t;
+    const int boff = (wn * 64 + g) * SLD + t;
+    for (int c = 0; c < total; ++c) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(c + STAGES - 1);
+        const double* sA = smem + (c % STAGES) * STAGE_DOUBLES;
+        const double* sB = SAME_AB ? sA : sA + TILE * SLD;
+        hook.pre(c);
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; ++kk) {
+            double a[4], b[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = sA[aoff + mi * 8 * SLD + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) b[ni] = sB[boff + ni * 8 * SLD + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+        }
+        hook.post(sA, c);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+// Row / column of accumulator element (mi, ni, e) inside the 128x128 tile.
+__device__ __forceinline__ int acc_row(int mi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    return (warp & 3) * 32 + mi * 8 + (lane >> 2);
+}
+__device__ __forceinline__ int acc_col(int ni, int e) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    return (warp >> 2) * 64 + ni * 8 + 2 * (lane & 3) + e;
+}
+
+// smem row stride for a [128 x dpad] scaled-input tile: stride mod 16 in {4, 12} keeps fragment loads conflict-free
+__host__ __device__ __forceinline__ int feat_sld(int dpad) { return (dpad % 8 == 0) ? dpad + 4 : dpad; }
+
+// Load a [128 x dpad] tile of scaled inputs (global row stride dpad) into smem with stride sld (cp.async; caller waits).
+__device__ __forceinline__ void load_feat_tile(double* s, int sld, const double* g, int dpad) {
+    const int per_row = dpad / 2;  // 16-byte chunks per row
+    for (int id = threadIdx.x; id < TILE * per_row; id += NTHREADS) {
+        const int row = id / per_row, cc = (id % per_row) * 2;
+        cp_async16(s + row * sld + cc, g + (long long)row * dpad + cc);
+    }
+}
+
+// Squared-exponential tile in GEMM form, covar.py:102-149:  sqd = (|aR|^2 + |aC|^2) - 2 aR.aC ;  k = sig2 exp(-sqd)
+// The cross term runs on DMMA.  f(mi, ni, e, kval) is called for every accumulator element of the thread.
+template <typename F>
+__device__ __forceinline__ void gen_se_tile(const double* sR, const double* sC, int sld, const double* nR, const double* nC,
+                                            int dpad, double sig2, F&& f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const double* pa = sR + (wm * 32 + g) * sld + t;
+    double nr[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) nr[mi] = nR[wm * 32 + mi * 8 + g];
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        double G[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) G[mi][0] = G[mi][1] = 0.0;
+        const double* pb = sC + (wn * 64 + ni * 8 + g) * sld + t;
+        for (int k = 0; k < dpad; k += 4) {
+            const double b = pb[k];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma(G[mi], pa[mi * 8 * sld + k], b);
+        }
+        const int c0 = wn * 64 + ni * 8 + 2 * t;
+        const double nc0 = nC[c0], nc1 = nC[c0 + 1];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            f(mi, ni, 0, sig2 * exp(-(-2.0 * G[mi][0] + (nr[mi] + nc0))));
+            f(mi, ni, 1, sig2 * exp(-(-2.0 * G[mi][1] + (nr[mi] + nc1))));
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// In-place lower Cholesky of the 128x128 tile T (row stride XLD) by all 256 threads; right-looking, two barriers
+// per column.  colk is a 128-double scratch.  Returns (through *fail) the first 1-based column with a non-positive
+// pivot, 0 if none.  Strict upper triangle is left untouched.
+__device__ __forceinline__ void potf2_smem(double* T, double* colk, int* fail) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = 0; k < TILE; ++k) {
+        __syncthreads();
+        const double d = T[k * XLD + k];
+        if (tid == 0 && !(d > 0.0) && *fail == 0) *fail = k + 1;
+        const double l = sqrt(d);
+        if (tid > k && tid < TILE) {
+            const double v = T[tid * XLD + k] / l;
+            colk[tid] = v;
+            T[tid * XLD + k] = v;
+        }
+        __syncthreads();
+        if (tid == 0) T[k * XLD + k] = l;
+        for (int i = k + 1 + warp; i < TILE; i += NTHREADS / 32) {
+            const double ci = colk[i];
+            for (int j = k + 1 + lane; j <= i; j += 32) T[i * XLD + j] -= ci * colk[j];
+        }
+    }
+    __syncthreads();
+}
+
+// In-place inverse of the lower-triangular 128x128 tile T (row stride XLD); columns from last to first (dtrti2).
+__device__ __forceinline__ void trti2_smem(double* T, double* colk) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = TILE - 1; j >= 0; --j) {
+        __syncthreads();
+        const double ajj = 1.0 / T[j * XLD + j];
+        if (tid > j && tid < TILE) colk[tid] = T[tid * XLD + j];
+        __syncthreads();
+        // new column j below the diagonal: -ajj * Tinv[j+1:, j+1:] * colk[j+1:]
+        for (int i = j + 1 + warp; i < TILE; i += NTHREADS / 32) {
+            double s = 0.0;
+            for (int k = j + 1 + lane; k <= i; k += 32) s += T[i * XLD + k] * colk[k];
+            s = warp_sum(s);
+            if (lane == 0) T[i * XLD + j] = -ajj * s;
+        }
+        if (tid == 0) T[j * XLD + j] = ajj;
+    }
+    __syncthreads();
+}
+
+}  // namespace gpr

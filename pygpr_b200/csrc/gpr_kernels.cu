@@ -1,0 +1,761 @@
+// pygpr_b200 — sm_100a kernels + C ABI for the PyGPR hot path (see include/pygpr_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (pygpr_b200/csrc/build.py)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pygpr_b200.h"
+#include "gpr_core.cuh"
+
+using namespace gpr;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (no exceptions cross the C boundary)
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "", long long v = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, v);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) return fail(GPR_ERR_CUDA, "%s (cuda error %lld)", cudaGetErrorString(e__), (long long)e__); \
+    } while (0)
+#define ARG_CHECK(cond)                                                                 \
+    do {                                                                                \
+        if (!(cond)) return fail(GPR_ERR_BAD_ARG, "bad argument: %s (line %lld)", #cond, __LINE__); \
+    } while (0)
+
+extern "C" int gpr_abi_version(void) { return GPR_ABI_VERSION; }
+extern "C" const char* gpr_last_error(void) { return g_err; }
+extern "C" int gpr_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+template <typename K>
+static cudaError_t opt_in_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: ARD scaling  a = x * ls (zero padded), nrm = |a|^2            covar.py:137-140, 106
+// HBM-bound elementwise; one thread per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void se_scale_kernel(const double* __restrict__ x, long long x_bstride, const double* __restrict__ hp,
+                                int hp_stride, int n, int d, int npad, int dpad, double* __restrict__ a,
+                                double* __restrict__ nrm) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    const double* ls = hp + (long long)b * hp_stride + 1;
+    double* ar = a + ((long long)b * npad + i) * dpad;
+    double s = 0.0;
+    if (i < n) {
+        const double* xr = x + (long long)b * x_bstride + (long long)i * d;
+        for (int k = 0; k < d; ++k) {
+            const double v = xr[k] * ls[k];
+            ar[k] = v;
+            s += v * v;  // same left-to-right order as tc.sum(x.square(), 2) on short rows
+        }
+        for (int k = d; k < dpad; ++k) ar[k] = 0.0;
+    } else {
+        for (int k = 0; k < dpad; ++k) ar[k] = 0.0;
+    }
+    nrm[(long long)b * npad + i] = s;
+}
+
+extern "C" int gpr_se_scale(const double* x, long long x_bstride, const double* hp, int hp_stride, int B, int n, int d,
+                            int npad, int dpad, double* a, double* nrm, void* stream) {
+    ARG_CHECK(x && hp && a && nrm);
+    ARG_CHECK(B > 0 && n > 0 && d > 0 && npad >= n && dpad >= d && dpad % 4 == 0);
+    dim3 grid((npad + 127) / 128, B);
+    se_scale_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, x_bstride, hp, hp_stride, n, d, npad, dpad, a, nrm);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1/K2: stand-alone kernel-matrix builders (API parity of Covar.kernel; the fit/predict path
+// generates these tiles inside the factorisation / solve kernels instead).
+// ---------------------------------------------------------------------------------------------
+struct FeatSmem {
+    double* sR;
+    double* sC;
+    double* nR;
+    double* nC;
+    int sld;
+};
+__device__ __forceinline__ FeatSmem carve_feat(double* base, int dpad) {
+    FeatSmem f;
+    f.sld = feat_sld(dpad);
+    f.sR = base;
+    f.sC = base + TILE * f.sld;
+    f.nR = f.sC + TILE * f.sld;
+    f.nC = f.nR + TILE;
+    return f;
+}
+static inline int feat_smem_bytes(int dpad) { return (2 * TILE * feat_sld(dpad) + 2 * TILE) * 8; }
+
+// rows from (aR, nrmR) tile tr, cols from (aC, nrmC) tile tc; out[b][row][col] with leading dim ld.
+//   mode 0 (symmetric build): diag_add on row==col, identity padding up to `ldlim` when pad_identity
+//   mode 1 (cross): plain
+__global__ void __launch_bounds__(NTHREADS) se_tile_kernel(const double* __restrict__ aR, const double* __restrict__ nrmR,
+                                                           int rpad, const double* __restrict__ aC,
+                                                           const double* __restrict__ nrmC, int cpad,
+                                                           const double* __restrict__ hp, int hp_stride,
+                                                           const double* __restrict__ diag_add, int nrows, int ncols,
+                                                           int dpad, double* __restrict__ out, long long ld,
+                                                           long long out_bstride, int mode, int pad_identity,
+                                                           int lower_only) {
+    extern __shared__ double smem[];
+    const int tc = blockIdx.x, tr = blockIdx.y, b = blockIdx.z;
+    if (lower_only && tc > tr) return;
+    FeatSmem f = carve_feat(smem, dpad);
+    load_feat_tile(f.sR, f.sld, aR + ((long long)b * rpad + tr * TILE) * dpad, dpad);
+    load_feat_tile(f.sC, f.sld, aC + ((long long)b * cpad + tc * TILE) * dpad, dpad);
+    cp_async_commit();
+    if (threadIdx.x < TILE) {
+        f.nR[threadIdx.x] = nrmR[(long long)b * rpad + tr * TILE + threadIdx.x];
+        f.nC[threadIdx.x] = nrmC[(long long)b * cpad + tc * TILE + threadIdx.x];
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const double sig = hp[(long long)b * hp_stride];
+    const double sig2 = sig * sig;
+    const double dadd = (mode == 0 && diag_add) ? diag_add[b] : 0.0;
+    double* ob = out + (long long)b * out_bstride;
+    const long long lim_r = (mode == 0 && pad_identity) ? ld : nrows;
+    const long long lim_c = (mode == 0 && pad_identity) ? ld : ncols;
+    gen_se_tile(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig2, [&](int mi, int ni, int e, double kv) {
+        const long long r = (long long)tr * TILE + acc_row(mi);
+        const long long c = (long long)tc * TILE + acc_col(ni, e);
+        if (r < nrows && c < ncols) {
+            ob[r * ld + c] = (mode == 0 && r == c) ? kv + dadd : kv;
+        } else if (r < lim_r && c < lim_c) {
+            ob[r * ld + c] = (r == c) ? 1.0 : 0.0;
+        }
+    });
+}
+
+extern "C" int gpr_se_build(const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
+                            int B, int n, int npad, int dpad, double* K, int ldk, int pad_identity, int lower_only,
+                            void* stream) {
+    ARG_CHECK(a && nrm && hp && K);
+    ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && ldk >= n);
+    ARG_CHECK(!pad_identity || ldk <= npad);
+    const int smem = feat_smem_bytes(dpad);
+    if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused SE tile%s (dpad=%lld)", "", dpad);
+    CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
+    const int nt = (pad_identity ? (ldk + TILE - 1) / TILE : (n + TILE - 1) / TILE);
+    dim3 grid(nt, nt, B);
+    se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, nrm, npad, a, nrm, npad, hp, hp_stride, diag_add, n, n,
+                                                                   dpad, K, ldk, (long long)ldk * ldk, 0, pad_identity,
+                                                                   lower_only);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+extern "C" int gpr_se_cross(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
+                            const double* hp, int hp_stride, int B, int m, int n, int dpad, double* Ks, void* stream) {
+    ARG_CHECK(as && nrms && a && nrm && hp && Ks);
+    ARG_CHECK(B > 0 && m > 0 && n > 0 && mpad % TILE == 0 && npad % TILE == 0 && mpad >= m && npad >= n && dpad % 4 == 0);
+    const int smem = feat_smem_bytes(dpad);
+    if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused SE tile%s (dpad=%lld)", "", dpad);
+    CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
+    dim3 grid((n + TILE - 1) / TILE, (m + TILE - 1) / TILE, B);
+    se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(as, nrms, mpad, a, nrm, npad, hp, hp_stride, nullptr, m, n,
+                                                                   dpad, Ks, n, (long long)m * n, 1, 0, 0);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// dK materialisation for kernel_and_grad (API parity; small n only)                 covar.py:184-199
+__global__ void se_grad_kernel(const double* __restrict__ Kse, const double* __restrict__ x, const double* __restrict__ hp,
+                               int hp_stride, int n, int d, double* __restrict__ dK) {
+    const int b = blockIdx.z, p = blockIdx.y;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * n) return;
+    const int i = idx / n, j = idx % n;
+    const double k = Kse[(long long)b * n * n + idx];
+    const double* h = hp + (long long)b * hp_stride;
+    double v;
+    if (p == 0) {
+        v = k * (2.0 / h[0]);  // covar.py:189
+    } else {
+        const double* xb = x + (long long)b * n * d;
+        const double df = xb[(long long)i * d + (p - 1)] - xb[(long long)j * d + (p - 1)];
+        v = df * df * h[p] * k * (-2.0);  // covar.py:194-197
+    }
+    dK[(((long long)b * (d + 1) + p) * n) * n + idx] = v;
+}
+
+extern "C" int gpr_se_kernel_grad(const double* Kse, const double* x, const double* hp, int hp_stride, int B, int n, int d,
+                                  double* dK, void* stream) {
+    ARG_CHECK(Kse && x && hp && dK && B > 0 && n > 0 && d > 0);
+    dim3 grid((unsigned)(((long long)n * n + 255) / 256), d + 1, B);
+    se_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Kse, x, hp, hp_stride, n, d, dK);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: batched blocked left-looking Cholesky.  Two launches per block column j:
+//   potrf_diag_kernel : T = K_jj - L[j,0:j] L[j,0:j]^T (DMMA) -> potf2 in smem -> L_jj, inv(L_jj);
+//                       forward solve z_j = inv(L_jj)(y_j - L[j,0:j] z[0:j]) fused (GEMV on the chunks
+//                       already in smem), plus sum log L_ii and z.z  -> NLML pieces for free.
+//   potrf_panel_kernel: L_ij = (K_ij - L[i,0:j] L[j,0:j]^T) inv(L_jj)^T for every row tile i>j (DMMA twice).
+// ---------------------------------------------------------------------------------------------
+struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-warp per row, 8 rows per half-warp
+    const double* z;
+    double zk;
+    double part[8];
+    __device__ __forceinline__ void pre(int c) { zk = z ? z[c * KC + (threadIdx.x & 15)] : 0.0; }
+    __device__ __forceinline__ void post(const double* sA, int) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const double* p = sA + (warp * 16 + (lane >> 4) * 8) * SLD + (lane & 15);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[r] += p[r * SLD] * zk;
+    }
+};
+
+template <bool GEN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
+                  const double* __restrict__ hp, int hp_stride, const double* __restrict__ diag_add, int dpad,
+                  double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
+                  double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
+    extern __shared__ double smem[];
+    __shared__ double colk[TILE];
+    __shared__ double svec[TILE];
+    __shared__ int s_fail;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nt = npad / TILE;
+    double* Lb = L + (long long)b * npad * npad;
+    double* Ljj = Lb + ((long long)j * TILE) * npad + j * TILE;
+    if (tid == 0) s_fail = 0;
+
+    double acc[4][8][2];
+    zero_acc(acc);
+    GemvHook hook;
+    hook.z = y ? z + (long long)b * npad : nullptr;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) hook.part[r] = 0.0;
+    Seg s0{Lb + ((long long)j * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
+    Seg s1{nullptr, 0, nullptr, 0, 0};
+    mainloop<true>(acc, s0, s1, smem, hook);
+
+    // GEMV result of the fused forward solve
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double v = hook.part[r];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 15) == 0) svec[warp * 16 + (lane >> 4) * 8 + r] = v;
+        }
+    }
+
+    double* T = smem;  // full tile overlays the (drained) pipeline stages
+    if (GEN) {
+        // generate K_jj into T, then subtract the accumulated product
+        double* fbase = smem + TILE * XLD;
+        FeatSmem f = carve_feat(fbase, dpad);
+        load_feat_tile(f.sR, f.sld, a + ((long long)b * npad + j * TILE) * dpad, dpad);
+        cp_async_commit();
+        if (tid < TILE) f.nR[tid] = nrm[(long long)b * npad + j * TILE + tid];
+        cp_async_wait<0>();
+        __syncthreads();
+        const double sig = hp[(long long)b * hp_stride];
+        const double dadd = diag_add ? diag_add[b] : 0.0;
+        gen_se_tile(f.sR, f.sR, f.sld, f.nR, f.nR, dpad, sig * sig, [&](int mi, int ni, int e, double kv) {
+            const int r = acc_row(mi), c = acc_col(ni, e);
+            const int gr = j * TILE + r, gc = j * TILE + c;
+            double v;
+            if (gr < n && gc < n) v = (r == c) ? kv + dadd : kv;
+            else v = (r == c) ? 1.0 : 0.0;
+            T[r * XLD + c] = v - acc[mi][ni][e];
+        });
+    } else {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                const int r = acc_row(mi), c = acc_col(ni, 0);
+                const double2 k2 = *reinterpret_cast<const double2*>(Ljj + (long long)r * npad + c);
+                T[r * XLD + c] = k2.x - acc[mi][ni][0];
+                T[r * XLD + c + 1] = k2.y - acc[mi][ni][1];
+            }
+    }
+    potf2_smem(T, colk, &s_fail);
+
+    // write L_jj (strict upper zeroed) and accumulate sum log L_ii
+    for (int id = tid; id < TILE * TILE; id += NTHREADS) {
+        const int r = id >> 7, c = id & 127;
+        Ljj[(long long)r * npad + c] = (c <= r) ? T[r * XLD + c] : 0.0;
+    }
+    if (tid < 32) {
+        double s = 0.0;
+        for (int k = tid; k < TILE; k += 32) s += log(T[k * XLD + k]);
+        s = warp_sum(s);
+        if (tid == 0) {
+            if (logdet_half) logdet_half[b] = (j == 0 ? 0.0 : logdet_half[b]) + s;
+            if (info) {
+                if (j == 0) info[b] = 0;
+                if (s_fail && info[b] == 0) info[b] = j * TILE + s_fail;
+            }
+        }
+    }
+    trti2_smem(T, colk);
+    double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
+    for (int id = tid; id < TILE * TILE; id += NTHREADS) {
+        const int r = id >> 7, c = id & 127;
+        inv[id] = (c <= r) ? T[r * XLD + c] : 0.0;
+    }
+    if (y) {
+        // z_j = inv(L_jj) (y_j - L[j,0:j] z[0:j])
+        if (tid < TILE) colk[tid] = y[(long long)b * npad + j * TILE + tid] - svec[tid];
+        __syncthreads();
+        if (tid < TILE) {
+            double s = 0.0;
+            for (int k = 0; k <= tid; ++k) s += T[tid * XLD + k] * colk[k];
+            z[(long long)b * npad + j * TILE + tid] = s;
+            svec[tid] = s * s;
+        }
+        __syncthreads();
+        if (tid < 32 && zz) {
+            double s = svec[tid] + svec[tid + 32] + svec[tid + 64] + svec[tid + 96];
+            s = warp_sum(s);
+            if (tid == 0) zz[b] = (j == 0 ? 0.0 : zz[b]) + s;
+        }
+    }
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
+                   const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.y, i = j + 1 + blockIdx.x;
+    const int nt = npad / TILE;
+    double* Lb = L + (long long)b * npad * npad;
+    double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
+
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
+    mainloop<false>(acc, s0, none, smem, nh);
+
+    if (GEN) {
+        FeatSmem f = carve_feat(smem, dpad);
+        load_feat_tile(f.sR, f.sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+        load_feat_tile(f.sC, f.sld, a + ((long long)b * npad + j * TILE) * dpad, dpad);
+        cp_async_commit();
+        if (threadIdx.x < TILE) {
+            f.nR[threadIdx.x] = nrm[(long long)b * npad + i * TILE + threadIdx.x];
+            f.nC[threadIdx.x] = nrm[(long long)b * npad + j * TILE + threadIdx.x];
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        const double sig = hp[(long long)b * hp_stride];
+        gen_se_tile(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig * sig, [&](int mi, int ni, int e, double kv) {
+            const int gr = i * TILE + acc_row(mi), gc = j * TILE + acc_col(ni, e);
+            acc[mi][ni][e] = ((gr < n && gc < n) ? kv : 0.0) - acc[mi][ni][e];
+        });
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+                *reinterpret_cast<double2*>(Lij + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    } else {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                double2* p = reinterpret_cast<double2*>(Lij + (long long)acc_row(mi) * npad + acc_col(ni, 0));
+                double2 k2 = *p;
+                k2.x -= acc[mi][ni][0];
+                k2.y -= acc[mi][ni][1];
+                *p = k2;
+            }
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // triangular solve as a product with the inverted diagonal block:  L_ij = Xhat * inv(L_jj)^T
+    zero_acc(acc);
+    Seg s1{Lij, npad, invdiag + ((long long)b * nt + j) * TILE * TILE, TILE, TILE / KC};
+    mainloop<false>(acc, s1, none, smem, nh);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            *reinterpret_cast<double2*>(Lij + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+}
+
+extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
+                                 const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y,
+                                 double* z, double* logdet_half, double* zz, int* info, void* stream) {
+    ARG_CHECK(L && invdiag);
+    ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n);
+    ARG_CHECK(!gen || (a && nrm && hp && dpad > 0 && dpad % 4 == 0));
+    ARG_CHECK(!y || z);
+    ARG_CHECK(!zz || y);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    int smem_diag = MAIN_SMEM_BYTES, smem_panel = MAIN_SMEM_BYTES;
+    if (gen) {
+        const int fb = feat_smem_bytes(dpad);
+        if (TILE * XLD * 8 + fb > 227 * 1024)
+            return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
+        if (TILE * XLD * 8 + fb > smem_diag) smem_diag = TILE * XLD * 8 + fb;
+        if (fb > smem_panel) smem_panel = fb;
+        CUDA_TRY(opt_in_smem(potrf_diag_kernel<true>, smem_diag));
+        CUDA_TRY(opt_in_smem(potrf_panel_kernel<true>, smem_panel));
+    } else {
+        CUDA_TRY(opt_in_smem(potrf_diag_kernel<false>, smem_diag));
+        CUDA_TRY(opt_in_smem(potrf_panel_kernel<false>, smem_panel));
+    }
+    for (int j = 0; j < nt; ++j) {
+        if (gen)
+            potrf_diag_kernel<true><<<B, NTHREADS, smem_diag, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad, invdiag,
+                                                                     y, z, logdet_half, zz, info);
+        else
+            potrf_diag_kernel<false><<<B, NTHREADS, smem_diag, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad,
+                                                                      invdiag, y, z, logdet_half, zz, info);
+        if (j + 1 < nt) {
+            dim3 grid(nt - 1 - j, B);
+            if (gen)
+                potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag);
+            else
+                potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: alpha = L^-T z.  HBM-bound (reads the lower triangle of L once); one CTA per expert walks the block
+// columns from last to first:  alpha_j = inv(L_jj)^T (z_j - sum_{i>j} L_ij^T alpha_i).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS) trsv_backward_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
+                                                                 int npad, const double* __restrict__ z,
+                                                                 double* __restrict__ alpha) {
+    extern __shared__ double sal[];  // alpha for this expert [npad]
+    __shared__ double part[NTHREADS / 32][TILE];
+    __shared__ double rhs[TILE];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nt = npad / TILE;
+    const double* Lb = L + (long long)b * npad * npad;
+    for (int j = nt - 1; j >= 0; --j) {
+        // s[c] = sum_{r >= (j+1)*128} L[r, j*128 + c] * alpha[r]; lane owns columns 4*lane..4*lane+3
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        const double* col = Lb + (long long)j * TILE + 4 * lane;
+        const int r0 = (j + 1) * TILE;
+        int r = r0 + warp;
+        for (; r + 3 * 8 < npad; r += 4 * 8) {
+            double2 v[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double* p = col + (long long)(r + u * 8) * npad;
+                v[u][0] = *reinterpret_cast<const double2*>(p);
+                v[u][1] = *reinterpret_cast<const double2*>(p + 2);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double al = sal[r + u * 8];
+                s0 += v[u][0].x * al; s1 += v[u][0].y * al; s2 += v[u][1].x * al; s3 += v[u][1].y * al;
+            }
+        }
+        for (; r < npad; r += 8) {
+            const double* p = col + (long long)r * npad;
+            const double2 v0 = *reinterpret_cast<const double2*>(p), v1 = *reinterpret_cast<const double2*>(p + 2);
+            const double al = sal[r];
+            s0 += v0.x * al; s1 += v0.y * al; s2 += v1.x * al; s3 += v1.y * al;
+        }
+        part[warp][4 * lane + 0] = s0; part[warp][4 * lane + 1] = s1;
+        part[warp][4 * lane + 2] = s2; part[warp][4 * lane + 3] = s3;
+        __syncthreads();
+        if (tid < TILE) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NTHREADS / 32; ++w) s += part[w][tid];
+            rhs[tid] = z[(long long)b * npad + j * TILE + tid] - s;
+        }
+        __syncthreads();
+        // alpha_j[c] = sum_{k >= c} inv[k][c] * rhs[k]     (inv lower triangular, read coalesced by rows)
+        const double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
+        s0 = s1 = s2 = s3 = 0;
+        for (int k = warp; k < TILE; k += 8) {
+            const double* p = inv + k * TILE + 4 * lane;
+            const double2 v0 = *reinterpret_cast<const double2*>(p), v1 = *reinterpret_cast<const double2*>(p + 2);
+            const double rk = rhs[k];
+            s0 += v0.x * rk; s1 += v0.y * rk; s2 += v1.x * rk; s3 += v1.y * rk;
+        }
+        part[warp][4 * lane + 0] = s0; part[warp][4 * lane + 1] = s1;
+        part[warp][4 * lane + 2] = s2; part[warp][4 * lane + 3] = s3;
+        __syncthreads();
+        if (tid < TILE) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NTHREADS / 32; ++w) s += part[w][tid];
+            sal[j * TILE + tid] = s;
+            alpha[(long long)b * npad + j * TILE + tid] = s;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int gpr_trsv_backward(const double* L, const double* invdiag, int B, int npad, const double* z, double* alpha,
+                                 void* stream) {
+    ARG_CHECK(L && invdiag && z && alpha && B > 0 && npad > 0 && npad % TILE == 0);
+    const int smem = npad * 8;
+    if (smem > 200 * 1024) return fail(GPR_ERR_UNSUPPORTED, "matrix order too large for the single-CTA backward solve%s (npad=%lld)", "", npad);
+    CUDA_TRY(opt_in_smem(trsv_backward_kernel, smem));
+    trsv_backward_kernel<<<B, NTHREADS, smem, (cudaStream_t)stream>>>(L, invdiag, npad, z, alpha);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: batched prediction.  Persistent CTAs pull (expert, 128-test-point tile) tasks; each task is an
+// independent blocked forward substitution  V^T[:, i] = (K*[:, i] - V^T[:, 0:i] L[i, 0:i]^T) inv(L_ii)^T
+// — i.e. the Cholesky factorisation extended by 128 extra rows — with K* tiles generated in smem
+// (never in HBM), the mean  K* alpha  and the variance reduction  sum V^2  fused into the epilogues.
+// V^T lives in a per-CTA scratch slab [128, npad] that only this CTA touches.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ a,
+               const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
+               const double* __restrict__ prior, const double* __restrict__ xs, int B, int n, int npad, int d, int dpad, int m,
+               double* __restrict__ mean, double* __restrict__ var, int want_var, double* __restrict__ scratch,
+               int* __restrict__ counter) {
+    extern __shared__ double smem[];
+    __shared__ int s_task;
+    __shared__ double red[2][2][TILE];  // [mean|var][wn][row]
+    const int tid = threadIdx.x;
+    const int nt = npad / TILE;
+    const int mt = (m + TILE - 1) / TILE;
+    const int ntasks = B * mt;
+    const int sld = feat_sld(dpad);
+    // persistent region (after the pipeline stages): scaled test tile + its norms + alpha block + col norms
+    double* sT = smem + MAIN_SMEM_BYTES / 8;  // [128 x sld]
+    double* nT = sT + TILE * sld;             // [128]
+    double* sAl = nT + TILE;                  // [128] alpha block of the current step
+    double* Vt = scratch + (long long)blockIdx.x * TILE * npad;
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_task = atomicAdd(counter, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= ntasks) break;
+        const int b = task / mt, ct = task % mt;
+        const double* hb = hp + (long long)b * hp_stride;
+        const double sig2 = hb[0] * hb[0];
+        const double* Lb = L + (long long)b * npad * npad;
+
+        // scaled test tile  as = xs * ls_b  (zero rows beyond m, zero cols beyond d) and its norms
+        for (int id = tid; id < TILE * dpad; id += NTHREADS) {
+            const int r = id / dpad, k = id % dpad;
+            const int gr = ct * TILE + r;
+            sT[r * sld + k] = (gr < m && k < d) ? xs[(long long)gr * d + k] * hb[1 + k] : 0.0;
+        }
+        __syncthreads();
+        if (tid < TILE) {
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s += sT[tid * sld + k] * sT[tid * sld + k];
+            nT[tid] = s;
+        }
+        double macc[4] = {0, 0, 0, 0}, vacc[4] = {0, 0, 0, 0};
+
+        for (int i = 0; i < nt; ++i) {
+            double acc[4][8][2];
+            zero_acc(acc);
+            __syncthreads();  // V^T columns written by the previous step are visible; staged features are free
+            if (want_var && i > 0) {
+                Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
+                mainloop<false>(acc, s0, none, smem, nh);
+            }
+            // K*(test tile, train block i) in smem-staged features
+            double* sC = smem;
+            double* nC = sC + TILE * sld;
+            load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+            cp_async_commit();
+            if (tid < TILE) {
+                nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
+                sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
+            }
+            cp_async_wait<0>();
+            __syncthreads();
+            double* Vi = Vt + i * TILE;
+            gen_se_tile(sT, sC, sld, nT, nC, dpad, sig2, [&](int mi, int ni, int e, double kv) {
+                const int c = acc_col(ni, e);
+                if (i * TILE + c >= n) kv = 0.0;  // padding columns carry no covariance
+                macc[mi] += kv * sAl[c];
+                acc[mi][ni][e] = kv - acc[mi][ni][e];
+            });
+            if (!want_var) continue;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+                    *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            __threadfence_block();
+            __syncthreads();
+            zero_acc(acc);
+            Seg s1{Vi, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
+            mainloop<false>(acc, s1, none, smem, nh);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) {
+                    vacc[mi] += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+                    *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                }
+            __threadfence_block();
+        }
+        // reduce the per-thread row partials: over the 4 lanes of a quad, then over the two column warps
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            double mv = macc[mi], vv = vacc[mi];
+            mv += __shfl_xor_sync(0xffffffffu, mv, 1);
+            mv += __shfl_xor_sync(0xffffffffu, mv, 2);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+            if ((lane & 3) == 0) {
+                red[0][warp >> 2][acc_row(mi)] = mv;
+                red[1][warp >> 2][acc_row(mi)] = vv;
+            }
+        }
+        __syncthreads();
+        if (tid < TILE) {
+            const int gr = ct * TILE + tid;
+            if (gr < m) {
+                mean[(long long)b * m + gr] = red[0][0][tid] + red[0][1][tid];
+                if (want_var) var[(long long)b * m + gr] = prior[b] - (red[1][0][tid] + red[1][1][tid]);
+            }
+        }
+    }
+}
+
+static inline long long predict_smem_bytes(int dpad) { return MAIN_SMEM_BYTES + (long long)(TILE * feat_sld(dpad) + 2 * TILE) * 8; }
+
+extern "C" long long gpr_predict_scratch_bytes(int npad) {
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) sms = 148;
+    return (long long)sms * TILE * npad * 8 + 256;
+}
+
+extern "C" int gpr_predict(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                           const double* hp, int hp_stride, const double* prior, const double* xs, int B, int n, int npad,
+                           int d, int dpad, int m, double* mean, double* var, int want_var, void* scratch, void* stream) {
+    ARG_CHECK(L && invdiag && a && nrm && alpha && hp && xs && mean && scratch);
+    ARG_CHECK(!want_var || (var && prior));
+    ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
+    const long long smem = predict_smem_bytes(dpad);
+    if (smem > 227 * 1024 || (TILE * feat_sld(dpad) + TILE) * 8 > MAIN_SMEM_BYTES)
+        return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused prediction%s (dpad=%lld)", "", dpad);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(opt_in_smem(predict_kernel, (int)smem));
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    const int mt = (m + TILE - 1) / TILE;
+    const long long ntasks = (long long)B * mt;
+    const int grid = (int)(ntasks < sms ? ntasks : sms);
+    // layout of scratch: [int counter (256 B)] [grid slabs of 128 x npad doubles]
+    int* counter = reinterpret_cast<int*>(scratch);
+    double* slabs = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+    CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
+    predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
+                                                      mean, var, want_var, slabs, counter);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: GRBCM aggregation (HBM-trivial elementwise + sum over the expert axis)        gr_bcm.py:116-149
+// ---------------------------------------------------------------------------------------------
+__global__ void grbcm_partial_kernel(const double* __restrict__ mean_l, const double* __restrict__ var_l,
+                                     const double* __restrict__ var_g, int nc_local, int first_global_index, int m,
+                                     double* __restrict__ S, double* __restrict__ beta_rows, double* __restrict__ prec_rows) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const double pg = 1.0 / var_g[c];              // gr_bcm.py:128
+    const double lpg = log(pg);
+    double sb = 0.0, sp = 0.0, sm = 0.0;
+    for (int i = 0; i < nc_local; ++i) {
+        const double p = 1.0 / var_l[(long long)i * m + c];             // gr_bcm.py:129
+        double beta = 0.5 * (log(p) - lpg);                              // gr_bcm.py:131
+        if (first_global_index + i == 0) beta = 1.0;                     // gr_bcm.py:132
+        const double pb = p * beta;                                      // gr_bcm.py:140
+        sb += beta;
+        sp += pb;
+        sm += mean_l[(long long)i * m + c] * pb;
+        if (beta_rows) beta_rows[(long long)i * m + c] = beta;
+        if (prec_rows) prec_rows[(long long)i * m + c] = p;
+    }
+    S[c] = sb;
+    S[m + c] = sp;
+    S[2 * (long long)m + c] = sm;
+}
+
+__global__ void grbcm_finalize_kernel(const double* __restrict__ S, const double* __restrict__ mean_g,
+                                      const double* __restrict__ var_g, int m, double* __restrict__ mu,
+                                      double* __restrict__ var, double* __restrict__ beta0, double* __restrict__ prec0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const double pg = 1.0 / var_g[c];
+    const double b0 = -(S[c] - 1.0);                                     // gr_bcm.py:133
+    const double pb0 = pg * b0;
+    const double v = 1.0 / (pb0 + S[m + c]);                             // gr_bcm.py:143
+    mu[c] = (mean_g[c] * pb0 + S[2 * (long long)m + c]) * v;             // gr_bcm.py:144
+    var[c] = v;
+    if (beta0) beta0[c] = b0;
+    if (prec0) prec0[c] = pg;
+}
+
+extern "C" int grbcm_partial(const double* mean_l, const double* var_l, const double* var_g, int nc_local,
+                             int first_global_index, int m, double* S, double* beta_rows, double* prec_rows, void* stream) {
+    ARG_CHECK(var_g && S && m > 0 && nc_local >= 0 && (nc_local == 0 || (mean_l && var_l)));
+    grbcm_partial_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_l, var_l, var_g, nc_local, first_global_index,
+                                                                            m, S, beta_rows, prec_rows);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+extern "C" int grbcm_finalize(const double* S, const double* mean_g, const double* var_g, int m, double* mu, double* var,
+                              double* beta0, double* prec0, void* stream) {
+    ARG_CHECK(S && mean_g && var_g && mu && var && m > 0);
+    grbcm_finalize_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, mean_g, var_g, m, mu, var, beta0, prec0);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6/K7: LML gradient (placeholder until the trtri / lauum kernels land)
+// ---------------------------------------------------------------------------------------------
+extern "C" long long gpr_lml_grad_scratch_bytes(int B, int npad, int d) { return 256; }
+extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                            const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                            double* grad, void* scratch, void* stream) {
+    return fail(GPR_ERR_UNSUPPORTED, "gpr_lml_grad not implemented yet%s", "");
+}

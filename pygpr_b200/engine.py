@@ -1,0 +1,247 @@
+"""Host-side driver of the CUDA hot path: thin Python over the C ABI (include/pygpr_b200.h).
+
+Everything here works on contiguous float64 CUDA tensors with an explicit leading expert
+dimension ``B``; the reference-shaped API (covar.py / gpr.py / loss.py / gr_bcm.py) sits on top.
+Torch is used for device memory and streams only; all arithmetic of the path runs in the
+library's sm_100a kernels.  No CPU fallback exists: a missing library or device raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import TILE
+
+F64 = torch.float64
+JITTER = 1e-7  # gpr.py:68, loss.py:38,63,96
+
+
+def device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("pygpr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dev(t: torch.Tensor) -> torch.Tensor:
+    """float64, contiguous, on the current CUDA device."""
+    return t.detach().to(device=device(), dtype=F64).contiguous()
+
+
+def round_up(n: int, mult: int) -> int:
+    return (n + mult - 1) // mult * mult
+
+
+def scale_inputs(x: torch.Tensor, hp: torch.Tensor, B: int, npad: Optional[int] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """a = x*ls zero-padded to [B, npad, dpad]; nrm = |a|^2 [B, npad]   (covar.py:137-140, 106).
+
+    x: [B, n, d] or [n, d] / [1, n, d] (shared by all experts); hp: [B, P] with ls = hp[:, 1:1+d].
+    """
+    x = x.reshape(-1, x.shape[-2], x.shape[-1])
+    n, d = x.shape[-2], x.shape[-1]
+    assert x.shape[0] in (1, B)
+    npad = round_up(n, TILE) if npad is None else npad
+    dpad = round_up(d, 4)
+    a = torch.empty(B, npad, dpad, dtype=F64, device=x.device)
+    nrm = torch.empty(B, npad, dtype=F64, device=x.device)
+    x_bstride = 0 if x.shape[0] == 1 else n * d
+    hp_stride = 0 if hp.shape[0] == 1 else hp.shape[-1]
+    _lib.call("gpr_se_scale", _p(x), x_bstride, _p(hp), hp_stride, B, n, d, npad, dpad, _p(a), _p(nrm), _stream())
+    return a, nrm
+
+
+def se_kernel_matrix(hp: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Dense K_se [B, n, n] (no noise, no jitter) — Squared_exponential.kernel, covar.py:129-150."""
+    B, n = x.shape[0], x.shape[1]
+    a, nrm = scale_inputs(x, hp, B)
+    K = torch.empty(B, n, n, dtype=F64, device=x.device)
+    _lib.call("gpr_se_build", _p(a), _p(nrm), _p(hp), hp.shape[-1], None, B, n, a.shape[1], a.shape[2],
+              _p(K), n, 0, 0, _stream())
+    return K
+
+
+def se_cross_matrix(hp: torch.Tensor, x: torch.Tensor, xp: torch.Tensor) -> torch.Tensor:
+    """Dense K* [B, m, n] — cross branch of Squared_exponential.kernel, covar.py:151-160.
+
+    Exactly one of x / xp may carry fewer batch entries than hp (broadcast), as in the reference.
+    """
+    B = hp.shape[0]
+    n, m = x.shape[-2], xp.shape[-2]
+    a, nrm = scale_inputs(x, hp, B)
+    as_, nrms = scale_inputs(xp, hp, B)
+    Ks = torch.empty(B, m, n, dtype=F64, device=hp.device)
+    _lib.call("gpr_se_cross", _p(as_), _p(nrms), as_.shape[1], _p(a), _p(nrm), a.shape[1], _p(hp), hp.shape[-1],
+              B, m, n, a.shape[2], _p(Ks), _stream())
+    return Ks
+
+
+def se_kernel_grad(hp: torch.Tensor, x: torch.Tensor, Kse: torch.Tensor) -> torch.Tensor:
+    """dK [B, d+1, n, n] for Squared_exponential.kernel_and_grad (covar.py:184-199); API parity only."""
+    B, n, d = x.shape
+    dK = torch.empty(B, d + 1, n, n, dtype=F64, device=x.device)
+    _lib.call("gpr_se_kernel_grad", _p(Kse), _p(x), _p(hp), hp.shape[-1], B, n, d, _p(dK), _stream())
+    return dK
+
+
+@dataclass
+class FitState:
+    """Device-resident result of a batched fit (the reference's krnchd / wt, gpr.py:57-59, plus extras)."""
+    B: int
+    n: int
+    npad: int
+    d: int
+    dpad: int
+    has_noise: bool
+    hp: torch.Tensor          # [B, P]
+    a: torch.Tensor           # [B, npad, dpad] scaled inputs
+    nrm: torch.Tensor         # [B, npad]
+    L: torch.Tensor           # [B, npad, npad] lower factor (blocks above the block diagonal undefined)
+    invdiag: torch.Tensor     # [B, npad/128, 128, 128]
+    z: torch.Tensor           # [B, npad]  L^-1 y
+    alpha: Optional[torch.Tensor]  # [B, npad]  K^-1 y
+    logdet_half: torch.Tensor  # [B]
+    zz: torch.Tensor          # [B]
+    info: torch.Tensor        # [B] int32
+    prior: torch.Tensor       # [B] sig^2 + sig_n^2
+
+    def nlml(self) -> torch.Tensor:
+        """NLML = 1/2 y^T alpha + sum log L_ii + n/2 log 2 pi   (loss.py:49-51); y^T alpha = z.z"""
+        return 0.5 * self.zz + self.logdet_half + 0.5 * self.n * math.log(2.0 * math.pi)
+
+    def check(self) -> None:
+        """Mirror tc.cholesky's RuntimeError on a non-PD matrix (gpr.py:69)."""
+        bad = torch.nonzero(self.info)
+        if bad.numel():
+            b = int(bad[0, 0])
+            raise torch.linalg.LinAlgError(
+                "cholesky: expert %d: the leading minor of order %d is not positive-definite" % (b, int(self.info[b])))
+
+
+def split_hp(hp: torch.Tensor, d: int, has_noise: bool, jitter: float = JITTER):
+    """diag_add = sig_n^2 + jitter (covar.py:238 + gpr.py:68), prior = sig^2 + sig_n^2 (gpr.py:98)."""
+    sig2 = hp[:, 0] * hp[:, 0]
+    if has_noise:
+        sn2 = hp[:, d + 1] * hp[:, d + 1]
+        return (sn2 + jitter).contiguous(), (sig2 + sn2).contiguous()
+    return torch.full_like(sig2, jitter), sig2.contiguous()
+
+
+def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, want_alpha: bool = True,
+        jitter: float = JITTER, L_out: Optional[torch.Tensor] = None) -> FitState:
+    """Batched Exact_GP.update (gpr.py:65-74) for cov = Compose([SE, WN]) or SE alone.
+
+    K is never materialised: tiles are generated inside the factorisation (gen=1).
+    x:[B,n,d], y:[B,n], hp:[B,P] — CUDA float64 contiguous.
+    """
+    B, n, d = x.shape
+    assert hp.shape == (B, d + 1 + int(has_noise)), (hp.shape, B, d, has_noise)
+    npad = round_up(n, TILE)
+    nt = npad // TILE
+    dev = x.device
+    a, nrm = scale_inputs(x, hp, B, npad)
+    dpad = a.shape[2]
+    diag_add, prior = split_hp(hp, d, has_noise, jitter)
+    L = torch.empty(B, npad, npad, dtype=F64, device=dev) if L_out is None else L_out
+    invdiag = torch.empty(B, nt, TILE, TILE, dtype=F64, device=dev)
+    ypad = torch.zeros(B, npad, dtype=F64, device=dev)
+    ypad[:, :n] = y
+    z = torch.empty(B, npad, dtype=F64, device=dev)
+    logdet_half = torch.empty(B, dtype=F64, device=dev)
+    zz = torch.empty(B, dtype=F64, device=dev)
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
+              _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _stream())
+    alpha = None
+    if want_alpha:
+        alpha = torch.empty(B, npad, dtype=F64, device=dev)
+        _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _stream())
+    return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior)
+
+
+def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
+    """In-place batched Cholesky of a padded [B, npad, npad] buffer holding the lower triangle of K
+    (identity on the padding).  Returns (invdiag, z, logdet_half, zz, info).  tc.cholesky, gpr.py:69."""
+    B, npad, _ = K.shape
+    nt = npad // TILE
+    dev = K.device
+    invdiag = torch.empty(B, nt, TILE, TILE, dtype=F64, device=dev)
+    logdet_half = torch.empty(B, dtype=F64, device=dev)
+    info = torch.empty(B, dtype=torch.int32, device=dev)
+    z = zz = None
+    if y is not None:
+        z = torch.empty(B, npad, dtype=F64, device=dev)
+        zz = torch.empty(B, dtype=F64, device=dev)
+    _lib.call("gpr_potrf_batched", _p(K), 0, None, None, None, 0, None, B, npad, npad, 0,
+              _p(invdiag), _p(y), _p(z), _p(logdet_half), _p(zz), _p(info), _stream())
+    return invdiag, z, logdet_half, zz, info
+
+
+_scratch_cache = {}
+
+
+def _scratch(nbytes: int, dev: torch.device) -> torch.Tensor:
+    key = (dev.index, "predict")
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _scratch_cache[key] = buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return buf
+
+
+def predict(st: FitState, xs: torch.Tensor, want_var: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """mean [B, m] and variance [B, m] of every expert at xs [m, d]  (gpr.py:76-106)."""
+    assert st.alpha is not None
+    m = xs.shape[0]
+    dev = xs.device
+    mean = torch.empty(st.B, m, dtype=F64, device=dev)
+    var = torch.empty(st.B, m, dtype=F64, device=dev) if want_var else None
+    scratch = _scratch(int(_lib.load().gpr_predict_scratch_bytes(st.npad)), dev)
+    _lib.call("gpr_predict", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
+              _p(st.prior), _p(xs), st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), int(want_var),
+              _p(scratch), _stream())
+    return mean, var
+
+
+def lml_grad(st: FitState) -> torch.Tensor:
+    """d NLML / d hp [B, P] from a finished fit (destroys the strict block-upper part of st.L)   loss.py:59-128."""
+    assert st.alpha is not None
+    P = st.d + 1 + int(st.has_noise)
+    grad = torch.empty(st.B, P, dtype=F64, device=st.L.device)
+    nbytes = int(_lib.load().gpr_lml_grad_scratch_bytes(st.B, st.npad, st.d))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=st.L.device)
+    _lib.call("gpr_lml_grad", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
+              int(st.has_noise), st.B, st.n, st.npad, st.d, st.dpad, _p(grad), _p(scratch), _stream())
+    return grad
+
+
+def grbcm_partial(mean_l: torch.Tensor, var_l: torch.Tensor, var_g: torch.Tensor, first_global_index: int,
+                  want_rows: bool = False):
+    """Per-rank partial sums S [3, m] over the local experts (gr_bcm.py:128-144, split for sharding)."""
+    nc_local, m = mean_l.shape
+    S = torch.empty(3, m, dtype=F64, device=var_g.device)
+    beta_rows = torch.empty(nc_local, m, dtype=F64, device=var_g.device) if want_rows else None
+    prec_rows = torch.empty(nc_local, m, dtype=F64, device=var_g.device) if want_rows else None
+    _lib.call("grbcm_partial", _p(mean_l), _p(var_l), _p(var_g), nc_local, first_global_index, m, _p(S),
+              _p(beta_rows), _p(prec_rows), _stream())
+    return S, beta_rows, prec_rows
+
+
+def grbcm_finalize(S: torch.Tensor, mean_g: torch.Tensor, var_g: torch.Tensor, want_rows: bool = False):
+    m = mean_g.shape[0]
+    mu = torch.empty(m, dtype=F64, device=S.device)
+    var = torch.empty(m, dtype=F64, device=S.device)
+    beta0 = torch.empty(m, dtype=F64, device=S.device) if want_rows else None
+    prec0 = torch.empty(m, dtype=F64, device=S.device) if want_rows else None
+    _lib.call("grbcm_finalize", _p(S), _p(mean_g), _p(var_g), m, _p(mu), _p(var), _p(beta0), _p(prec0), _stream())
+    return mu, var, beta0, prec0

@@ -1,0 +1,118 @@
+"""GPU parity of the C-ABI kernels (through pygpr_b200.engine) against the CPU oracle on seeded inputs."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+SPEC = ["se", "wn"]
+TOL = 1e-8  # north_star: relative 1e-8 on mean / variance / LML in FP64 (well-conditioned inputs)
+
+
+def _data(seed, B, n, d, m, sig_n=0.3, per_expert=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, n, d, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(B, n, generator=g, dtype=torch.float64)
+    xs = torch.rand(m, d, generator=g, dtype=torch.float64)
+    hp = torch.empty(B, d + 2, dtype=torch.float64)
+    hp[:, 0] = 1.0
+    hp[:, 1:d + 1] = 2.0 / math.sqrt(d)
+    hp[:, d + 1] = sig_n
+    if per_expert:
+        hp = hp * (0.5 + torch.rand(B, d + 2, generator=g, dtype=torch.float64))
+    return x, y, xs, hp
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pygpr_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import pygpr_oracle
+    return pygpr_oracle
+
+
+@pytest.mark.parametrize("B,n,d,m", [(1, 37, 3, 11), (4, 130, 5, 29), (2, 256, 16, 300), (3, 300, 7, 129)])
+def test_se_kernels(eng, orc, B, n, d, m):
+    x, y, xs, hp = _data(1, B, n, d, m, per_expert=True)
+    hp_se = hp[:, :d + 1].contiguous()
+    K = eng.se_kernel_matrix(hp_se.cuda(), x.cuda()).cpu()
+    assert_close(K.numpy(), orc.se_kernel(hp_se, x).numpy(), 1e-13, "K_se")
+    Ks = eng.se_cross_matrix(hp_se.cuda(), x.cuda(), xs.cuda()).cpu()
+    assert_close(Ks.numpy(), orc.se_kernel(hp_se, x, xs).numpy(), 1e-13, "K*_se")
+    dK = eng.se_kernel_grad(hp_se.cuda(), x.cuda(), K.cuda()).cpu()
+    assert_close(dK.numpy(), orc.se_kernel_and_grad(hp_se, x)[1].numpy(), 1e-13, "dK_se")
+
+
+@pytest.mark.parametrize("B,n,d,m,per", [(1, 37, 3, 11, False), (1, 128, 2, 128, False), (4, 130, 5, 29, True),
+                                         (2, 256, 16, 300, False), (3, 300, 7, 129, True), (2, 1000, 1, 200, False),
+                                         (1, 1500, 8, 64, False)])
+def test_fit_predict(eng, orc, B, n, d, m, per):
+    x, y, xs, hp = _data(2, B, n, d, m, per_expert=per)
+    st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True)
+    torch.cuda.synchronize()
+    assert int(st.info.abs().sum()) == 0
+    L_ref, alpha_ref = orc.gp_fit(SPEC, hp, x, y)
+    L = torch.tril(st.L[:, :n, :n]).cpu()
+    assert_close(L.numpy(), L_ref.numpy(), 1e-10, "L")
+    assert_close(st.alpha[:, :n].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha")
+    assert float(st.alpha[:, n:].abs().max()) == 0.0 if st.npad > n else True
+    assert_close(st.nlml().cpu().numpy(), orc.mle_loss(SPEC, hp, x, y).numpy(), TOL, "nlml")
+    mean_ref, var_ref = orc.gp_predict(SPEC, hp, x, y, xs, "diag", fit=(L_ref, alpha_ref))
+    mean, var = eng.predict(st, xs.cuda(), True)
+    assert_close(mean.cpu().numpy(), mean_ref.numpy(), TOL, "mean")
+    assert_close(var.cpu().numpy(), var_ref.numpy(), TOL, "var")
+    mean2, none = eng.predict(st, xs.cuda(), False)
+    assert none is None
+    assert_close(mean2.cpu().numpy(), mean_ref.numpy(), TOL, "mean (no var)")
+
+
+def test_potrf_inplace_and_info(eng, orc):
+    x, y, xs, hp = _data(3, 2, 200, 4, 8)
+    K = orc.compose_kernel(SPEC, hp, x)
+    K.diagonal(dim1=-2, dim2=-1).add_(1e-7)
+    npad = 256
+    Kp = torch.eye(npad, dtype=torch.float64).repeat(2, 1, 1)
+    Kp[:, :200, :200] = K
+    Kd = Kp.cuda()
+    invdiag, z, ldh, zz, info = eng.potrf_inplace(Kd)
+    assert int(info.abs().sum()) == 0
+    assert_close(torch.tril(Kd[:, :200, :200]).cpu().numpy(), torch.linalg.cholesky(K).numpy(), 1e-10, "L in place")
+    assert_close(ldh.cpu().numpy(), torch.linalg.cholesky(K).diagonal(dim1=-2, dim2=-1).log().sum(-1).numpy(), 1e-10, "logdet")
+    # a non positive-definite matrix is reported LAPACK-style in info (first bad leading minor), not as a crash
+    Kbad = Kp.clone()
+    Kbad[1, 150, 150] = -1.0
+    Kb = Kbad.cuda()
+    _, _, _, _, info = eng.potrf_inplace(Kb)
+    info = info.cpu()
+    assert int(info[0]) == 0 and int(info[1]) == 151
+
+
+def test_grbcm_aggregate(eng, orc):
+    g = torch.Generator().manual_seed(5)
+    nc, m = 9, 333
+    mean_l = torch.randn(nc, m, generator=g, dtype=torch.float64)
+    var_l = 0.05 + torch.rand(nc, m, generator=g, dtype=torch.float64)
+    mean_g = torch.randn(m, generator=g, dtype=torch.float64)
+    var_g = 0.5 + torch.rand(m, generator=g, dtype=torch.float64)
+    mu_ref, var_ref, beta_ref, prec_ref = orc.grbcm_aggregate(mean_g, var_g, mean_l, var_l)
+    # single shard
+    S, br, pr = eng.grbcm_partial(mean_l.cuda(), var_l.cuda(), var_g.cuda(), 0, want_rows=True)
+    mu, var, b0, p0 = eng.grbcm_finalize(S, mean_g.cuda(), var_g.cuda(), want_rows=True)
+    assert_close(mu.cpu().numpy(), mu_ref.numpy(), 1e-12, "mu_A")
+    assert_close(var.cpu().numpy(), var_ref.numpy(), 1e-12, "var_A")
+    assert_close(torch.cat((b0[None], br)).cpu().numpy(), beta_ref.numpy(), 1e-12, "beta")
+    assert_close(torch.cat((p0[None], pr)).cpu().numpy(), prec_ref.numpy(), 1e-12, "prec")
+    # two shards summed = the all-reduce of SURVEY §8(e)
+    S1, _, _ = eng.grbcm_partial(mean_l[:4].cuda(), var_l[:4].cuda(), var_g.cuda(), 0)
+    S2, _, _ = eng.grbcm_partial(mean_l[4:].cuda(), var_l[4:].cuda(), var_g.cuda(), 4)
+    mu2, var2, _, _ = eng.grbcm_finalize(S1 + S2, mean_g.cuda(), var_g.cuda())
+    assert_close(mu2.cpu().numpy(), mu_ref.numpy(), 1e-12, "mu_A sharded")
+    assert_close(var2.cpu().numpy(), var_ref.numpy(), 1e-12, "var_A sharded")
