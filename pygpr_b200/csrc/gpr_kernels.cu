@@ -751,11 +751,222 @@ extern "C" int grbcm_finalize(const double* S, const double* mean_g, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6/K7: LML gradient (placeholder until the trtri / lauum kernels land)
+// K6/K7: gradient of the negative log marginal likelihood without forming dK      loss.py:59-128
+//   (1) transpose_invdiag_kernel : U_jj = inv(L_jj)^T
+//   (2) trtri_kernel   : U = L^-T, one persistent task per (expert, block row j); forward substitution on the
+//                        identity, i.e.  U[j,i] = -(sum_{k=j}^{i-1} U[j,k] L[i,k]^T) inv(L_ii)^T,  written into the
+//                        strict block-upper part of L's buffer (row tile j is private to its task)
+//   (3) lauum_grad_kernel : K^-1[i,j] = sum_{k>=i} U[i,k] U[j,k]^T (lower tiles only), never stored: the epilogue
+//                        forms M = (K^-1 - alpha alpha^T) o K_se with K_se generated on chip and reduces
+//                        sum M, sum M (a_ik - a_jk)^2 per input dimension, and tr(W) into per-tile partials
+//   (4) grad_finalize_kernel : fixed-order (deterministic) sum of the partials and the 1/sig, -1/ls_k, sig_n factors
 // ---------------------------------------------------------------------------------------------
-extern "C" long long gpr_lml_grad_scratch_bytes(int B, int npad, int d) { return 256; }
+__global__ void transpose_invdiag_kernel(const double* __restrict__ invdiag, double* __restrict__ invdiagT) {
+    __shared__ double t[32][33];
+    const long long base = (long long)blockIdx.z * TILE * TILE;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = invdiag[base + (long long)(by + r) * TILE + bx + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) invdiagT[base + (long long)(bx + r) * TILE + by + threadIdx.x] = t[threadIdx.x][r];
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ invdiagT, int B, int npad,
+             int* __restrict__ counter) {
+    extern __shared__ double smem[];
+    __shared__ int s_task;
+    const int nt = npad / TILE;
+    const int ntasks = B * (nt - 1);
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_task = atomicAdd(counter, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= ntasks) break;
+        const int b = task / (nt - 1), j = task % (nt - 1);  // j ascending = longest rows first within an expert
+        double* Lb = L + (long long)b * npad * npad;
+        const double* Ujj = invdiagT + ((long long)b * nt + j) * TILE * TILE;
+        double* Urow = Lb + ((long long)j * TILE) * npad;      // row tile j of U lives in the block-upper part
+        for (int i = j + 1; i < nt; ++i) {
+            double acc[4][8][2];
+            zero_acc(acc);
+            __syncthreads();
+            const double* Li = Lb + ((long long)i * TILE) * npad;
+            Seg s0{Ujj, TILE, Li + (long long)j * TILE, npad, TILE / KC};
+            Seg s1{Urow + (long long)(j + 1) * TILE, npad, Li + (long long)(j + 1) * TILE, npad, (i - j - 1) * (TILE / KC)};
+            mainloop<false>(acc, s0, s1, smem, nh);
+            double* Uji = Urow + (long long)i * TILE;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+                    *reinterpret_cast<double2*>(Uji + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                        make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+            __threadfence_block();
+            __syncthreads();
+            zero_acc(acc);
+            Seg s2{Uji, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
+            mainloop<false>(acc, s2, none, smem, nh);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+                    *reinterpret_cast<double2*>(Uji + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            __threadfence_block();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdiagT, const double* __restrict__ a,
+                  const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
+                  int n, int npad, int d, int dpad, double* __restrict__ partials, int P) {
+    extern __shared__ double smem[];
+    __shared__ double sAi[TILE], sAj[TILE];
+    __shared__ double wred[NTHREADS / 32][36];
+    const int nt = npad / TILE;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // tile index -> (i, j), i >= j, ordered by i (long k-ranges first)
+    int ti = blockIdx.x, i = 0;
+    while (ti >= i + 1) { ti -= i + 1; ++i; }
+    const int j = ti;
+    const double* Lb = L + (long long)b * npad * npad;
+    const double* Uii = invdiagT + ((long long)b * nt + i) * TILE * TILE;
+    const double* Ui = Lb + ((long long)i * TILE) * npad;
+    const double* Uj = Lb + ((long long)j * TILE) * npad;
+
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, TILE / KC};
+    Seg s1{Ui + (long long)(i + 1) * TILE, npad, Uj + (long long)(i + 1) * TILE, npad, (nt - 1 - i) * (TILE / KC)};
+    mainloop<false>(acc, s0, s1, smem, nh);
+
+    // epilogue: M = (K^-1 - alpha_i alpha_j^T) o K_se  -> smem tile
+    double* Ms = smem;
+    FeatSmem f = carve_feat(smem + TILE * XLD, dpad);
+    load_feat_tile(f.sR, f.sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+    load_feat_tile(f.sC, f.sld, a + ((long long)b * npad + j * TILE) * dpad, dpad);
+    cp_async_commit();
+    if (tid < TILE) {
+        f.nR[tid] = nrm[(long long)b * npad + i * TILE + tid];
+        f.nC[tid] = nrm[(long long)b * npad + j * TILE + tid];
+        sAi[tid] = alpha[(long long)b * npad + i * TILE + tid];
+        sAj[tid] = alpha[(long long)b * npad + j * TILE + tid];
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const double* hb = hp + (long long)b * hp_stride;
+    double trw = 0.0;
+    gen_se_tile(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, hb[0] * hb[0], [&](int mi, int ni, int e, double kv) {
+        const int r = acc_row(mi), c = acc_col(ni, e);
+        const bool live = (i * TILE + r < n) && (j * TILE + c < n);
+        const double w = acc[mi][ni][e] - sAi[r] * sAj[c];
+        Ms[r * XLD + c] = live ? w * kv : 0.0;
+        if (i == j && r == c && live) trw += w;
+    });
+    __syncthreads();
+    // reduction: thread -> column c, 64 rows;  q[0] = sum M, q[1+k] = sum M (a_rk - a_ck)^2
+    const int c = tid & 127, rh = tid >> 7;
+    const double wgt = (i == j) ? 1.0 : 2.0;
+    double q0 = 0.0;
+    for (int k0 = 0; k0 < d; k0 += 16) {
+        double ac[16], q[16];
+        const int kn = (d - k0 < 16) ? d - k0 : 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { ac[k] = (k < kn) ? f.sC[c * f.sld + k0 + k] : 0.0; q[k] = 0.0; }
+        for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+            const double mv = Ms[r * XLD + c];
+            if (k0 == 0) q0 += mv;
+            const double* ar = f.sR + r * f.sld + k0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < kn) { const double df = ar[k] - ac[k]; q[k] += mv * df * df; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const double v = warp_sum(q[k]);
+            if (lane == 0) wred[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < kn) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NTHREADS / 32; ++w) s += wred[w][tid];
+            partials[((long long)b * gridDim.x + blockIdx.x) * P + 1 + k0 + tid] = s * wgt;
+        }
+        __syncthreads();
+    }
+    {
+        const double v0 = warp_sum(q0), v1 = warp_sum(trw);
+        if (lane == 0) { wred[warp][0] = v0; wred[warp][1] = v1; }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int w = 0; w < NTHREADS / 32; ++w) { s0 += wred[w][0]; s1 += wred[w][1]; }
+            double* pt = partials + ((long long)b * gridDim.x + blockIdx.x) * P;
+            pt[0] = s0 * wgt;
+            if (P > d + 1) pt[d + 1] = s1;
+        }
+    }
+}
+
+__global__ void grad_finalize_kernel(const double* __restrict__ partials, int ntiles, int P, const double* __restrict__ hp,
+                                     int hp_stride, int d, double* __restrict__ grad) {
+    const int b = blockIdx.x, p = threadIdx.x;
+    if (p >= P) return;
+    double s = 0.0;
+    for (int t = 0; t < ntiles; ++t) s += partials[((long long)b * ntiles + t) * P + p];
+    const double* hb = hp + (long long)b * hp_stride;
+    double g;
+    if (p == 0) g = s / hb[0];                                  // (1/sig) sum M
+    else if (p <= d) g = (hb[p] != 0.0) ? -s / hb[p] : 0.0;     // -ls_k sum M dx^2 = -(1/ls_k) sum M da^2
+    else g = hb[p] * s;                                         // sig_n tr(W)
+    grad[(long long)b * P + p] = g;
+}
+
+static inline long long lml_feat_bytes(int dpad) { return (long long)TILE * XLD * 8 + feat_smem_bytes(dpad); }
+
+extern "C" long long gpr_lml_grad_scratch_bytes(int B, int npad, int d) {
+    const long long nt = npad / TILE;
+    const long long ntiles = nt * (nt + 1) / 2;
+    return 256 + (long long)B * nt * TILE * TILE * 8 + (long long)B * ntiles * (d + 2) * 8;
+}
+
 extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
                             const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
                             double* grad, void* scratch, void* stream) {
-    return fail(GPR_ERR_UNSUPPORTED, "gpr_lml_grad not implemented yet%s", "");
+    ARG_CHECK(L && invdiag && a && nrm && alpha && hp && grad && scratch);
+    ARG_CHECK(B > 0 && n > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
+    const long long smem_l = lml_feat_bytes(dpad);
+    if (smem_l > 227 * 1024 || d + 2 > NTHREADS)
+        return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused gradient%s (dpad=%lld)", "", dpad);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    const int ntiles = nt * (nt + 1) / 2;
+    const int P = d + 1 + (has_noise ? 1 : 0);
+    int* counter = reinterpret_cast<int*>(scratch);
+    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+    double* partials = invdiagT + (long long)B * nt * TILE * TILE;
+    CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
+    transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
+    if (nt > 1) {
+        CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
+        int sms = gpr_device_sm_count();
+        if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+        const long long ntasks = (long long)B * (nt - 1);
+        const int grid = (int)(ntasks < sms ? ntasks : sms);
+        trtri_kernel<<<grid, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, counter);
+    }
+    const int smem = (int)(smem_l > MAIN_SMEM_BYTES ? smem_l : MAIN_SMEM_BYTES);
+    CUDA_TRY(opt_in_smem(lauum_grad_kernel, smem));
+    lauum_grad_kernel<<<dim3(ntiles, B), NTHREADS, smem, st>>>(L, invdiagT, a, nrm, alpha, hp, hp_stride, n, npad, d, dpad,
+                                                               partials, P);
+    grad_finalize_kernel<<<B, ((P + 31) / 32) * 32, 0, st>>>(partials, ntiles, P, hp, hp_stride, d, grad);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
 }

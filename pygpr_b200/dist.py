@@ -1,0 +1,50 @@
+"""Expert sharding across GPUs: one process per GPU, torch.distributed (NCCL over NVLink) as plumbing.
+
+GRBCM experts are independent until the precision-weighted sums over the expert axis
+(gr_bcm.py:133,143-144), so the local experts are split into contiguous blocks, one per rank, and the only
+data-path collective is an all-reduce(sum, float64) of the [3, m] partial sums per prediction batch (and of
+[1+P] NLML/gradient scalars when hyper-parameters are shared).  The communication expert is replicated.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def world(group=None) -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if not is_dist():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def shard_bounds(nc: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of the nc local experts owned by `rank` (ceil(nc/G) per rank)."""
+    per = -(-nc // world_size)
+    lo = min(rank * per, nc)
+    return lo, min(lo + per, nc)
+
+
+def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum over ranks (no-op for a single process)."""
+    if is_dist() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_gather_rows(t: torch.Tensor, counts, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks [n_r, m] (n_r = counts[r]) in rank order."""
+    if not (is_dist() and dist.get_world_size(group) > 1):
+        return t
+    mx = max(counts)
+    pad = torch.zeros(mx, *t.shape[1:], dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in counts]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:c] for o, c in zip(outs, counts)], dim=0)

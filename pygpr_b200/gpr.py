@@ -1,0 +1,162 @@
+"""GPR models with the reference's API (PyGPR/gpr.py), running on the sm_100a library."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import engine
+from .covar import Covar, fused_spec, _back
+
+
+class GPR:
+    """Base class for Gaussian process regression models (gpr.py:13-43)."""
+
+    def __init__(self, x: Tensor, y: Tensor, cov: Covar) -> None:
+        self.x: Tensor = x
+        self.y: Tensor = y
+        self.cov = cov
+        self.params: Tensor = NotImplemented
+        self.need_upd: bool = True
+
+    def set_params(self, params: Tensor) -> None:
+        self.params = torch.clone(params)                    # gpr.py:28-31
+        self.need_upd = True
+
+    def update(self) -> None:
+        raise NotImplementedError
+
+    def predict(self, xp: Tensor, var: str) -> Sequence[Tensor]:
+        raise NotImplementedError
+
+    def predict_var(self, xp: Tensor, **kwargs: Tensor) -> Tensor:
+        raise NotImplementedError
+
+    def predict_covar(self, xp: Tensor, **kwargs: Tensor) -> Tensor:
+        raise NotImplementedError
+
+
+def _unsupported(cov):
+    return NotImplementedError(
+        "pygpr_b200: the fused GPU path supports Squared_exponential or Compose([Squared_exponential(), "
+        "White_noise()]); got %r. Kernel-level calls (kernel / kernel_and_grad) work for any composition." % (cov,))
+
+
+class Exact_GP(GPR):
+    """Exact GP (gpr.py:46-120).  ``x:[n,d]`` or ``[nc,n,d]`` (one expert per batch entry), ``y`` alike.
+
+    ``update()`` factorises on the GPU (K is generated tile by tile inside the Cholesky, never stored);
+    ``krnchd`` (lower factor), ``wt`` (= K^-1 y) and ``krn`` keep the reference's names and shapes and are
+    materialised lazily on the device of ``x``.
+    """
+
+    def __init__(self, x: Tensor, y: Tensor, cov: Covar) -> None:
+        super().__init__(x, y, cov)
+        self.params: Tensor = cov.init_params(x)
+        self._state: Optional[engine.FitState] = None
+        self._krn = NotImplemented
+        self._wt = NotImplemented
+        self._krnchd = NotImplemented
+        self.need_upd = True
+
+    # -- reference attributes (gpr.py:57-59), filled lazily from the device state -------------------
+    @property
+    def batched(self) -> bool:
+        return self.x.dim() > 2
+
+    def _shape_out(self, t: Tensor) -> Tensor:
+        return _back(t if self.batched else t.squeeze(0), self.x)
+
+    @property
+    def krnchd(self):
+        if self._krnchd is NotImplemented and self._state is not None and not self.need_upd:
+            n = self._state.n
+            self._krnchd = self._shape_out(torch.tril(self._state.L[:, :n, :n]))
+        return self._krnchd
+
+    @krnchd.setter
+    def krnchd(self, v):
+        self._krnchd = v
+
+    @property
+    def wt(self):
+        if self._wt is NotImplemented and self._state is not None and not self.need_upd:
+            self._wt = self._shape_out(self._state.alpha[:, :self._state.n])
+        return self._wt
+
+    @wt.setter
+    def wt(self, v):
+        self._wt = v
+
+    @property
+    def krn(self):
+        if self._krn is NotImplemented and self._state is not None and not self.need_upd:
+            k = self.cov.kernel(self.params, self.x).clone()
+            k.diagonal(dim1=-2, dim2=-1).add_(engine.JITTER)  # gpr.py:68
+            self._krn = k
+        return self._krn
+
+    @krn.setter
+    def krn(self, v):
+        self._krn = v
+
+    # -----------------------------------------------------------------------------------------------
+    def _device_inputs(self):
+        x = engine._dev(self.x)
+        x = x.reshape(-1, x.shape[-2], x.shape[-1])
+        y = engine._dev(self.y).reshape(-1, self.y.shape[-1])
+        hp = engine._dev(self.params).reshape(-1, self.params.shape[-1])
+        B = max(x.shape[0], hp.shape[0])
+        if hp.shape[0] != B:
+            hp = hp.expand(B, -1).contiguous()
+        if x.shape[0] != B:
+            x = x.expand(B, -1, -1).contiguous()
+            y = y.expand(B, -1).contiguous()
+        return x, y, hp
+
+    def update(self) -> None:
+        if self.need_upd:
+            spec = fused_spec(self.cov)
+            if spec is None:
+                raise _unsupported(self.cov)
+            x, y, hp = self._device_inputs()
+            assert hp.shape[-1] == self.cov.get_params_shape(self.x)[-1]
+            self._state = engine.fit(x, y, hp, spec[0])      # gpr.py:67-72
+            self._state.check()
+            self._krn = self._wt = self._krnchd = NotImplemented
+            self.need_upd = False
+        return None
+
+    def predict(self, xp: Tensor, var: str = "full") -> Sequence[Tensor]:
+        self.update()
+        xs = engine._dev(xp).reshape(-1, xp.shape[-1])
+        if var == "full":
+            mean, covars = self._predict_full(xs)
+            covars = _back(covars.squeeze(0) if not self.batched else covars, xp)
+        elif var == "diag":
+            mean, v = engine.predict(self._state, xs, True)  # gpr.py:79-90
+            covars = self._shape_out(v)
+        else:
+            mean, _ = engine.predict(self._state, xs, False)
+            covars = NotImplemented                          # gpr.py:91-92
+        ys = _back(mean.squeeze(), self.x)                   # gpr.py:85: squeeze_() drops every size-1 axis
+        return [ys, covars]
+
+    def predict_var(self, xp: Tensor, **kwargs: Tensor) -> Tensor:
+        """Predictive variance at xp (gpr.py:96-106).  ``krns`` is accepted for signature parity and ignored:
+        the cross-covariance tiles are regenerated on chip."""
+        self.update()
+        xs = engine._dev(xp).reshape(-1, xp.shape[-1])
+        _, v = engine.predict(self._state, xs, True)
+        return self._shape_out(v)
+
+    def predict_covar(self, xp: Tensor, **kwargs: Tensor) -> Tensor:
+        """Full predictive covariance (gpr.py:108-120)."""
+        self.update()
+        xs = engine._dev(xp).reshape(-1, xp.shape[-1])
+        _, c = self._predict_full(xs)
+        return _back(c.squeeze(0) if not self.batched else c, xp)
+
+    def _predict_full(self, xs: Tensor):
+        return engine.predict_full(self._state, xs, self.cov)
