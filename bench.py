@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the PyGPR hot path on B200: GRBCM predictions/sec at n=1M, d=16 (BASELINE.json config 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--m M] [--small]
+
+Workload (reading A): 256 subsets x 4096 points of a 16-d synthetic regression problem; one subset
+is the communication set, so there are 255 local experts of order 8192 plus one communication expert of order
+4096.  A *step* is one GRBCM.predict of a batch of M test points with the factorisations resident (exactly what
+the reference's need_upd flag gives on every predict after the first).  The fit (batched Cholesky) and one
+LML-gradient evaluation are timed once before the steps and reported in the same JSON line as FP64 TFLOP/s.
+
+  value : whole-job predictions/sec, inputs resident in HBM, CUDA events, max over ranks
+  e2e   : the same through the public API (pygpr_b200.GRBCM.predict) with HOST tensors in and out
+          (pinned test points H2D + mean/variance D2H inside the timed region)
+  roofline : the dominant kernel (predict_kernel) against the FP64 GEMM peak measured in this run with cuBLAS
+  cpu_baseline : the CPU oracle (torch-CPU restatement of the reference) on a bounded sample, host cores stated
+
+With N>1 (torchrun, one rank per GPU) the 255 local experts are split into contiguous blocks and the only
+collective is the all-reduce of the [3, M] partial sums (strong scaling: the total work is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GRBCM predictions/sec at n=1M,d=16"
+UNIT = "predictions/s"
+
+
+def workload(small: bool):
+    if small:  # smoke-sized variant for quick checks (not the headline)
+        return dict(name="grbcm_small_64x1024_d8(A)", M_sub=16, m0=1024, d=8)
+    return dict(name="grbcm_n1M_d16_256x4096(A): xg[4096,16], xl[255,4096,16], 255 local experts of order 8192 + comm expert",
+                M_sub=256, m0=4096, d=16)
+
+
+def make_data(w, seed=0):
+    """x ~ U[0,1]^d, y = sin(sum x) + 0.1 N(0,1); subset 0 is the communication set."""
+    g = torch.Generator().manual_seed(seed)
+    M_sub, m0, d = w["M_sub"], w["m0"], w["d"]
+    x = torch.rand(M_sub, m0, d, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(M_sub, m0, generator=g, dtype=torch.float64)
+    return x[1:], y[1:], x[0], y[0]
+
+
+def make_hp(B, d):
+    hp = torch.empty(B, d + 2, dtype=torch.float64)
+    hp[:, 0] = 1.0
+    hp[:, 1:d + 1] = 2.0 / math.sqrt(d)
+    hp[:, d + 1] = 0.3
+    return hp
+
+
+def test_points(m, d, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(m, d, generator=g, dtype=torch.float64)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measure_dgemm_peak(dev):
+    """FP64 GEMM peak of THIS device, cuBLAS 8192^3 NT, best of 8 (MEASURED_PEAKS.json has no FP64 entry)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(a, b.t(), out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b.t(), out=c); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+def cpu_sample(w, m_s=256, nc_s=2):
+    """Bounded CPU sample of the same workload through the oracle: nc_s local experts + the communication expert,
+    m_s test points; returns (fit_s, predict_s) for the sample."""
+    from oracle import pygpr_oracle as orc
+    xl, yl, xg, yg = make_data(w)
+    d = w["d"]
+    xl, yl = xl[:nc_s], yl[:nc_s]
+    hp_l, hp_g = make_hp(nc_s, d), make_hp(1, d)[0]
+    xs = test_points(m_s, d)
+    spec = ["se", "wn"]
+    t0 = time.perf_counter()
+    fits = orc.grbcm_fit(spec, hp_g, hp_l, xl, yl, xg, yg, expert_chunk=1)
+    t1 = time.perf_counter()
+    out = orc.grbcm_predict(spec, hp_g, hp_l, xl, yl, xg, yg, xs, expert_chunk=1, fits=fits)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, fits, (xl, yl, xg, yg, hp_g, hp_l)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: /root/reference is Python and cannot be compiled
+    into oracle/_ref, nor does it exist on the GPU box) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pygpr_oracle as orc
+    w = workload(args.small)
+    nc = w["M_sub"] - 1
+    nc_s, m_s = (2, 256) if not args.small else (4, 256)
+    torch.set_num_threads(os.cpu_count() or 1)
+    fit_s, _, fits, (xl, yl, xg, yg, hp_g, hp_l) = cpu_sample(w, m_s, nc_s)
+    xs = test_points(m_s, w["d"])
+    spec = ["se", "wn"]
+
+    def step():
+        orc.grbcm_predict(spec, hp_g, hp_l, xl, yl, xg, yg, xs, expert_chunk=1, fits=fits)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    # scale the sample to the whole job: local experts are equal-sized and independent
+    n_l, n_g = 2 * w["m0"], w["m0"]
+    work_full = nc * n_l ** 2 + n_g ** 2
+    work_s = nc_s * n_l ** 2 + n_g ** 2
+    value = m_s / (dt * work_full / work_s)
+    sample = ("%d of %d local experts + communication expert, %d test points per step; predictions/s scaled by the "
+              "N^2 work ratio %.1f to the whole job" % (nc_s, nc, m_s, work_full / work_s))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": w["name"], "m_per_step": m_s},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "fit_s_sample": fit_s},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=4096, help="test points per step")
+    ap.add_argument("--small", action="store_true", help="smoke-sized workload (not the headline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grad", action="store_true", help="skip the LML-gradient timing")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import pygpr_b200 as P
+    from pygpr_b200 import dist as gdist
+    from pygpr_b200 import engine as eng
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    w = workload(args.small)
+    d, m = w["d"], args.m
+    xl, yl, xg, yg = make_data(w)
+    nc_total = xl.shape[0]
+    lo, hi = gdist.shard_bounds(nc_total, world, rank)
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+    model = P.GRBCM(xl[lo:hi].contiguous(), yl[lo:hi].contiguous(), xg, yg, cov, expert_offset=lo, nc_total=nc_total)
+    model.gpl.set_params(make_hp(hi - lo, d))
+    model.gpg.set_params(make_hp(1, d)[0])
+    del xl, yl
+    peak_tf = measure_dgemm_peak(dev)
+
+    # ---- fit: batched Cholesky (+ fused forward solve, backward solve), timed once after a warm-up pass -------------
+    n_l, n_g, nc_loc = 2 * w["m0"], w["m0"], hi - lo
+    model.gpg.update(); model.gpl.update(); barrier()
+    model.gpl.need_upd = True; model.gpg.need_upd = True
+    model.gpl._state = None  # release the first factor before allocating the second (137 GB at N=1)
+    torch.cuda.empty_cache()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); e0.record(); model.gpg.update(); model.gpl.update(); e1.record(); barrier()
+    fit_ms = max_over_ranks(e0.elapsed_time(e1))
+    fit_flops = nc_total * n_l ** 3 / 3.0 + world * n_g ** 3 / 3.0  # the comm expert is replicated on every rank
+    st = model.gpl._state
+
+    # ---- steps: GRBCM.predict on m test points, factors resident -----------------------------------------------------
+    xs_host = test_points(m, d).pin_memory()
+    xs_dev = xs_host.to(dev)
+
+    pk_ms = []
+
+    def step_device():
+        mg, vg = eng.predict(model.gpg._state, xs_dev, True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        ml, vl = eng.predict(st, xs_dev, True)
+        k1.record()
+        pk_ms.append((k0, k1))
+        S, _, _ = eng.grbcm_partial(ml, vl, vg[0], lo)
+        gdist.all_reduce_sum_(S)
+        return eng.grbcm_finalize(S, mg[0], vg[0])[:2]
+
+    for _ in range(args.warmup):
+        step_device()
+    pk_ms.clear()
+    launches0 = eng.LAUNCHES
+    gpu_index = int(os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[local_rank]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank
+    with ClockSampler(gpu_index) as cs:
+        barrier(); e0.record()
+        for _ in range(args.steps):
+            mu, var = step_device()
+        e1.record(); barrier()
+    step_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = eng.LAUNCHES - launches0
+    kern_ms = sum(a.elapsed_time(b) for a, b in pk_ms) / len(pk_ms)
+    kern_ms = max_over_ranks(kern_ms)
+    value = m / (step_ms * 1e-3)
+    clocks = cs.summary()
+
+    # ---- e2e: public API, host tensors in and out -------------------------------------------------------------------
+    for _ in range(2):
+        model.predict(xs_host, var="diag")
+    barrier(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mu_h, var_h = model.predict(xs_host, var="diag")
+    barrier(); e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = max_over_ranks(e2e_ms)
+    assert not mu_h.is_cuda and bool(torch.isfinite(mu_h).all()) and bool((var_h > 0).all())
+
+    # ---- LML gradient (trtri + fused lauum/gradient) on the resident factors ---------------------------------------------
+    grad_ms = None
+    if not args.no_grad:
+        eng.lml_grad(st); barrier()
+        barrier(); e0.record(); g = eng.lml_grad(st); e1.record(); barrier()
+        grad_ms = max_over_ranks(e0.elapsed_time(e1))
+        assert bool(torch.isfinite(g).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pred_flops_kernel = nc_loc * float(n_l) ** 2 * m          # algorithmic N^2 per test point per expert
+    roof = {"bound": "tensor", "kernel": "predict_kernel", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf, "traffic": None,
+            "peak_source": "cuBLAS dgemm 8192^3 (A B^T) measured in this run on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
+            "kernel_ms": kern_ms, "flops_per_launch": pred_flops_kernel}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": w["name"], "m_per_step": m, "experts_per_rank": nc_loc,
+                                            "l2": "per-step working set (factors %.1f GB) exceeds the 126 MB L2" % (nc_loc * n_l * n_l * 8 / 1e9),
+                                            "parallelism": "experts sharded over %d GPU(s); all-reduce of [3,m] sums" % world},
+            "roofline": roof,
+            "fit": {"ms": fit_ms, "tflops": fit_flops / fit_ms * 1e-9, "frac_of_peak": fit_flops / fit_ms * 1e-9 / (peak_tf * world),
+                    "flops": fit_flops, "what": "batched Cholesky N^3/3 per expert incl. kernel build, forward+backward solve"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": m / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m * d * 8, "d2h_bytes_per_step": 2 * m * 8,
+                    "ms_per_step": e2e_ms}}
+    if grad_ms is not None:
+        gflops = nc_total * float(n_l) ** 3 * 2.0 / 3.0
+        line["lml_grad"] = {"ms": grad_ms, "tflops": gflops / grad_ms * 1e-9, "frac_of_peak": gflops / grad_ms * 1e-9 / (peak_tf * world),
+                            "what": "L^-T + fused K^-1/gradient reduction, 2N^3/3 per expert (Cholesky reported under fit)",
+                            "cholesky_plus_grad_tflops": (gflops + fit_flops) / (grad_ms + fit_ms) * 1e-9}
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        nc_s, m_s = (2, 256) if not args.small else (4, 256)
+        fit_s, pred_s, _, _ = cpu_sample(w, m_s, nc_s)
+        work_full = nc_total * n_l ** 2 + n_g ** 2
+        work_s = nc_s * n_l ** 2 + n_g ** 2
+        line["cpu_baseline"] = {"value": m_s / (pred_s * work_full / work_s), "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port",
+                                "sample": "oracle (torch-CPU restatement of the reference): %d of %d local experts + comm expert, %d test "
+                                          "points, predict %.2f s (fit %.2f s); scaled by the N^2 work ratio %.1f" %
+                                          (nc_s, nc_total, m_s, pred_s, fit_s, work_full / work_s)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

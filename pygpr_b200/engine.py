@@ -19,6 +19,14 @@ from ._lib import TILE
 F64 = torch.float64
 JITTER = 1e-7  # gpr.py:68, loss.py:38,63,96
 
+# number of library kernels launched so far (bench.py reports the delta over its timed region)
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def device() -> torch.device:
     if not torch.cuda.is_available():
@@ -59,6 +67,7 @@ def scale_inputs(x: torch.Tensor, hp: torch.Tensor, B: int, npad: Optional[int] 
     x_bstride = 0 if x.shape[0] == 1 else n * d
     hp_stride = 0 if hp.shape[0] == 1 else hp.shape[-1]
     _lib.call("gpr_se_scale", _p(x), x_bstride, _p(hp), hp_stride, B, n, d, npad, dpad, _p(a), _p(nrm), _stream())
+    _count(1)
     return a, nrm
 
 
@@ -69,6 +78,7 @@ def se_kernel_matrix(hp: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     K = torch.empty(B, n, n, dtype=F64, device=x.device)
     _lib.call("gpr_se_build", _p(a), _p(nrm), _p(hp), hp.shape[-1], None, B, n, a.shape[1], a.shape[2],
               _p(K), n, 0, 0, _stream())
+    _count(1)
     return K
 
 
@@ -84,6 +94,7 @@ def se_cross_matrix(hp: torch.Tensor, x: torch.Tensor, xp: torch.Tensor) -> torc
     Ks = torch.empty(B, m, n, dtype=F64, device=hp.device)
     _lib.call("gpr_se_cross", _p(as_), _p(nrms), as_.shape[1], _p(a), _p(nrm), a.shape[1], _p(hp), hp.shape[-1],
               B, m, n, a.shape[2], _p(Ks), _stream())
+    _count(1)
     return Ks
 
 
@@ -163,10 +174,12 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     info = torch.empty(B, dtype=torch.int32, device=dev)
     _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
               _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _stream())
+    _count(2 * nt - 1)
     alpha = None
     if want_alpha:
         alpha = torch.empty(B, npad, dtype=F64, device=dev)
         _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _stream())
+        _count(1)
     return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior)
 
 
@@ -185,6 +198,7 @@ def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
         zz = torch.empty(B, dtype=F64, device=dev)
     _lib.call("gpr_potrf_batched", _p(K), 0, None, None, None, 0, None, B, npad, npad, 0,
               _p(invdiag), _p(y), _p(z), _p(logdet_half), _p(zz), _p(info), _stream())
+    _count(2 * nt - 1)
     return invdiag, z, logdet_half, zz, info
 
 
@@ -210,6 +224,7 @@ def predict(st: FitState, xs: torch.Tensor, want_var: bool = True) -> Tuple[torc
     _lib.call("gpr_predict", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
               _p(st.prior), _p(xs), st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), int(want_var),
               _p(scratch), _stream())
+    _count(1)
     return mean, var
 
 
@@ -222,6 +237,7 @@ def lml_grad(st: FitState) -> torch.Tensor:
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=st.L.device)
     _lib.call("gpr_lml_grad", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
               int(st.has_noise), st.B, st.n, st.npad, st.d, st.dpad, _p(grad), _p(scratch), _stream())
+    _count(4 if st.npad > TILE else 3)
     return grad
 
 
@@ -234,6 +250,7 @@ def grbcm_partial(mean_l: torch.Tensor, var_l: torch.Tensor, var_g: torch.Tensor
     prec_rows = torch.empty(nc_local, m, dtype=F64, device=var_g.device) if want_rows else None
     _lib.call("grbcm_partial", _p(mean_l), _p(var_l), _p(var_g), nc_local, first_global_index, m, _p(S),
               _p(beta_rows), _p(prec_rows), _stream())
+    _count(1)
     return S, beta_rows, prec_rows
 
 
@@ -244,4 +261,5 @@ def grbcm_finalize(S: torch.Tensor, mean_g: torch.Tensor, var_g: torch.Tensor, w
     beta0 = torch.empty(m, dtype=F64, device=S.device) if want_rows else None
     prec0 = torch.empty(m, dtype=F64, device=S.device) if want_rows else None
     _lib.call("grbcm_finalize", _p(S), _p(mean_g), _p(var_g), m, _p(mu), _p(var), _p(beta0), _p(prec0), _stream())
+    _count(1)
     return mu, var, beta0, prec0

@@ -122,6 +122,7 @@ class Exact_GP(GPR):
                 raise _unsupported(self.cov)
             x, y, hp = self._device_inputs()
             assert hp.shape[-1] == self.cov.get_params_shape(self.x)[-1]
+            self._state = None                                # free the old factor first (it can fill most of HBM)
             self._state = engine.fit(x, y, hp, spec[0])      # gpr.py:67-72
             self._state.check()
             self._krn = self._wt = self._krnchd = NotImplemented
