@@ -35,7 +35,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // D(8x8) += A(8x4, row) * B(4x8, col):  lane (g=lane/4, t=lane%4) holds A[g][t], B[t][g], C[g][2t..2t+1]
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c[0]), "+d"(c[1])
         : "d"(a), "d"(b));
 }
@@ -64,58 +64,75 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][8][2]) {
 // acc += A * B^T over the chunks of s0 then s1.  SAME_AB: the B tile is the A tile (diagonal blocks) and is
 // loaded once.  HOOK gets every landed A chunk tile (used to fuse the forward solve into the Cholesky).
 // Ends with all copies drained and a __syncthreads(), so the caller may reuse `smem` immediately.
+//
+// Schedule (r01 ncu: a burst of 8 LDGSTS per thread right after the barrier backed up the LSU queue and idled the
+// tensor pipe ~12% of every chunk): the copies of chunk c+3 are issued in four slices, one between each k4 block of
+// DMMAs of chunk c, and the A/B fragments of the next k4 block are fetched into a second register set before the
+// current block's 32 DMMAs, so neither LDGSTS back-pressure nor LDS latency sits in front of the tensor pipe.
 template <bool SAME_AB, typename HOOK>
 __device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, const Seg& s1, double* smem, HOOK& hook) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
-    const int total = s0.nchunks + s1.nchunks;
+    const int n0 = s0.nchunks;
+    const int total = n0 + s1.nchunks;
+    // per-thread copy coordinates: slice q moves rows (tid>>3) + 32 q, 16-byte column (tid&7)
+    const int crow = tid >> 3, ccol = (tid & 7) * 2;
+    const long long offA0 = crow * s0.lda + ccol, offB0 = crow * s0.ldb + ccol;
+    const long long offA1 = crow * s1.lda + ccol, offB1 = crow * s1.ldb + ccol;
+    const int soff = crow * SLD + ccol;
 
-    auto issue = [&](int c) {
+    auto issue_slice = [&](int c, int q) {  // one quarter (32 rows) of chunk c
         if (c < total) {
-            const bool first = c < s0.nchunks;
-            const Seg& s = first ? s0 : s1;
-            const int lc = first ? c : c - s0.nchunks;
-            double* sA = smem + (c % STAGES) * STAGE_DOUBLES;
-            double* sB = sA + TILE * SLD;
-            const double* gA = s.A + (long long)lc * KC;
-            const double* gB = s.B + (long long)lc * KC;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int id = tid + q * NTHREADS;
-                const int row = id >> 3, cc = (id & 7) * 2;
-                cp_async16(sA + row * SLD + cc, gA + row * s.lda + cc);
-                if (!SAME_AB) cp_async16(sB + row * SLD + cc, gB + row * s.ldb + cc);
+            const bool first = c < n0;
+            const int lc = first ? c : c - n0;
+            double* sA = smem + (c % STAGES) * STAGE_DOUBLES + soff + q * 32 * SLD;
+            const double* gA = (first ? s0.A + offA0 + (long long)q * 32 * s0.lda : s1.A + offA1 + (long long)q * 32 * s1.lda) + (long long)lc * KC;
+            cp_async16(sA, gA);
+            if (!SAME_AB) {
+                const double* gB = (first ? s0.B + offB0 + (long long)q * 32 * s0.ldb : s1.B + offB1 + (long long)q * 32 * s1.ldb) + (long long)lc * KC;
+                cp_async16(sA + TILE * SLD, gB);
             }
         }
-        cp_async_commit();
     };
 
 #pragma unroll
-    for (int c = 0; c < STAGES - 1; ++c) issue(c);
+    for (int c = 0; c < STAGES - 1; ++c) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) issue_slice(c, q);
+        cp_async_commit();
+    }
 
     const int aoff = (wm * 32 + g) * SLD + t;
     const int boff = (wn * 64 + g) * SLD + t;
     for (int c = 0; c < total; ++c) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        issue(c + STAGES - 1);
         const double* sA = smem + (c % STAGES) * STAGE_DOUBLES;
         const double* sB = SAME_AB ? sA : sA + TILE * SLD;
         hook.pre(c);
+        double fa[2][4], fb[2][8];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) fa[0][mi] = sA[aoff + mi * 8 * SLD];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) fb[0][ni] = sB[boff + ni * 8 * SLD];
 #pragma unroll
         for (int kk = 0; kk < KC / 4; ++kk) {
-            double a[4], b[8];
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk + 1 < KC / 4) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = sA[aoff + mi * 8 * SLD + kk * 4];
+                for (int mi = 0; mi < 4; ++mi) fa[nxt][mi] = sA[aoff + mi * 8 * SLD + (kk + 1) * 4];
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) b[ni] = sB[boff + ni * 8 * SLD + kk * 4];
+                for (int ni = 0; ni < 8; ++ni) fb[nxt][ni] = sB[boff + ni * 8 * SLD + (kk + 1) * 4];
+            }
+            issue_slice(c + STAGES - 1, kk);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+                for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[cur][mi], fb[cur][ni]);
         }
+        cp_async_commit();
         hook.post(sA, c);
     }
     cp_async_wait<0>();

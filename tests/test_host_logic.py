@@ -1,0 +1,116 @@
+"""Host-side logic that needs no GPU: optimisers (PyGPR/tests/test_opt.py), learn-rate rule, sharding, gloo all-reduce."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class QuadLoss:
+    """Random SPD quadratic standing in for a Loss (the reference's test uses Loss(None) the same way)."""
+
+    def __init__(self, dim, seed):
+        rng = np.random.RandomState(seed)
+        A = rng.rand(dim, dim)
+        self.H = A @ A.T + dim * np.eye(dim)
+        self.b = rng.rand(dim)
+        self.model = None
+        self.loss_value = None
+        self.grad_value = None
+
+    def loss(self, x):
+        return 0.5 * x @ self.H @ x - self.b @ x
+
+    def grad(self, x):
+        return self.H @ x - self.b
+
+    def loss_and_grad(self, x):
+        return self.loss(x), self.grad(x)
+
+
+@pytest.mark.parametrize("dim", [2, 3, 5, 7])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_opt_quad(dim, seed, tmp_path, monkeypatch):
+    """CG_Quad and BFGS_Quad reach the minimiser of a random SPD quadratic (PyGPR/tests/test_opt.py:20-56)."""
+    from pygpr_b200 import BFGS_Quad, CG_Quad, hessian
+    monkeypatch.chdir(tmp_path)
+    loss = QuadLoss(dim, seed)
+    xmin = np.linalg.solve(loss.H, loss.b)
+    x0 = np.random.RandomState(seed + 10).rand(dim)
+    cg = CG_Quad(loss, gtol=1e-8, max_iter=200, fd_eps=1e-6)
+    cg.minimize(x0.copy())
+    assert np.allclose(cg.x, xmin, rtol=1e-3)
+    bf = BFGS_Quad(loss, gtol=1e-8, max_iter=200)
+    bf.minimize(x0.copy(), H0=hessian(x0, loss.grad, 1e-6))
+    assert np.allclose(bf.x, xmin, rtol=1e-3)
+    assert os.path.exists("opt.dat")
+
+
+def test_learn_rate_parabola():
+    """On an exact quadratic the parabola through f(theta), f(theta -/+ eps J) gives the exact line minimum
+    (hp_update.py:14-22): gamma = J.J / J.H.J."""
+    from pygpr_b200 import get_learn_rate
+    loss = QuadLoss(4, 3)
+    theta = torch.tensor([0.3, -0.2, 0.5, 0.1])
+    gamma = get_learn_rate(theta, loss, 1e-3)
+    J = loss.grad(theta.numpy())
+    assert np.isclose(gamma, (J @ J) / (J @ loss.H @ J), rtol=1e-6)
+
+
+def test_shard_bounds_cover_all_experts():
+    from pygpr_b200.dist import shard_bounds
+    for nc in (1, 7, 63, 255, 511):
+        for ws in (1, 2, 4, 8):
+            parts = [shard_bounds(nc, ws, r) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == nc
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+            assert max(hi - lo for lo, hi in parts) == -(-nc // ws)
+    assert [hi - lo for lo, hi in (shard_bounds(255, 8, r) for r in range(8))] == [32] * 7 + [31]
+
+
+def _partial_cpu(mean_l, var_l, var_g, first):
+    """numpy restatement of grbcm_partial (include/pygpr_b200.h) used only to exercise the sharded protocol on CPU."""
+    p = 1.0 / var_l
+    beta = 0.5 * (torch.log(p) - torch.log(1.0 / var_g))
+    if first == 0:
+        beta[0] = 1.0
+    return torch.stack((beta.sum(0), (beta * p).sum(0), (beta * p * mean_l).sum(0)))
+
+
+def _worker(rank, ws, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from oracle import pygpr_oracle as orc
+    from pygpr_b200 import dist as gdist
+    g = torch.Generator().manual_seed(7)
+    nc, m = 9, 57
+    mean_l = torch.randn(nc, m, generator=g, dtype=torch.float64)
+    var_l = 0.05 + torch.rand(nc, m, generator=g, dtype=torch.float64)
+    mean_g = torch.randn(m, generator=g, dtype=torch.float64)
+    var_g = 0.5 + torch.rand(m, generator=g, dtype=torch.float64)
+    lo, hi = gdist.shard_bounds(nc, ws, rank)
+    S = _partial_cpu(mean_l[lo:hi], var_l[lo:hi], var_g, lo)
+    gdist.all_reduce_sum_(S)                                   # the [3, m] all-reduce of SURVEY §8(e)
+    b0 = 1.0 - S[0]
+    var_a = 1.0 / (S[1] + b0 / var_g)
+    mu_a = var_a * (S[2] + b0 * mean_g / var_g)
+    mu_ref, var_ref, beta_ref, _ = orc.grbcm_aggregate(mean_g, var_g, mean_l, var_l)
+    ok = torch.allclose(mu_a, mu_ref, rtol=1e-12, atol=1e-14) and torch.allclose(var_a, var_ref, rtol=1e-12, atol=1e-14)
+    rows = gdist.all_gather_rows(mean_l[lo:hi].contiguous(), [gdist.shard_bounds(nc, ws, r)[1] - gdist.shard_bounds(nc, ws, r)[0] for r in range(ws)])
+    ok = ok and torch.equal(rows, mean_l) and gdist.world() == (rank, ws)
+    open(os.path.join(tmp, "ok%d" % rank), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_sharded_aggregation_gloo_world2(tmp_path):
+    """Two CPU ranks (gloo): shard the experts, all-reduce the partial sums, every rank recovers the oracle's aggregate."""
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(os.path.join(str(tmp_path), "ok%d" % r)).read() for r in range(2)] == ["1", "1"]
