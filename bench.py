@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the PyGPR hot path on B200: GRBCM predictions/sec at n=1M, d=16 (BASELINE.json config 4).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--m M] [--small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--test-points M] [--small]
 
 Workload (reading A): 256 subsets x 4096 points of a 16-d synthetic regression problem; one subset
 is the communication set, so there are 255 local experts of order 8192 plus one communication expert of order
@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--m", type=int, default=4096, help="test points per step")
+    ap.add_argument("--test-points", dest="m", type=int, default=4096, help="test points per step")
     ap.add_argument("--small", action="store_true", help="smoke-sized workload (not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-grad", action="store_true", help="skip the LML-gradient timing")

@@ -93,7 +93,7 @@ int gpr_se_kernel_grad(const double* Kse, const double* x, const double* hp, int
  * half of tc.cholesky_solve gpr.py:70-72 / loss.py:44 (C6) and the NLML scalar loss.py:49-51 (C14).
  *
  *   L        [B, npad, npad] in: see `gen`; out: lower factor (strict upper triangle of each
- *            diagonal block zeroed; blocks above the block diagonal are NOT touched)
+ *            diagonal block zeroed; blocks above the block diagonal are used as scratch)
  *   gen == 0 the lower triangle of K (+ identity padding) is already in L (in-place factorisation)
  *   gen != 0 K is generated on the fly from (a, nrm, hp, diag_add) — L is write-only
  *   invdiag  [B, npad/128, 128, 128] out: inverses of the diagonal blocks of L (lower triangular)

@@ -200,47 +200,143 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// In-place lower Cholesky of the 128x128 tile T (row stride XLD) by all 256 threads; right-looking, two barriers
-// per column.  colk is a 128-double scratch.  Returns (through *fail) the first 1-based column with a non-positive
-// pivot, 0 if none.  Strict upper triangle is left untouched.
-__device__ __forceinline__ void potf2_smem(double* T, double* colk, int* fail) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = 0; k < TILE; ++k) {
-        __syncthreads();
-        const double d = T[k * XLD + k];
-        if (tid == 0 && !(d > 0.0) && *fail == 0) *fail = k + 1;
-        const double l = sqrt(d);
-        if (tid > k && tid < TILE) {
-            const double v = T[tid * XLD + k] / l;
-            colk[tid] = v;
-            T[tid * XLD + k] = v;
+// ---------------------------------------------------------------------------------------------
+// Register-resident factorisation of one 128x128 diagonal tile.
+// The lower triangle is cut into 136 blocks of 8x8; thread q < 136 owns block (bi, bj) in 64 registers, so a
+// right-looking step is 16 shared loads + 64 predicated DFMA per thread and ONE barrier (the published column /
+// row is double buffered).  r01 profile: the first version walked the tile in shared memory with two barriers and
+// a store->load alias chain per column and took ~0.5 ms per tile; this takes ~20 us.
+// ---------------------------------------------------------------------------------------------
+struct DiagBlock {
+    int bi, bj;       // block row / column (bi >= bj); bi = -1 for idle threads
+    double R[8][8];
+};
+
+__device__ __forceinline__ void diag_block_coords(DiagBlock& d) {
+    const int q = threadIdx.x;
+    d.bi = -1;
+    d.bj = 0;
+    if (q < 136) {
+        int bi = 0, rem = q;
+        while (rem >= bi + 1) { rem -= bi + 1; ++bi; }
+        d.bi = bi;
+        d.bj = rem;
+    }
+}
+
+// T (row stride XLD) holds the symmetric tile (lower part used).  On return T holds L in the lower triangle AND its
+// transpose in the upper triangle (T[k][i] = L[i][k]) so a column of L is a contiguous row for the inversion.
+// pub: 2 x 128 doubles scratch.  *fail receives the first 1-based column with a non-positive pivot (0 if none).
+__device__ __forceinline__ void potf2_reg(double* T, double* pub, int* fail, DiagBlock& d) {
+    const bool live = d.bi >= 0;
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d.R[r][c] = T[(d.bi * 8 + r) * XLD + d.bj * 8 + c];
+    }
+    for (int kb = 0; kb < 16; ++kb) {
+#pragma unroll
+        for (int kr = 0; kr < 8; ++kr) {
+            const int k = kb * 8 + kr;
+            double* u = pub + (k & 1) * TILE;
+            if (live && d.bj == kb) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) u[d.bi * 8 + r] = d.R[r][kr];
+            }
+            __syncthreads();
+            const double p = u[k];
+            if (threadIdx.x == 0 && !(p > 0.0) && *fail == 0) *fail = k + 1;
+            if (live && d.bj >= kb) {
+                const double s = sqrt(p);
+                const double rinv = 1.0 / s;  // dpotf2 scales the column by the reciprocal of the pivot
+                double li[8], lj[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) li[r] = u[d.bi * 8 + r] * rinv;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) lj[c] = u[d.bj * 8 + c] * rinv;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (d.bi * 8 + r > k && d.bj * 8 + c > k) d.R[r][c] -= li[r] * lj[c];
+                if (d.bj == kb) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int gr = d.bi * 8 + r;
+                        if (gr > k) d.R[r][kr] = li[r];
+                        else if (gr == k) d.R[r][kr] = s;
+                    }
+                }
+            }
         }
-        __syncthreads();
-        if (tid == 0) T[k * XLD + k] = l;
-        for (int i = k + 1 + warp; i < TILE; i += NTHREADS / 32) {
-            const double ci = colk[i];
-            for (int j = k + 1 + lane; j <= i; j += 32) T[i * XLD + j] -= ci * colk[j];
-        }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int gr = d.bi * 8 + r, gc = d.bj * 8 + c;
+                if (gr >= gc) {
+                    T[gr * XLD + gc] = d.R[r][c];
+                    T[gc * XLD + gr] = d.R[r][c];
+                }
+            }
     }
     __syncthreads();
 }
 
-// In-place inverse of the lower-triangular 128x128 tile T (row stride XLD); columns from last to first (dtrti2).
-__device__ __forceinline__ void trti2_smem(double* T, double* colk) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int j = TILE - 1; j >= 0; --j) {
-        __syncthreads();
-        const double ajj = 1.0 / T[j * XLD + j];
-        if (tid > j && tid < TILE) colk[tid] = T[tid * XLD + j];
-        __syncthreads();
-        // new column j below the diagonal: -ajj * Tinv[j+1:, j+1:] * colk[j+1:]
-        for (int i = j + 1 + warp; i < TILE; i += NTHREADS / 32) {
-            double s = 0.0;
-            for (int k = j + 1 + lane; k <= i; k += 32) s += T[i * XLD + k] * colk[k];
-            s = warp_sum(s);
-            if (lane == 0) T[i * XLD + j] = -ajj * s;
+// X = L^-1 by right-looking forward substitution on the identity, blocks in registers.  T as left by potf2_reg
+// (column k of L readable as row k).  On return T holds X in the lower triangle and zeros above it.
+__device__ __forceinline__ void trtri_reg(double* T, double* pub, DiagBlock& d) {
+    const bool live = d.bi >= 0;
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d.R[r][c] = (d.bi == d.bj && r == c) ? 1.0 : 0.0;
+    }
+    for (int kb = 0; kb < 16; ++kb) {
+#pragma unroll
+        for (int kr = 0; kr < 8; ++kr) {
+            const int k = kb * 8 + kr;
+            double* xr = pub + (k & 1) * TILE;
+            if (live && d.bi == kb) {  // row k of X is final: X[k][c] = R[k][c] / L[k][k]
+                const double dkk = T[k * XLD + k];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double v = (d.bj * 8 + c <= k) ? d.R[kr][c] / dkk : 0.0;
+                    d.R[kr][c] = v;
+                    xr[d.bj * 8 + c] = v;
+                }
+            }
+            __syncthreads();
+            if (live && d.bi >= kb && d.bj <= kb) {
+                double lc[8], xv[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) lc[r] = T[k * XLD + d.bi * 8 + r];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xv[c] = xr[d.bj * 8 + c];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (d.bi * 8 + r > k) d.R[r][c] -= lc[r] * xv[c];
+            }
         }
-        if (tid == 0) T[j * XLD + j] = ajj;
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int gr = d.bi * 8 + r, gc = d.bj * 8 + c;
+                if (gr >= gc) T[gr * XLD + gc] = d.R[r][c];
+                else T[gr * XLD + gc] = 0.0;
+                if (gr > gc) T[gc * XLD + gr] = 0.0;
+            }
     }
     __syncthreads();
 }

@@ -206,21 +206,43 @@ extern "C" int gpr_se_kernel_grad(const double* Kse, const double* x, const doub
 
 // ---------------------------------------------------------------------------------------------
 // K3: batched blocked left-looking Cholesky.  Two launches per block column j:
-//   potrf_diag_kernel : T = K_jj - L[j,0:j] L[j,0:j]^T (DMMA) -> potf2 in smem -> L_jj, inv(L_jj);
+//   potrf_diag_kernel : T = K_jj - L[j,0:j] L[j,0:j]^T -> potf2 + inverse in registers -> L_jj, inv(L_jj);
 //                       forward solve z_j = inv(L_jj)(y_j - L[j,0:j] z[0:j]) fused (GEMV on the chunks
 //                       already in smem), plus sum log L_ii and z.z  -> NLML pieces for free.
 //   potrf_panel_kernel: L_ij = (K_ij - L[i,0:j] L[j,0:j]^T) inv(L_jj)^T for every row tile i>j (DMMA twice).
+// Look-ahead: the diagonal kernel sits on the critical path with only B CTAs, so all of its product except the last
+// 128-deep block is computed one launch earlier by an extra CTA per expert inside the (wide) panel launch of column
+// j-1 and parked in the unused upper block (j-1, j) of L; the diagonal kernel then costs O(1) tiles, not O(j).
 // ---------------------------------------------------------------------------------------------
 struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-warp per row, 8 rows per half-warp
     const double* z;
     double zk;
     double part[8];
+    __device__ __forceinline__ void init(const double* zp) {
+        z = zp;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[r] = 0.0;
+    }
     __device__ __forceinline__ void pre(int c) { zk = z ? z[c * KC + (threadIdx.x & 15)] : 0.0; }
     __device__ __forceinline__ void post(const double* sA, int) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const double* p = sA + (warp * 16 + (lane >> 4) * 8) * SLD + (lane & 15);
 #pragma unroll
         for (int r = 0; r < 8; ++r) part[r] += p[r * SLD] * zk;
+    }
+    // out[row] = (add ? add[row] : 0) + reduced partial; rows owned by lanes 0 and 16 of each warp
+    __device__ __forceinline__ void reduce_to(double* out, const double* add) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double v = part[r];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            const int row = warp * 16 + (lane >> 4) * 8 + r;
+            if ((lane & 15) == 0) out[row] = v + (add ? add[row] : 0.0);
+        }
     }
 };
 
@@ -231,42 +253,31 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
                   double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
                   double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
     extern __shared__ double smem[];
-    __shared__ double colk[TILE];
+    __shared__ double pub[2 * TILE];
     __shared__ double svec[TILE];
     __shared__ int s_fail;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int nt = npad / TILE;
     double* Lb = L + (long long)b * npad * npad;
     double* Ljj = Lb + ((long long)j * TILE) * npad + j * TILE;
+    double* zb = y ? z + (long long)b * npad : nullptr;
     if (tid == 0) s_fail = 0;
 
+    // product over the LAST block column only (k-block j-1); blocks 0..j-2 were summed by the look-ahead CTA
     double acc[4][8][2];
     zero_acc(acc);
     GemvHook hook;
-    hook.z = y ? z + (long long)b * npad : nullptr;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) hook.part[r] = 0.0;
-    Seg s0{Lb + ((long long)j * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
+    hook.init(zb && j > 0 ? zb + (long long)(j - 1) * TILE : nullptr);
+    const double* Arow = Lb + ((long long)j * TILE) * npad + (long long)(j > 0 ? j - 1 : 0) * TILE;
+    Seg s0{Arow, npad, Arow, npad, j > 0 ? TILE / KC : 0};
     Seg s1{nullptr, 0, nullptr, 0, 0};
     mainloop<true>(acc, s0, s1, smem, hook);
-
-    // GEMV result of the fused forward solve
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            double v = hook.part[r];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 15) == 0) svec[warp * 16 + (lane >> 4) * 8 + r] = v;
-        }
-    }
+    const bool have_part = j >= 2;
+    const double* dpart = Lb + ((long long)(j - 1) * TILE) * npad + (long long)j * TILE;  // upper block (j-1, j)
+    hook.reduce_to(svec, (have_part && zb) ? zb + (long long)j * TILE : nullptr);
 
     double* T = smem;  // full tile overlays the (drained) pipeline stages
     if (GEN) {
-        // generate K_jj into T, then subtract the accumulated product
         double* fbase = smem + TILE * XLD;
         FeatSmem f = carve_feat(fbase, dpad);
         load_feat_tile(f.sR, f.sld, a + ((long long)b * npad + j * TILE) * dpad, dpad);
@@ -282,6 +293,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
             double v;
             if (gr < n && gc < n) v = (r == c) ? kv + dadd : kv;
             else v = (r == c) ? 1.0 : 0.0;
+            if (have_part) v -= dpart[(long long)r * npad + c];
             T[r * XLD + c] = v - acc[mi][ni][e];
         });
     } else {
@@ -290,12 +302,20 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni) {
                 const int r = acc_row(mi), c = acc_col(ni, 0);
-                const double2 k2 = *reinterpret_cast<const double2*>(Ljj + (long long)r * npad + c);
+                double2 k2 = *reinterpret_cast<const double2*>(Ljj + (long long)r * npad + c);
+                if (have_part) {
+                    const double2 p2 = *reinterpret_cast<const double2*>(dpart + (long long)r * npad + c);
+                    k2.x -= p2.x;
+                    k2.y -= p2.y;
+                }
                 T[r * XLD + c] = k2.x - acc[mi][ni][0];
                 T[r * XLD + c + 1] = k2.y - acc[mi][ni][1];
             }
     }
-    potf2_smem(T, colk, &s_fail);
+    __syncthreads();
+    DiagBlock blk;
+    diag_block_coords(blk);
+    potf2_reg(T, pub, &s_fail, blk);
 
     // write L_jj (strict upper zeroed) and accumulate sum log L_ii
     for (int id = tid; id < TILE * TILE; id += NTHREADS) {
@@ -314,21 +334,22 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
             }
         }
     }
-    trti2_smem(T, colk);
+    trtri_reg(T, pub, blk);
     double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
-    for (int id = tid; id < TILE * TILE; id += NTHREADS) {
-        const int r = id >> 7, c = id & 127;
-        inv[id] = (c <= r) ? T[r * XLD + c] : 0.0;
-    }
+    for (int id = tid; id < TILE * TILE; id += NTHREADS) inv[id] = T[(id >> 7) * XLD + (id & 127)];
     if (y) {
-        // z_j = inv(L_jj) (y_j - L[j,0:j] z[0:j])
-        if (tid < TILE) colk[tid] = y[(long long)b * npad + j * TILE + tid] - svec[tid];
+        // z_j = inv(L_jj) (y_j - L[j,0:j] z[0:j]); warp per row, lanes along k, fixed-order reduction
+        if (tid < TILE) pub[tid] = y[(long long)b * npad + j * TILE + tid] - svec[tid];
         __syncthreads();
-        if (tid < TILE) {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < TILE; r += NTHREADS / 32) {
             double s = 0.0;
-            for (int k = 0; k <= tid; ++k) s += T[tid * XLD + k] * colk[k];
-            z[(long long)b * npad + j * TILE + tid] = s;
-            svec[tid] = s * s;
+            for (int k = lane; k <= r; k += 32) s += T[r * XLD + k] * pub[k];
+            s = warp_sum(s);
+            if (lane == 0) {
+                zb[j * TILE + r] = s;
+                svec[r] = s * s;
+            }
         }
         __syncthreads();
         if (tid < 32 && zz) {
@@ -339,20 +360,42 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     }
 }
 
+// grid.x = (nt-1-j) row tiles, plus one look-ahead CTA per expert when lookahead != 0 (j >= 1, j+1 < nt):
+// that CTA forms  P = L[j+1,0:j] L[j+1,0:j]^T  (k-blocks 0..j-1, complete since the previous launches) for the NEXT
+// diagonal tile into the upper block (j, j+1) and the matching forward-solve partial into z[(j+1)*128 ...].
 template <bool GEN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
-                   const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag) {
+                   const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag, int lookahead,
+                   double* __restrict__ z) {
     extern __shared__ double smem[];
-    const int b = blockIdx.y, i = j + 1 + blockIdx.x;
+    const int b = blockIdx.y;
     const int nt = npad / TILE;
     double* Lb = L + (long long)b * npad * npad;
-    double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
-
     double acc[4][8][2];
     zero_acc(acc);
-    NoHook nh;
     Seg none{nullptr, 0, nullptr, 0, 0};
+
+    if (lookahead && blockIdx.x == gridDim.x - 1) {
+        const double* Arow = Lb + ((long long)(j + 1) * TILE) * npad;
+        GemvHook hook;
+        hook.init(z ? z + (long long)b * npad : nullptr);
+        Seg s0{Arow, npad, Arow, npad, j * (TILE / KC)};
+        mainloop<true>(acc, s0, none, smem, hook);
+        double* dpart = Lb + ((long long)j * TILE) * npad + (long long)(j + 1) * TILE;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+                *reinterpret_cast<double2*>(dpart + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        if (z) hook.reduce_to(z + (long long)b * npad + (long long)(j + 1) * TILE, nullptr);
+        return;
+    }
+
+    const int i = j + 1 + blockIdx.x;
+    double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
+    NoHook nh;
     Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
     mainloop<false>(acc, s0, none, smem, nh);
 
@@ -436,11 +479,14 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
             potrf_diag_kernel<false><<<B, NTHREADS, smem_diag, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad,
                                                                       invdiag, y, z, logdet_half, zz, info);
         if (j + 1 < nt) {
-            dim3 grid(nt - 1 - j, B);
+            const int lookahead = (j >= 1) ? 1 : 0;
+            dim3 grid(nt - 1 - j + lookahead, B);
             if (gen)
-                potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag);
+                potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag,
+                                                                             lookahead, y ? z : nullptr);
             else
-                potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag);
+                potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag,
+                                                                              lookahead, y ? z : nullptr);
         }
     }
     CUDA_TRY(cudaGetLastError());
