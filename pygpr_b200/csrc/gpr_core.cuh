@@ -202,10 +202,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---------------------------------------------------------------------------------------------
 // Register-resident factorisation of one 128x128 diagonal tile.
-// The lower triangle is cut into 136 blocks of 8x8; thread q < 136 owns block (bi, bj) in 64 registers, so a
-// right-looking step is 16 shared loads + 64 predicated DFMA per thread and ONE barrier (the published column /
-// row is double buffered).  r01 profile: the first version walked the tile in shared memory with two barriers and
-// a store->load alias chain per column and took ~0.5 ms per tile; this takes ~20 us.
+// The lower triangle is cut into 136 blocks of 8x8; thread q < 136 owns block (bi, bj) in 64 registers.  A
+// right-looking step is: owners of the pivot column (row) publish 8 values, ONE barrier (the published vector is
+// double buffered), then every live block does 4 LDS.128 x2 + 64 unconditional DFMA.  Boundary blocks mask the
+// published vector instead of predicating the update, the kr loop stays rolled (register column/row selected by a
+// switch only in the 8-value publish), and no sqrt/divide sits on the step-to-step dependency chain: the Cholesky
+// update uses u_i u_j / p with the columns kept unscaled until the end.  (r01: the smem version took ~0.5 ms per
+// tile, a fully unrolled/predicated register version 0.36 ms (240 KB of code, 53 % barrier stalls).)
 // ---------------------------------------------------------------------------------------------
 struct DiagBlock {
     int bi, bj;       // block row / column (bi >= bj); bi = -1 for idle threads
@@ -224,52 +227,92 @@ __device__ __forceinline__ void diag_block_coords(DiagBlock& d) {
     }
 }
 
+template <int KR>
+__device__ __forceinline__ void publish_col(const DiagBlock& d, double* dst) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dst[r] = d.R[r][KR];
+}
+__device__ __forceinline__ void publish_col(const DiagBlock& d, int kr, double* dst) {
+    switch (kr) {
+        case 0: publish_col<0>(d, dst); break;
+        case 1: publish_col<1>(d, dst); break;
+        case 2: publish_col<2>(d, dst); break;
+        case 3: publish_col<3>(d, dst); break;
+        case 4: publish_col<4>(d, dst); break;
+        case 5: publish_col<5>(d, dst); break;
+        case 6: publish_col<6>(d, dst); break;
+        default: publish_col<7>(d, dst); break;
+    }
+}
+template <int KR>
+__device__ __forceinline__ void scale_publish_row(DiagBlock& d, double f, double* dst) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double v = d.R[KR][c] * f;
+        d.R[KR][c] = v;
+        dst[c] = v;
+    }
+}
+__device__ __forceinline__ void scale_publish_row(DiagBlock& d, int kr, double f, double* dst) {
+    switch (kr) {
+        case 0: scale_publish_row<0>(d, f, dst); break;
+        case 1: scale_publish_row<1>(d, f, dst); break;
+        case 2: scale_publish_row<2>(d, f, dst); break;
+        case 3: scale_publish_row<3>(d, f, dst); break;
+        case 4: scale_publish_row<4>(d, f, dst); break;
+        case 5: scale_publish_row<5>(d, f, dst); break;
+        case 6: scale_publish_row<6>(d, f, dst); break;
+        default: scale_publish_row<7>(d, f, dst); break;
+    }
+}
+
 // T (row stride XLD) holds the symmetric tile (lower part used).  On return T holds L in the lower triangle AND its
 // transpose in the upper triangle (T[k][i] = L[i][k]) so a column of L is a contiguous row for the inversion.
-// pub: 2 x 128 doubles scratch.  *fail receives the first 1-based column with a non-positive pivot (0 if none).
+// pub: 3 x 128 doubles scratch (two publish buffers + pivots).  *fail = first 1-based column with a non-positive
+// pivot (0 if none).
 __device__ __forceinline__ void potf2_reg(double* T, double* pub, int* fail, DiagBlock& d) {
     const bool live = d.bi >= 0;
+    double* piv = pub + 2 * TILE;
     if (live) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int c = 0; c < 8; ++c) d.R[r][c] = T[(d.bi * 8 + r) * XLD + d.bj * 8 + c];
     }
-    for (int kb = 0; kb < 16; ++kb) {
-#pragma unroll
-        for (int kr = 0; kr < 8; ++kr) {
-            const int k = kb * 8 + kr;
-            double* u = pub + (k & 1) * TILE;
-            if (live && d.bj == kb) {
-#pragma unroll
-                for (int r = 0; r < 8; ++r) u[d.bi * 8 + r] = d.R[r][kr];
-            }
-            __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < TILE; ++k) {
+        const int kb = k >> 3, kr = k & 7;
+        double* u = pub + (k & 1) * TILE;
+        if (live && d.bj == kb) publish_col(d, kr, u + d.bi * 8);   // unscaled column k (rows of this block)
+        __syncthreads();
+        if (live && d.bj >= kb) {
             const double p = u[k];
-            if (threadIdx.x == 0 && !(p > 0.0) && *fail == 0) *fail = k + 1;
-            if (live && d.bj >= kb) {
-                const double s = sqrt(p);
-                const double rinv = 1.0 / s;  // dpotf2 scales the column by the reciprocal of the pivot
-                double li[8], lj[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) li[r] = u[d.bi * 8 + r] * rinv;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) lj[c] = u[d.bj * 8 + c] * rinv;
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (d.bi * 8 + r > k && d.bj * 8 + c > k) d.R[r][c] -= li[r] * lj[c];
-                if (d.bj == kb) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int gr = d.bi * 8 + r;
-                        if (gr > k) d.R[r][kr] = li[r];
-                        else if (gr == k) d.R[r][kr] = s;
-                    }
-                }
+            if (d.bi == kb && d.bj == kb) {
+                piv[k] = p;
+                if (!(p > 0.0)) atomicMin(fail, k + 1);
             }
+            const double pinv = __drcp_rn(p);
+            double li[8], lj[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) li[r] = u[d.bi * 8 + r] * pinv;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) lj[c] = u[d.bj * 8 + c];
+            if (d.bj == kb) {  // columns <= k of the pivot block column are final (kept unscaled): mask them out
+#pragma unroll
+                for (int c = 0; c < 8; ++c) lj[c] = (c > kr) ? lj[c] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d.R[r][c] -= li[r] * lj[c];
         }
+    }
+    __syncthreads();
+    // L[i][k] = u_ik / sqrt(p_k),  L[k][k] = sqrt(p_k); write both triangles of T
+    if (threadIdx.x < TILE) {
+        const double sq = sqrt(piv[threadIdx.x]);
+        pub[threadIdx.x] = sq;
+        pub[TILE + threadIdx.x] = 1.0 / sq;
     }
     __syncthreads();
     if (live) {
@@ -279,8 +322,9 @@ __device__ __forceinline__ void potf2_reg(double* T, double* pub, int* fail, Dia
             for (int c = 0; c < 8; ++c) {
                 const int gr = d.bi * 8 + r, gc = d.bj * 8 + c;
                 if (gr >= gc) {
-                    T[gr * XLD + gc] = d.R[r][c];
-                    T[gc * XLD + gr] = d.R[r][c];
+                    const double v = (gr == gc) ? pub[gc] : d.R[r][c] * pub[TILE + gc];
+                    T[gr * XLD + gc] = v;
+                    T[gc * XLD + gr] = v;
                 }
             }
     }
@@ -291,39 +335,35 @@ __device__ __forceinline__ void potf2_reg(double* T, double* pub, int* fail, Dia
 // (column k of L readable as row k).  On return T holds X in the lower triangle and zeros above it.
 __device__ __forceinline__ void trtri_reg(double* T, double* pub, DiagBlock& d) {
     const bool live = d.bi >= 0;
+    double* dinv = pub + 2 * TILE;
+    if (threadIdx.x < TILE) dinv[threadIdx.x] = 1.0 / T[threadIdx.x * XLD + threadIdx.x];
     if (live) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int c = 0; c < 8; ++c) d.R[r][c] = (d.bi == d.bj && r == c) ? 1.0 : 0.0;
     }
-    for (int kb = 0; kb < 16; ++kb) {
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 0; k < TILE; ++k) {
+        const int kb = k >> 3, kr = k & 7;
+        double* xr = pub + (k & 1) * TILE;
+        if (live && d.bi == kb) scale_publish_row(d, kr, dinv[k], xr + d.bj * 8);  // row k of X is final
+        __syncthreads();
+        if (live && d.bi >= kb && d.bj <= kb) {
+            double lc[8], xv[8];
 #pragma unroll
-        for (int kr = 0; kr < 8; ++kr) {
-            const int k = kb * 8 + kr;
-            double* xr = pub + (k & 1) * TILE;
-            if (live && d.bi == kb) {  // row k of X is final: X[k][c] = R[k][c] / L[k][k]
-                const double dkk = T[k * XLD + k];
+            for (int r = 0; r < 8; ++r) lc[r] = T[k * XLD + d.bi * 8 + r];
+            if (d.bi == kb) {  // rows <= k of the pivot block row are final
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double v = (d.bj * 8 + c <= k) ? d.R[kr][c] / dkk : 0.0;
-                    d.R[kr][c] = v;
-                    xr[d.bj * 8 + c] = v;
-                }
+                for (int r = 0; r < 8; ++r) lc[r] = (r > kr) ? lc[r] : 0.0;
             }
-            __syncthreads();
-            if (live && d.bi >= kb && d.bj <= kb) {
-                double lc[8], xv[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) lc[r] = T[k * XLD + d.bi * 8 + r];
+            for (int c = 0; c < 8; ++c) xv[c] = xr[d.bj * 8 + c];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) xv[c] = xr[d.bj * 8 + c];
+            for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (d.bi * 8 + r > k) d.R[r][c] -= lc[r] * xv[c];
-            }
+                for (int c = 0; c < 8; ++c) d.R[r][c] -= lc[r] * xv[c];
         }
     }
     __syncthreads();

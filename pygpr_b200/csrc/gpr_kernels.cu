@@ -253,7 +253,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
                   double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
                   double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
     extern __shared__ double smem[];
-    __shared__ double pub[2 * TILE];
+    __shared__ double pub[3 * TILE];
     __shared__ double svec[TILE];
     __shared__ int s_fail;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -261,7 +261,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     double* Lb = L + (long long)b * npad * npad;
     double* Ljj = Lb + ((long long)j * TILE) * npad + j * TILE;
     double* zb = y ? z + (long long)b * npad : nullptr;
-    if (tid == 0) s_fail = 0;
+    if (tid == 0) s_fail = 1 << 30;
 
     // product over the LAST block column only (k-block j-1); blocks 0..j-2 were summed by the look-ahead CTA
     double acc[4][8][2];
@@ -330,7 +330,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
             if (logdet_half) logdet_half[b] = (j == 0 ? 0.0 : logdet_half[b]) + s;
             if (info) {
                 if (j == 0) info[b] = 0;
-                if (s_fail && info[b] == 0) info[b] = j * TILE + s_fail;
+                if (s_fail <= TILE && info[b] == 0) info[b] = j * TILE + s_fail;
             }
         }
     }
