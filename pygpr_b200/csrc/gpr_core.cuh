@@ -33,6 +33,46 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// ---- mbarrier pipeline state -----------------------------------------------------------------------------------
+// full[s]  : completes when all 256 threads' cp.async copies of the chunk in stage s have landed
+//            (cp.async.mbarrier.arrive.noinc, one per thread and phase)
+// empty[s] : completes when all 8 warps have finished reading stage s (one arrive per warp)
+// A running chunk counter g gives stage = g % STAGES and parity = (g / STAGES) & 1 across mainloop calls.
+struct Pipe {
+    unsigned bars;   // shared-space address of 2*STAGES mbarriers: full[0..STAGES), empty[0..STAGES)
+    unsigned g;      // chunks consumed so far by this CTA (identical in every thread)
+};
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// Call once per kernel (all threads), before the first mainloop.
+__device__ __forceinline__ void pipe_init(Pipe& p, unsigned long long* bars_smem) {
+    p.bars = (unsigned)__cvta_generic_to_shared(bars_smem);
+    p.g = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(p.bars + 8 * s, NTHREADS);
+            mbar_init(p.bars + 8 * (STAGES + s), NTHREADS / 32);
+        }
+    }
+    __syncthreads();
+}
+
 // D(8x8) += A(8x4, row) * B(4x8, col):  lane (g=lane/4, t=lane%4) holds A[g][t], B[t][g], C[g][2t..2t+1]
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -63,53 +103,62 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][8][2]) {
 
 // acc += A * B^T over the chunks of s0 then s1.  SAME_AB: the B tile is the A tile (diagonal blocks) and is
 // loaded once.  HOOK gets every landed A chunk tile (used to fuse the forward solve into the Cholesky).
-// Ends with all copies drained and a __syncthreads(), so the caller may reuse `smem` immediately.
+// Ends with a __syncthreads() after the last read, so the caller may reuse `smem` immediately.
 //
-// Schedule (r01 ncu: a burst of 8 LDGSTS per thread right after the barrier backed up the LSU queue and idled the
-// tensor pipe ~12% of every chunk): the copies of chunk c+3 are issued in four slices, one between each k4 block of
-// DMMAs of chunk c, and the A/B fragments of the next k4 block are fetched into a second register set before the
-// current block's 32 DMMAs, so neither LDGSTS back-pressure nor LDS latency sits in front of the tensor pipe.
+// Pipeline (r01 ncu history): v1 issued 8 LDGSTS per thread in a burst after a CTA barrier per chunk -> the LSU queue
+// backed up and the tensor pipe idled ~12 % of every chunk.  v2 sliced the copies between the k4 blocks and double
+// buffered the fragments (DMMA active 78 -> 86 %).  v3 (this): no CTA-wide barrier in the loop at all — per-stage
+// full/empty mbarriers; chunk c+2 is issued during chunk c into the stage freed at chunk c-2, so a warp only ever waits
+// for a stage that every warp left a whole chunk ago, and warps drift apart instead of hitting LDS/LDGSTS in lockstep.
+constexpr int PREFETCH = STAGES - 2;
+
 template <bool SAME_AB, typename HOOK>
-__device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, const Seg& s1, double* smem, HOOK& hook) {
+__device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, const Seg& s1, double* smem, HOOK& hook,
+                                         Pipe& pipe) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2;
     const int n0 = s0.nchunks;
     const int total = n0 + s1.nchunks;
+    const unsigned g0 = pipe.g;
     // per-thread copy coordinates: slice q moves rows (tid>>3) + 32 q, 16-byte column (tid&7)
     const int crow = tid >> 3, ccol = (tid & 7) * 2;
     const long long offA0 = crow * s0.lda + ccol, offB0 = crow * s0.ldb + ccol;
     const long long offA1 = crow * s1.lda + ccol, offB1 = crow * s1.ldb + ccol;
     const int soff = crow * SLD + ccol;
 
-    auto issue_slice = [&](int c, int q) {  // one quarter (32 rows) of chunk c
+    auto issue_slice = [&](int c, int q) {  // one quarter (32 rows) of chunk c; q == 0 first waits for the stage to be free
         if (c < total) {
+            const unsigned gc = g0 + c;
+            const unsigned st = gc % STAGES;
+            if (q == 0) mbar_wait(pipe.bars + 8 * (STAGES + st), ((gc / STAGES) & 1) ^ 1);
             const bool first = c < n0;
             const int lc = first ? c : c - n0;
-            double* sA = smem + (c % STAGES) * STAGE_DOUBLES + soff + q * 32 * SLD;
+            double* sA = smem + st * STAGE_DOUBLES + soff + q * 32 * SLD;
             const double* gA = (first ? s0.A + offA0 + (long long)q * 32 * s0.lda : s1.A + offA1 + (long long)q * 32 * s1.lda) + (long long)lc * KC;
             cp_async16(sA, gA);
             if (!SAME_AB) {
                 const double* gB = (first ? s0.B + offB0 + (long long)q * 32 * s0.ldb : s1.B + offB1 + (long long)q * 32 * s1.ldb) + (long long)lc * KC;
                 cp_async16(sA + TILE * SLD, gB);
             }
+            if (q == 3) cp_async_mbar_arrive(pipe.bars + 8 * st);
         }
     };
 
 #pragma unroll
-    for (int c = 0; c < STAGES - 1; ++c) {
+    for (int c = 0; c < PREFETCH; ++c) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) issue_slice(c, q);
-        cp_async_commit();
     }
 
     const int aoff = (wm * 32 + g) * SLD + t;
     const int boff = (wn * 64 + g) * SLD + t;
     for (int c = 0; c < total; ++c) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        const double* sA = smem + (c % STAGES) * STAGE_DOUBLES;
+        const unsigned gc = g0 + c;
+        const unsigned st = gc % STAGES;
+        mbar_wait(pipe.bars + 8 * st, (gc / STAGES) & 1);
+        const double* sA = smem + st * STAGE_DOUBLES;
         const double* sB = SAME_AB ? sA : sA + TILE * SLD;
         hook.pre(c);
         double fa[2][4], fb[2][8];
@@ -126,16 +175,17 @@ __device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, 
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni) fb[nxt][ni] = sB[boff + ni * 8 * SLD + (kk + 1) * 4];
             }
-            issue_slice(c + STAGES - 1, kk);
+            issue_slice(c + PREFETCH, kk);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[cur][mi], fb[cur][ni]);
         }
-        cp_async_commit();
         hook.post(sA, c);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pipe.bars + 8 * (STAGES + st));
     }
-    cp_async_wait<0>();
+    pipe.g = g0 + total;
     __syncthreads();
 }
 

@@ -253,6 +253,9 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
                   double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
                   double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
     __shared__ double pub[3 * TILE];
     __shared__ double svec[TILE];
     __shared__ int s_fail;
@@ -271,7 +274,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     const double* Arow = Lb + ((long long)j * TILE) * npad + (long long)(j > 0 ? j - 1 : 0) * TILE;
     Seg s0{Arow, npad, Arow, npad, j > 0 ? TILE / KC : 0};
     Seg s1{nullptr, 0, nullptr, 0, 0};
-    mainloop<true>(acc, s0, s1, smem, hook);
+    mainloop<true>(acc, s0, s1, smem, hook, pipe);
     const bool have_part = j >= 2;
     const double* dpart = Lb + ((long long)(j - 1) * TILE) * npad + (long long)j * TILE;  // upper block (j-1, j)
     hook.reduce_to(svec, (have_part && zb) ? zb + (long long)j * TILE : nullptr);
@@ -369,6 +372,9 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
                    const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag, int lookahead,
                    double* __restrict__ z) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
     const int b = blockIdx.y;
     const int nt = npad / TILE;
     double* Lb = L + (long long)b * npad * npad;
@@ -381,7 +387,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
         GemvHook hook;
         hook.init(z ? z + (long long)b * npad : nullptr);
         Seg s0{Arow, npad, Arow, npad, j * (TILE / KC)};
-        mainloop<true>(acc, s0, none, smem, hook);
+        mainloop<true>(acc, s0, none, smem, hook, pipe);
         double* dpart = Lb + ((long long)j * TILE) * npad + (long long)(j + 1) * TILE;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -397,7 +403,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
     double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
     NoHook nh;
     Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
-    mainloop<false>(acc, s0, none, smem, nh);
+    mainloop<false>(acc, s0, none, smem, nh, pipe);
 
     if (GEN) {
         FeatSmem f = carve_feat(smem, dpad);
@@ -439,7 +445,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
     // triangular solve as a product with the inverted diagonal block:  L_ij = Xhat * inv(L_jj)^T
     zero_acc(acc);
     Seg s1{Lij, npad, invdiag + ((long long)b * nt + j) * TILE * TILE, TILE, TILE / KC};
-    mainloop<false>(acc, s1, none, smem, nh);
+    mainloop<false>(acc, s1, none, smem, nh, pipe);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -590,6 +596,9 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
                double* __restrict__ mean, double* __restrict__ var, int want_var, double* __restrict__ scratch,
                int* __restrict__ counter) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
     __shared__ int s_task;
     __shared__ double red[2][2][TILE];  // [mean|var][wn][row]
     const int tid = threadIdx.x;
@@ -636,7 +645,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             __syncthreads();  // V^T columns written by the previous step are visible; staged features are free
             if (want_var && i > 0) {
                 Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
-                mainloop<false>(acc, s0, none, smem, nh);
+                mainloop<false>(acc, s0, none, smem, nh, pipe);
             }
             // K*(test tile, train block i) in smem-staged features
             double* sC = smem;
@@ -667,7 +676,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             __syncthreads();
             zero_acc(acc);
             Seg s1{Vi, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
-            mainloop<false>(acc, s1, none, smem, nh);
+            mainloop<false>(acc, s1, none, smem, nh, pipe);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -820,6 +829,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ invdiagT, int B, int npad,
              int* __restrict__ counter) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
     __shared__ int s_task;
     const int nt = npad / TILE;
     const int ntasks = B * (nt - 1);
@@ -842,7 +854,7 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
             const double* Li = Lb + ((long long)i * TILE) * npad;
             Seg s0{Ujj, TILE, Li + (long long)j * TILE, npad, TILE / KC};
             Seg s1{Urow + (long long)(j + 1) * TILE, npad, Li + (long long)(j + 1) * TILE, npad, (i - j - 1) * (TILE / KC)};
-            mainloop<false>(acc, s0, s1, smem, nh);
+            mainloop<false>(acc, s0, s1, smem, nh, pipe);
             double* Uji = Urow + (long long)i * TILE;
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
@@ -854,7 +866,7 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
             __syncthreads();
             zero_acc(acc);
             Seg s2{Uji, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
-            mainloop<false>(acc, s2, none, smem, nh);
+            mainloop<false>(acc, s2, none, smem, nh, pipe);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -871,6 +883,9 @@ lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdi
                   const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
                   int n, int npad, int d, int dpad, double* __restrict__ partials, int P) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
     __shared__ double sAi[TILE], sAj[TILE];
     __shared__ double wred[NTHREADS / 32][36];
     const int nt = npad / TILE;
@@ -889,7 +904,7 @@ lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdi
     NoHook nh;
     Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, TILE / KC};
     Seg s1{Ui + (long long)(i + 1) * TILE, npad, Uj + (long long)(i + 1) * TILE, npad, (nt - 1 - i) * (TILE / KC)};
-    mainloop<false>(acc, s0, s1, smem, nh);
+    mainloop<false>(acc, s0, s1, smem, nh, pipe);
 
     // epilogue: M = (K^-1 - alpha_i alpha_j^T) o K_se  -> smem tile
     double* Ms = smem;
