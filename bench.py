@@ -149,7 +149,7 @@ def run_reference(args):
     from oracle import pygpr_oracle as orc
     w = workload(args.small)
     nc = w["M_sub"] - 1
-    nc_s, m_s = (2, 256) if not args.small else (4, 256)
+    nc_s, m_s = (2, 1024) if not args.small else (4, 256)
     torch.set_num_threads(os.cpu_count() or 1)
     fit_s, _, fits, (xl, yl, xg, yg, hp_g, hp_l) = cpu_sample(w, m_s, nc_s)
     xs = test_points(m_s, w["d"])
@@ -328,7 +328,7 @@ def main():
                             "cholesky_plus_grad_tflops": (gflops + fit_flops) / (grad_ms + fit_ms) * 1e-9}
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        nc_s, m_s = (2, 256) if not args.small else (4, 256)
+        nc_s, m_s = (2, 1024) if not args.small else (4, 256)
         fit_s, pred_s, _, _ = cpu_sample(w, m_s, nc_s)
         work_full = nc_total * n_l ** 2 + n_g ** 2
         work_s = nc_s * n_l ** 2 + n_g ** 2

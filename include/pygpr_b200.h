@@ -157,6 +157,34 @@ int grbcm_partial(const double* mean_l, const double* var_l, const double* var_g
 int grbcm_finalize(const double* S, const double* mean_g, const double* var_g, int m,
                    double* mu, double* var, double* beta0, double* prec0, void* stream);
 
+/* ---- "next" rows: full predictive covariance and its GRBCM aggregation ------------------- */
+
+/* scratch bytes for gpr_predict_full (holds V^T [B, mpad, npad]) and gpr_potri_batched */
+long long gpr_predict_full_scratch_bytes(int B, int npad, int m);
+long long gpr_potri_scratch_bytes(int B, int npad);
+
+/*
+ * mean, variance AND full predictive covariance  cov[b] = K**(xs,xs) + noise_var_b I - K* K^-1 K*^T   [B, m, m]
+ * Replaces Exact_GP.predict_covar gpr.py:108-120 (and predict(var="full"), gpr.py:86-87).
+ *   as, nrms  scaled test points from gpr_se_scale(xs, hp) ([B, mpad, dpad], [B, mpad]); mpad = ceil(m/128)*128
+ *   noise_var [B] sig_n^2 (K** = cov.kernel(params, xp) includes the white noise, no jitter, gpr.py:110) or NULL
+ */
+int gpr_predict_full(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                     const double* hp, int hp_stride, const double* prior, const double* noise_var, const double* xs,
+                     const double* as, const double* nrms, int B, int n, int npad, int d, int dpad, int m, int mpad,
+                     double* mean, double* var, double* cov, void* scratch, void* stream);
+
+/*
+ * Kinv[b] = (L L^T)^-1 from a factor produced by gpr_potrf_batched (overwrites the block-upper part of L with L^-T).
+ * Replaces tc.cholesky_solve(identity, chol) gr_bcm.py:101-103 and tc.cholesky_inverse gr_bcm.py:112.
+ *   Kinv [B, ldo, ldo], only the leading n x n block is written (both triangles)
+ */
+int gpr_potri_batched(double* L, const double* invdiag, int B, int n, int npad, double* Kinv, int ldo, void* scratch,
+                      void* stream);
+
+/* prec[i,j] = sum_c Kinv[c,i,j] * (beta[c,i] + beta[c,j]) / 2      GRBCM.aggregate_full_covar gr_bcm.py:105-111 */
+int grbcm_full_combine(const double* Kinv, const double* beta, int nc1, int m, double* prec, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,11 @@ SIGNATURES = {
     "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "gpr_predict": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "gpr_lml_grad": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "gpr_predict_full_scratch_bytes": (c_longlong, [_I, _I, _I]),
+    "gpr_potri_scratch_bytes": (c_longlong, [_I, _I]),
+    "gpr_predict_full": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gpr_potri_batched": (c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
+    "grbcm_full_combine": (c_int, [_P, _P, _I, _I, _P, _P]),
     "grbcm_partial": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "grbcm_finalize": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
 }

@@ -594,7 +594,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
                const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
                const double* __restrict__ prior, const double* __restrict__ xs, int B, int n, int npad, int d, int dpad, int m,
                double* __restrict__ mean, double* __restrict__ var, int want_var, double* __restrict__ scratch,
-               int* __restrict__ counter) {
+               int* __restrict__ counter, double* __restrict__ vt_out) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -610,7 +610,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
     double* sT = smem + MAIN_SMEM_BYTES / 8;  // [128 x sld]
     double* nT = sT + TILE * sld;             // [128]
     double* sAl = nT + TILE;                  // [128] alpha block of the current step
-    double* Vt = scratch + (long long)blockIdx.x * TILE * npad;
+    double* Vt = scratch + (long long)blockIdx.x * TILE * npad;   // replaced per task when V^T is kept (vt_out)
     NoHook nh;
     Seg none{nullptr, 0, nullptr, 0, 0};
 
@@ -624,6 +624,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
         const double* hb = hp + (long long)b * hp_stride;
         const double sig2 = hb[0] * hb[0];
         const double* Lb = L + (long long)b * npad * npad;
+        if (vt_out) Vt = vt_out + ((long long)b * mt + ct) * TILE * npad;
 
         // scaled test tile  as = xs * ls_b  (zero rows beyond m, zero cols beyond d) and its norms
         for (int id = tid; id < TILE * dpad; id += NTHREADS) {
@@ -741,7 +742,80 @@ extern "C" int gpr_predict(const double* L, const double* invdiag, const double*
     double* slabs = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
     CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
     predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
-                                                      mean, var, want_var, slabs, counter);
+                                                      mean, var, want_var, slabs, counter, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N1: full predictive covariance  K** - V^T V  (gpr.py:108-120).  The forward substitution of predict_kernel is run
+// with V^T kept in a caller buffer [B, mpad, npad]; a tile kernel then forms  cov = K**(xs,xs) + noise I - V^T V
+// with K** generated on chip from the scaled test points.  API-parity path (O(B m n) memory), not the bench path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+covar_full_kernel(const double* __restrict__ vt, const double* __restrict__ as, const double* __restrict__ nrms,
+                  const double* __restrict__ hp, int hp_stride, const double* __restrict__ noise_var, int m, int mpad, int npad,
+                  int dpad, double* __restrict__ cov) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
+    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    const double* Vb = vt + (long long)b * mpad * npad;
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    Seg s0{Vb + (long long)ti * TILE * npad, npad, Vb + (long long)tj * TILE * npad, npad, npad / KC};
+    mainloop<false>(acc, s0, none, smem, nh, pipe);
+    FeatSmem f = carve_feat(smem, dpad);
+    load_feat_tile(f.sR, f.sld, as + ((long long)b * mpad + ti * TILE) * dpad, dpad);
+    load_feat_tile(f.sC, f.sld, as + ((long long)b * mpad + tj * TILE) * dpad, dpad);
+    cp_async_commit();
+    if (threadIdx.x < TILE) {
+        f.nR[threadIdx.x] = nrms[(long long)b * mpad + ti * TILE + threadIdx.x];
+        f.nC[threadIdx.x] = nrms[(long long)b * mpad + tj * TILE + threadIdx.x];
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const double sig = hp[(long long)b * hp_stride];
+    const double nv = noise_var ? noise_var[b] : 0.0;
+    double* cb = cov + (long long)b * m * m;
+    gen_se_tile(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig * sig, [&](int mi, int ni, int e, double kv) {
+        const long long r = (long long)ti * TILE + acc_row(mi), c = (long long)tj * TILE + acc_col(ni, e);
+        if (r < m && c < m) cb[r * m + c] = ((r == c) ? kv + nv : kv) - acc[mi][ni][e];
+    });
+}
+
+extern "C" long long gpr_predict_full_scratch_bytes(int B, int npad, int m) {
+    const long long mpad = (m + TILE - 1) / TILE * TILE;
+    return 256 + (long long)B * mpad * npad * 8;
+}
+
+extern "C" int gpr_predict_full(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                                const double* hp, int hp_stride, const double* prior, const double* noise_var, const double* xs,
+                                const double* as, const double* nrms, int B, int n, int npad, int d, int dpad, int m, int mpad,
+                                double* mean, double* var, double* cov, void* scratch, void* stream) {
+    ARG_CHECK(L && invdiag && a && nrm && alpha && hp && prior && xs && as && nrms && mean && var && cov && scratch);
+    ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
+    ARG_CHECK(mpad % TILE == 0 && mpad >= m && mpad - m < TILE);
+    const long long smem = predict_smem_bytes(dpad);
+    if (smem > 227 * 1024 || feat_smem_bytes(dpad) > MAIN_SMEM_BYTES)
+        return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused prediction%s (dpad=%lld)", "", dpad);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(opt_in_smem(predict_kernel, (int)smem));
+    CUDA_TRY(opt_in_smem(covar_full_kernel, MAIN_SMEM_BYTES));
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    const int mt = mpad / TILE;
+    const long long ntasks = (long long)B * mt;
+    const int grid = (int)(ntasks < sms ? ntasks : sms);
+    int* counter = reinterpret_cast<int*>(scratch);
+    double* vt = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+    CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
+    predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
+                                                      mean, var, 1, vt, counter, vt);
+    covar_full_kernel<<<dim3(mt, mt, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(vt, as, nrms, hp, hp_stride, noise_var, m, mpad, npad, dpad, cov);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }
@@ -1028,6 +1102,90 @@ extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, c
     lauum_grad_kernel<<<dim3(ntiles, B), NTHREADS, smem, st>>>(L, invdiagT, a, nrm, alpha, hp, hp_stride, n, npad, d, dpad,
                                                                partials, P);
     grad_finalize_kernel<<<B, ((P + 31) / 32) * 32, 0, st>>>(partials, ntiles, P, hp, hp_stride, d, grad);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N1: explicit inverse from the Cholesky factor (tc.cholesky_solve(identity) / cholesky_inverse, gr_bcm.py:101-112)
+//   gpr_potri_batched = transpose_invdiag + trtri_kernel (U = L^-T into the block-upper part of L) + lauum_store_kernel
+//   (K^-1 = U U^T, both triangles written).  grbcm_full_combine: prec = sum_c Kinv_c o (beta_c[i] + beta_c[j]) / 2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+lauum_store_kernel(const double* __restrict__ L, const double* __restrict__ invdiagT, int n, int npad, double* __restrict__ out,
+                   int ldo) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
+    const int nt = npad / TILE;
+    const int b = blockIdx.y;
+    int ti = blockIdx.x, i = 0;
+    while (ti >= i + 1) { ti -= i + 1; ++i; }
+    const int j = ti;
+    const double* Lb = L + (long long)b * npad * npad;
+    const double* Uii = invdiagT + ((long long)b * nt + i) * TILE * TILE;
+    const double* Ui = Lb + ((long long)i * TILE) * npad;
+    const double* Uj = Lb + ((long long)j * TILE) * npad;
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, TILE / KC};
+    Seg s1{Ui + (long long)(i + 1) * TILE, npad, Uj + (long long)(i + 1) * TILE, npad, (nt - 1 - i) * (TILE / KC)};
+    mainloop<false>(acc, s0, s1, smem, nh, pipe);
+    double* ob = out + (long long)b * ldo * ldo;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long r = (long long)i * TILE + acc_row(mi), c = (long long)j * TILE + acc_col(ni, e);
+                if (r < n && c < n) {
+                    ob[r * ldo + c] = acc[mi][ni][e];
+                    if (i != j) ob[c * ldo + r] = acc[mi][ni][e];
+                }
+            }
+}
+
+extern "C" long long gpr_potri_scratch_bytes(int B, int npad) { return 256 + (long long)B * (npad / TILE) * TILE * TILE * 8; }
+
+extern "C" int gpr_potri_batched(double* L, const double* invdiag, int B, int n, int npad, double* Kinv, int ldo, void* scratch,
+                                 void* stream) {
+    ARG_CHECK(L && invdiag && Kinv && scratch && B > 0 && n > 0 && npad % TILE == 0 && npad >= n && ldo >= n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    int* counter = reinterpret_cast<int*>(scratch);
+    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+    CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
+    transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
+    if (nt > 1) {
+        CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
+        int sms = gpr_device_sm_count();
+        if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+        const long long ntasks = (long long)B * (nt - 1);
+        trtri_kernel<<<(int)(ntasks < sms ? ntasks : sms), NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, counter);
+    }
+    CUDA_TRY(opt_in_smem(lauum_store_kernel, MAIN_SMEM_BYTES));
+    lauum_store_kernel<<<dim3(nt * (nt + 1) / 2, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiagT, n, npad, Kinv, ldo);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+__global__ void grbcm_full_combine_kernel(const double* __restrict__ Kinv, const double* __restrict__ beta, int nc1, int m,
+                                          double* __restrict__ prec) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)m * m) return;
+    const int i = idx / m, j = idx % m;
+    double s = 0.0;
+    for (int c = 0; c < nc1; ++c)
+        s += Kinv[(long long)c * m * m + idx] * (0.5 * (beta[(long long)c * m + i] + beta[(long long)c * m + j]));  // gr_bcm.py:107-111
+    prec[idx] = s;
+}
+
+extern "C" int grbcm_full_combine(const double* Kinv, const double* beta, int nc1, int m, double* prec, void* stream) {
+    ARG_CHECK(Kinv && beta && prec && nc1 > 0 && m > 0);
+    grbcm_full_combine_kernel<<<(unsigned)(((long long)m * m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Kinv, beta, nc1, m, prec);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }

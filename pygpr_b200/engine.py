@@ -263,3 +263,80 @@ def grbcm_finalize(S: torch.Tensor, mean_g: torch.Tensor, var_g: torch.Tensor, w
     _lib.call("grbcm_finalize", _p(S), _p(mean_g), _p(var_g), m, _p(mu), _p(var), _p(beta0), _p(prec0), _stream())
     _count(1)
     return mu, var, beta0, prec0
+
+
+# ---- "next" rows: full predictive covariance and its GRBCM aggregation -------------------------------
+def predict_full(st: FitState, xs: torch.Tensor, cov=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """mean [B, m] and full predictive covariance [B, m, m] = K** - K* K^-1 K*^T   (gpr.py:108-120).
+
+    K** = cov.kernel(params, xp) includes the white noise on its diagonal (no jitter), gpr.py:110.
+    """
+    assert st.alpha is not None
+    m = xs.shape[0]
+    dev = xs.device
+    mpad = round_up(m, TILE)
+    as_, nrms = scale_inputs(xs, st.hp, st.B, mpad)
+    noise_var = (st.hp[:, st.d + 1] * st.hp[:, st.d + 1]).contiguous() if st.has_noise else None
+    mean = torch.empty(st.B, m, dtype=F64, device=dev)
+    var = torch.empty(st.B, m, dtype=F64, device=dev)
+    covm = torch.empty(st.B, m, m, dtype=F64, device=dev)
+    scratch = torch.empty(int(_lib.load().gpr_predict_full_scratch_bytes(st.B, st.npad, m)), dtype=torch.uint8, device=dev)
+    _lib.call("gpr_predict_full", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
+              _p(st.prior), _p(noise_var), _p(xs), _p(as_), _p(nrms), st.B, st.n, st.npad, st.d, st.dpad, m, mpad,
+              _p(mean), _p(var), _p(covm), _p(scratch), _stream())
+    _count(2)
+    return mean, covm
+
+
+def spd_inverse(mats: torch.Tensor) -> torch.Tensor:
+    """Batched inverse of SPD matrices [B, m, m] through the library's Cholesky + potri
+    (tc.cholesky + tc.cholesky_solve(identity) / tc.cholesky_inverse, gr_bcm.py:101-103,112)."""
+    B, m, _ = mats.shape
+    mpad = round_up(m, TILE)
+    buf = torch.zeros(B, mpad, mpad, dtype=F64, device=mats.device)
+    buf[:, :m, :m] = mats
+    if mpad > m:
+        idx = torch.arange(m, mpad, device=mats.device)
+        buf[:, idx, idx] = 1.0
+    invdiag, _, _, _, info = potrf_inplace(buf)
+    bad = torch.nonzero(info)
+    if bad.numel():
+        raise torch.linalg.LinAlgError("cholesky: matrix %d is not positive-definite (leading minor %d)" %
+                                       (int(bad[0, 0]), int(info[int(bad[0, 0])])))
+    out = torch.empty(B, m, m, dtype=F64, device=mats.device)
+    scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(B, mpad)), dtype=torch.uint8, device=mats.device)
+    _lib.call("gpr_potri_batched", _p(buf), _p(invdiag), B, m, mpad, _p(out), m, _p(scratch), _stream())
+    _count(3)
+    return out
+
+
+def grbcm_aggregate_full(model, ys_g, covars_g, ys_l, covars_l):
+    """GRBCM.aggregate(var="full") + aggregate_full_covar (gr_bcm.py:99-114,116-149), experts possibly sharded."""
+    from . import dist as gdist
+    from .covar import _back
+    out_like = ys_g
+    mean_g = _dev(ys_g).reshape(-1)
+    m = mean_g.shape[0]
+    cov_g = _dev(covars_g).reshape(m, m)
+    mean_l = _dev(ys_l).reshape(-1, m)
+    cov_l = _dev(covars_l).reshape(-1, m, m)
+    var_g = torch.diagonal(cov_g).contiguous()                                   # gr_bcm.py:122
+    var_l = torch.diagonal(cov_l, dim1=-2, dim2=-1).contiguous()                 # gr_bcm.py:123
+    S, brow, prow = grbcm_partial(mean_l, var_l, var_g, model.expert_offset, want_rows=True)
+    gdist.all_reduce_sum_(S, model.group)
+    _, _, b0, p0 = grbcm_finalize(S, mean_g, var_g, want_rows=True)
+    model.beta = _back(torch.cat((b0[None], brow)), out_like)
+    model.prec = _back(torch.cat((p0[None], prow)), out_like)
+    # prec = sum_c Kinv_c o (beta_c[i] + beta_c[j]) / 2 ; the communication expert's term is added by the rank owning expert 0
+    own_g = model.expert_offset == 0
+    mats = torch.cat((cov_g[None], cov_l)) if own_g else cov_l
+    betas = torch.cat((b0[None], brow)) if own_g else brow
+    kinv = spd_inverse(mats.contiguous())                                        # gr_bcm.py:100-103
+    prec = torch.empty(m, m, dtype=F64, device=mean_g.device)
+    _lib.call("grbcm_full_combine", _p(kinv), _p(betas.contiguous()), betas.shape[0], m, _p(prec), _stream())
+    _count(1)
+    gdist.all_reduce_sum_(prec, model.group)
+    covars = spd_inverse(prec[None])[0]                                          # gr_bcm.py:112
+    total = S[2] + mean_g * p0 * b0                                              # (ys * prec * beta).sum(0), gr_bcm.py:147
+    mu = total * torch.diagonal(covars)
+    return _back(mu, out_like), _back(covars, out_like)
