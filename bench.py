@@ -307,7 +307,9 @@ def main():
 
     pred_flops_kernel = nc_loc * float(n_l) ** 2 * m          # algorithmic N^2 per test point per expert
     roof = {"bound": "tensor", "kernel": "predict_kernel", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
-            "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf, "traffic": None,
+            "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf,
+            # dram__bytes_read+write of this launch from profiles/r01_ncu_predict_kernel_bench_scale.json (valid for the default 1-GPU config)
+            "traffic": 3.123e12 if (world == 1 and not args.small and m == 4096) else None,
             "peak_source": "cuBLAS dgemm 8192^3 (A B^T) measured in this run on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
             "kernel_ms": kern_ms, "flops_per_launch": pred_flops_kernel}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -185,6 +185,15 @@ int gpr_potri_batched(double* L, const double* invdiag, int B, int n, int npad, 
 /* prec[i,j] = sum_c Kinv[c,i,j] * (beta[c,i] + beta[c,j]) / 2      GRBCM.aggregate_full_covar gr_bcm.py:105-111 */
 int grbcm_full_combine(const double* Kinv, const double* beta, int nc1, int m, double* prec, void* stream);
 
+/* ---- "next" row N3: data partitioning (sampler.py) -------------------------------------------------------- */
+/*
+ * D[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  (GEMM form, cross term on DMMA) — euclidean_dist sampler.py:94-100, used by
+ * cluster_samples / MATERN1.cluster_samples (nearest-centre assignment, sampler.py:62-80,103-119).
+ *   ax,nx / ay,ny  from gpr_se_scale with unit length-scales ([1,npad,dpad],[1,npad]);  D [nx_rows, ny_rows]
+ */
+int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay, const double* ny, int npady,
+                int nx_rows, int ny_rows, int dpad, double* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,7 @@ SIGNATURES = {
     "gpr_predict_full": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpr_potri_batched": (c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
     "grbcm_full_combine": (c_int, [_P, _P, _I, _I, _P, _P]),
+    "gpr_sq_dist": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "grbcm_partial": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "grbcm_finalize": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
 }

@@ -213,7 +213,8 @@ __device__ __forceinline__ void load_feat_tile(double* s, int sld, const double*
 
 // Squared-exponential tile in GEMM form, covar.py:102-149:  sqd = (|aR|^2 + |aC|^2) - 2 aR.aC ;  k = sig2 exp(-sqd)
 // The cross term runs on DMMA.  f(mi, ni, e, kval) is called for every accumulator element of the thread.
-template <typename F>
+// RAW: hand the squared distance itself to f (no exponential).
+template <bool RAW = false, typename F>
 __device__ __forceinline__ void gen_se_tile(const double* sR, const double* sC, int sld, const double* nR, const double* nC,
                                             int dpad, double sig2, F&& f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -238,8 +239,9 @@ __device__ __forceinline__ void gen_se_tile(const double* sR, const double* sC, 
         const double nc0 = nC[c0], nc1 = nC[c0 + 1];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
-            f(mi, ni, 0, sig2 * exp(-(-2.0 * G[mi][0] + (nr[mi] + nc0))));
-            f(mi, ni, 1, sig2 * exp(-(-2.0 * G[mi][1] + (nr[mi] + nc1))));
+            const double d0 = -2.0 * G[mi][0] + (nr[mi] + nc0), d1 = -2.0 * G[mi][1] + (nr[mi] + nc1);
+            f(mi, ni, 0, RAW ? d0 : sig2 * exp(-d0));
+            f(mi, ni, 1, RAW ? d1 : sig2 * exp(-d1));
         }
     }
 }

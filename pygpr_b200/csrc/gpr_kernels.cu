@@ -105,6 +105,7 @@ static inline int feat_smem_bytes(int dpad) { return (2 * TILE * feat_sld(dpad) 
 // rows from (aR, nrmR) tile tr, cols from (aC, nrmC) tile tc; out[b][row][col] with leading dim ld.
 //   mode 0 (symmetric build): diag_add on row==col, identity padding up to `ldlim` when pad_identity
 //   mode 1 (cross): plain
+//   mode 2 (squared distance): |aR|^2 + |aC|^2 - 2 aR.aC without the exponential (sampler.py:94-100)
 __global__ void __launch_bounds__(NTHREADS) se_tile_kernel(const double* __restrict__ aR, const double* __restrict__ nrmR,
                                                            int rpad, const double* __restrict__ aC,
                                                            const double* __restrict__ nrmC, int cpad,
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(NTHREADS) se_tile_kernel(const double* __restr
     double* ob = out + (long long)b * out_bstride;
     const long long lim_r = (mode == 0 && pad_identity) ? ld : nrows;
     const long long lim_c = (mode == 0 && pad_identity) ? ld : ncols;
-    gen_se_tile(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig2, [&](int mi, int ni, int e, double kv) {
+    auto store = [&](int mi, int ni, int e, double kv) {
         const long long r = (long long)tr * TILE + acc_row(mi);
         const long long c = (long long)tc * TILE + acc_col(ni, e);
         if (r < nrows && c < ncols) {
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(NTHREADS) se_tile_kernel(const double* __restr
         } else if (r < lim_r && c < lim_c) {
             ob[r * ld + c] = (r == c) ? 1.0 : 0.0;
         }
-    });
+    };
+    if (mode == 2) gen_se_tile<true>(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig2, store);
+    else gen_se_tile<false>(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig2, store);
 }
 
 extern "C" int gpr_se_build(const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
@@ -171,6 +174,23 @@ extern "C" int gpr_se_cross(const double* as, const double* nrms, int mpad, cons
     dim3 grid((n + TILE - 1) / TILE, (m + TILE - 1) / TILE, B);
     se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(as, nrms, mpad, a, nrm, npad, hp, hp_stride, nullptr, m, n,
                                                                    dpad, Ks, n, (long long)m * n, 1, 0, 0);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// Squared Euclidean distances in GEMM form, D[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   (sampler.py:94-100, N3)
+extern "C" int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay, const double* ny, int npady, int nx_rows,
+                           int ny_rows, int dpad, double* D, void* stream) {
+    ARG_CHECK(ax && nx && ay && ny && D && nx_rows > 0 && ny_rows > 0 && npadx % TILE == 0 && npady % TILE == 0 && dpad % 4 == 0);
+    const int smem = feat_smem_bytes(dpad);
+    if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the distance tile%s (dpad=%lld)", "", dpad);
+    CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
+    static const double one_host = 1.0;
+    (void)one_host;
+    dim3 grid((ny_rows + TILE - 1) / TILE, (nx_rows + TILE - 1) / TILE, 1);
+    // hp is only read for sig (unused in raw mode); pass nx as a valid device pointer
+    se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(ax, nx, npadx, ay, ny, npady, nx, 0, nullptr, nx_rows, ny_rows, dpad,
+                                                                   D, ny_rows, 0, 2, 0, 0);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }

@@ -85,6 +85,66 @@ class GRBCM(GPR):
             ys_l = ys_l.reshape(1, -1)
         return self.aggregate(ys_g, covars_g, ys_l, covars_l, var=var)  # gr_bcm.py:155
 
+    # ---- hyper-parameter training --------------------------------------------------------------
+    def train(self, method="CG", jac=True):
+        """Per-expert maximum-likelihood training: one scipy minimisation per local expert, then the communication expert.
+
+        The reference's ``train`` / ``cost_fun_*`` (gr_bcm.py:36-97) call names that do not exist and cannot run; this is
+        what they were written to do, on the working ``MLE``.  Results land in ``gpl.params[cen]`` / ``gpg.params``, the final
+        NLML and gradient in ``gpl.llhd, gpl.jac_llhd, gpg.llhd, gpg.jac_llhd``; returns the communication expert's result.
+        """
+        import scipy.optimize as opt
+        from .loss import MLE
+        gpl, gpg = self.gpl, self.gpg
+        hp = torch.clone(gpl.params).reshape(self.nc, -1)
+        gpl.llhd = torch.empty(self.nc)
+        gpl.jac_llhd = torch.empty_like(hp)
+
+        def fit_one(model, start):
+            loss = MLE(model)
+            fun = loss.loss_and_grad if jac else loss.loss
+            res = opt.minimize(fun, start.detach().cpu().numpy(), jac=True if jac else None, method=method)
+            fin_l, fin_j = loss.loss_and_grad(res.x)
+            return res, float(fin_l), torch.from_numpy(fin_j.copy())
+
+        for cen in range(self.nc):
+            res, l, j = fit_one(Exact_GP(gpl.x[cen], gpl.y[cen], gpl.cov), hp[cen])
+            hp[cen] = torch.from_numpy(res.x)
+            gpl.llhd[cen] = l
+            gpl.jac_llhd[cen] = j
+        gpl.set_params(hp)
+        res, l, j = fit_one(Exact_GP(gpg.x, gpg.y, gpg.cov), gpg.params)
+        gpg.set_params(torch.from_numpy(res.x))
+        gpg.llhd, gpg.jac_llhd = torch.tensor(l), j
+        return res
+
+    def train_batched(self, steps: int = 10, eps: float = 1e-4):
+        """B200-native training loop: ALL local experts (and the communication expert) take a quadratic-fit gradient
+        step per iteration, ``theta <- theta - gamma J`` with ``gamma`` from ``get_learn_rate`` (hp_update.py:6-28), i.e. one
+        batched ``loss_and_grad`` + two batched ``loss`` evaluations per step for the whole committee.  Per-expert
+        hyper-parameters need no collective; returns the NLML history [steps, nc]."""
+        import numpy as np
+        from .loss import MLE
+        hist = []
+        for model in (self.gpl, self.gpg):
+            loss = MLE(model)
+            for _ in range(steps):
+                theta = model.params.detach().cpu().numpy()
+                f0, J = loss.loss_and_grad(theta)                       # the three evaluations of hp_update.py:14-17
+                f_minus = loss.loss(theta - eps * J)
+                f_plus = loss.loss(theta + eps * J)
+                slope = (f_minus - f_plus) / (2.0 * eps)
+                curv = (f_minus + f_plus - 2 * f0) / (2.0 * eps ** 2)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    gamma = np.asarray(-0.5 * (slope / curv))           # hp_update.py:22
+                step = gamma[..., None] * J
+                # a non-convex parabola (gamma <= 0 or not finite) gives no usable step: leave that expert where it is
+                ok = np.isfinite(step).all(-1, keepdims=True) & (gamma[..., None] > 0)
+                model.set_params(torch.from_numpy(theta - np.where(ok, step, 0.0)))
+                if model is self.gpl:
+                    hist.append(np.array(f0, copy=True))
+        return np.stack(hist) if hist else np.zeros((0, self.nc))
+
     def gather_weights(self):
         """(beta, prec) for ALL experts [nc_total+1, m] when sharded (all-gather of the local rows)."""
         if not self.sharded:
@@ -97,6 +157,75 @@ class GRBCM(GPR):
             td = engine._dev(t)
             out.append(_back(torch.cat((td[:1], gdist.all_gather_rows(td[1:].contiguous(), counts, self.group))), t))
         return tuple(out)
+
+
+class GRBCM_MLE:
+    """Summed negative log marginal likelihood of a GRBCM at ONE shared hyper-parameter vector (BASELINE
+    config 5: "GRBCM hyperparameter training loop (summed LML gradient allreduce)").
+
+        loss(theta) = NLML_g(theta) + sum_i NLML_i(theta)         theta: ndarray [P]
+
+    Same duck type as ``Loss`` (``loss / grad / loss_and_grad`` on numpy, ``loss_value / grad_value``, ``model`` with
+    ``params / set_params``), so ``CG``, ``CG_Quad``, ``BFGS_Quad``, ``Nelder_Mead`` and ``get_learn_rate`` drive it unchanged.
+    Local experts are evaluated in batches of ``chunk`` (0 = all at once) to bound HBM; with experts sharded over ranks
+    the ``[1+P]`` partial sums are all-reduced (NCCL), the replicated communication expert is added once.
+    """
+
+    def __init__(self, model: "GRBCM", chunk: int = 0) -> None:
+        self.grbcm = model
+        self.model = self                     # optimisers call loss.model.params / set_params
+        self.chunk = chunk
+        self.loss_value = NotImplemented
+        self.grad_value = NotImplemented
+        self.params = torch.clone(model.gpg.params)
+
+    def set_params(self, params) -> None:
+        """Write the shared vector into every expert and mark the factorisations stale."""
+        self.params = torch.clone(params)
+        g = self.grbcm
+        g.gpg.set_params(params)
+        g.gpl.set_params(params.reshape(1, -1).repeat(g.nc, 1))
+
+    def _eval(self, theta, want_grad: bool):
+        import numpy as np
+        from .loss import MLE
+        g = self.grbcm
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        P = theta.shape[-1]
+        acc = np.zeros(1 + P)
+        step = self.chunk if self.chunk > 0 else max(g.nc, 1)
+        for s in range(0, g.nc, step):
+            e = min(s + step, g.nc)
+            part = MLE(Exact_GP(g.gpl.x[s:e], g.gpl.y[s:e], g.gpl.cov))
+            th = np.tile(theta, (e - s, 1))
+            if want_grad:
+                l, j = part.loss_and_grad(th)
+                acc[0] += np.sum(l)
+                acc[1:] += np.sum(np.reshape(j, (e - s, P)), axis=0)
+            else:
+                acc[0] += np.sum(part.loss(th))
+        t = torch.from_numpy(acc)
+        if gdist.is_dist():
+            t = engine._dev(t)
+            gdist.all_reduce_sum_(t, g.group)         # [1+P] doubles
+            acc = t.cpu().numpy()
+        glob = MLE(g.gpg)
+        if want_grad:
+            l, j = glob.loss_and_grad(theta)
+            return float(acc[0] + l), acc[1:] + j
+        return float(acc[0] + glob.loss(theta)), None
+
+    def loss(self, params):
+        self.loss_value, _ = self._eval(params, False)
+        return self.loss_value
+
+    def grad(self, params):
+        _, self.grad_value = self._eval(params, True)
+        return self.grad_value
+
+    def loss_and_grad(self, params):
+        self.loss_value, self.grad_value = self._eval(params, True)
+        return (self.loss_value, self.grad_value)
 
 
 def log_likelihood_batched(x, y, hp, cov, **kwargs):
