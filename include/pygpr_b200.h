@@ -105,7 +105,10 @@ int gpr_se_kernel_grad(const double* Kse, const double* x, const double* hp, int
 int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
                       const double* diag_add, int B, int n, int npad, int dpad,
                       double* invdiag, const double* y, double* z, double* logdet_half, double* zz,
-                      int* info, void* stream);
+                      int* info, void* work, void* stream);
+/* bytes of `work` for gpr_potrf_batched (split-K slots + counters used when a launch has fewer tiles than SMs);
+ * work == NULL is allowed and disables the split (slower for few experts, same results up to summation order) */
+long long gpr_potrf_work_bytes(int B, int npad);
 
 /*
  * alpha = L^-T z  (backward half of cholesky_solve, gpr.py:70-72).  HBM-bound: reads L once.

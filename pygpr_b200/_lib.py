@@ -27,7 +27,8 @@ SIGNATURES = {
     "gpr_se_build": (c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "gpr_se_cross": (c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "gpr_se_kernel_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gpr_potrf_work_bytes": (c_longlong, [_I, _I]),
     "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "gpr_predict": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "gpr_lml_grad": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),

@@ -433,4 +433,42 @@ __device__ __forceinline__ void trtri_reg(double* T, double* pub, DiagBlock& d) 
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split-K with a last-arriver fix-up, for launches that have fewer tiles than SMs (few experts, late block columns).
+// Each of the S CTAs of a tile multiplies a slice of the k-range, parks its 128x128 partial in a slot, and bumps the
+// tile's counter; the CTA that observes S-1 sums all S slots IN PART ORDER (bit-reproducible whichever CTA it is) and
+// carries on with the tile's epilogue.  No CTA ever waits for another one.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool splitk_combine(double (&acc)[4][8][2], double* slots, int part, int S, int* counter, int* s_flag) {
+    double* mine = slots + (long long)part * TILE * TILE;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            __stcg(reinterpret_cast<double2*>(mine + acc_row(mi) * TILE + acc_col(ni, 0)), make_double2(acc[mi][ni][0], acc[mi][ni][1]));
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(counter, 1);
+        *s_flag = (old == S - 1);
+        if (old == S - 1) *counter = 0;   // ready for the next launch
+    }
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    zero_acc(acc);
+    for (int p = 0; p < S; ++p) {
+        const double* sp = slots + (long long)p * TILE * TILE;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(sp + acc_row(mi) * TILE + acc_col(ni, 0)));
+                acc[mi][ni][0] += v.x;
+                acc[mi][ni][1] += v.y;
+            }
+    }
+    return true;
+}
+
 }  // namespace gpr

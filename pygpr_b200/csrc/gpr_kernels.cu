@@ -390,24 +390,45 @@ template <bool GEN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
                    const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag, int lookahead,
-                   double* __restrict__ z) {
+                   double* __restrict__ z, int S, double* __restrict__ sk_slots, double* __restrict__ sk_gemv,
+                   int* __restrict__ sk_counters) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
+    __shared__ int s_flag;
     Pipe pipe;
     pipe_init(pipe, pipe_bars);
     const int b = blockIdx.y;
     const int nt = npad / TILE;
+    const int ntile_x = gridDim.x / S;                 // row tiles (+ the look-ahead tile) in this launch
+    const int tx = blockIdx.x / S, part = blockIdx.x % S;
+    // this CTA's slice of the j k-blocks
+    const int kb0 = (int)((long long)part * j / S), kb1 = (int)((long long)(part + 1) * j / S);
+    double* slots = sk_slots + ((long long)b * ntile_x + tx) * S * TILE * TILE;
+    int* counter = sk_counters + (long long)b * nt + tx;
     double* Lb = L + (long long)b * npad * npad;
     double acc[4][8][2];
     zero_acc(acc);
     Seg none{nullptr, 0, nullptr, 0, 0};
 
-    if (lookahead && blockIdx.x == gridDim.x - 1) {
-        const double* Arow = Lb + ((long long)(j + 1) * TILE) * npad;
+    if (lookahead && tx == ntile_x - 1) {
+        const double* Arow = Lb + ((long long)(j + 1) * TILE) * npad + (long long)kb0 * TILE;
         GemvHook hook;
-        hook.init(z ? z + (long long)b * npad : nullptr);
-        Seg s0{Arow, npad, Arow, npad, j * (TILE / KC)};
+        hook.init(z ? z + (long long)b * npad + (long long)kb0 * TILE : nullptr);
+        Seg s0{Arow, npad, Arow, npad, (kb1 - kb0) * (TILE / KC)};
         mainloop<true>(acc, s0, none, smem, hook, pipe);
+        double* zdst = z ? z + (long long)b * npad + (long long)(j + 1) * TILE : nullptr;
+        if (S > 1) {
+            double* gv = sk_gemv + (long long)b * S * TILE;
+            if (z) hook.reduce_to(gv + part * TILE, nullptr);
+            if (!splitk_combine(acc, slots, part, S, counter, &s_flag)) return;
+            if (z && threadIdx.x < TILE) {
+                double v = 0.0;
+                for (int p = 0; p < S; ++p) v += __ldcg(gv + p * TILE + threadIdx.x);
+                zdst[threadIdx.x] = v;
+            }
+        } else if (z) {
+            hook.reduce_to(zdst, nullptr);
+        }
         double* dpart = Lb + ((long long)j * TILE) * npad + (long long)(j + 1) * TILE;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -415,15 +436,16 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
             for (int ni = 0; ni < 8; ++ni)
                 *reinterpret_cast<double2*>(dpart + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        if (z) hook.reduce_to(z + (long long)b * npad + (long long)(j + 1) * TILE, nullptr);
         return;
     }
 
-    const int i = j + 1 + blockIdx.x;
+    const int i = j + 1 + tx;
     double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
     NoHook nh;
-    Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
+    Seg s0{Lb + ((long long)i * TILE) * npad + (long long)kb0 * TILE, npad, Lb + ((long long)j * TILE) * npad + (long long)kb0 * TILE, npad,
+           (kb1 - kb0) * (TILE / KC)};
     mainloop<false>(acc, s0, none, smem, nh, pipe);
+    if (S > 1 && !splitk_combine(acc, slots, part, S, counter, &s_flag)) return;
 
     if (GEN) {
         FeatSmem f = carve_feat(smem, dpad);
@@ -474,9 +496,41 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
                 make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
+// Split factor for a launch of `tiles` equal-depth tiles of `depth` k-blocks.  Two effects are traded: (i) a launch with
+// fewer tiles than SMs leaves SMs idle, (ii) a launch of a few waves wastes up to one wave in the ragged tail.  Cost
+// model in tile units (one 128^3 product): waves * (depth/S + epilogue) + fix-up; S = 1..8, slices keep >= 1 block.
+static int choose_split(long long tiles, int depth, int sms, long long slot_cap) {
+    if (depth < 2 || tiles >= 8LL * sms) return 1;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int S = 1; S <= 8 && S <= depth; ++S) {
+        if (S > 1 && tiles * S > slot_cap) break;
+        const double waves = (double)((tiles * S + sms - 1) / sms);
+        const double cost = waves * ((double)depth / S + 1.1) + (S > 1 ? 0.4 + 0.08 * S : 0.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = S; }
+    }
+    if (tiles < sms) {  // far below one wave: allow deeper splits, ~2 CTAs per SM
+        long long s = (2LL * sms) / tiles;
+        if (s > depth) s = depth;
+        if (s > 32) s = 32;
+        if (s > best && tiles * s <= slot_cap) best = (int)s;
+    }
+    return best;
+}
+static inline long long align256(long long v) { return (v + 255) / 256 * 256; }
+// workspace layout: [counters: B*nt ints][gemv slots: B*32*128 doubles][tile slots: 12*sms + B*nt tiles of 128x128 doubles]
+static long long potrf_slot_tiles(int B, int nt, int sms) { return 12LL * sms + (long long)B * nt; }
+
+extern "C" long long gpr_potrf_work_bytes(int B, int npad) {
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int nt = npad / TILE;
+    return align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
+}
+
 extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
                                  const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y,
-                                 double* z, double* logdet_half, double* zz, int* info, void* stream) {
+                                 double* z, double* logdet_half, double* zz, int* info, void* work, void* stream) {
     ARG_CHECK(L && invdiag);
     ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n);
     ARG_CHECK(!gen || (a && nrm && hp && dpad > 0 && dpad % 4 == 0));
@@ -484,6 +538,17 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
     ARG_CHECK(!zz || y);
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = npad / TILE;
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    int* counters = nullptr;
+    double* gemv = nullptr;
+    double* slots = nullptr;
+    if (work) {  // without a workspace the factorisation runs unsplit
+        counters = reinterpret_cast<int*>(work);
+        gemv = reinterpret_cast<double*>(reinterpret_cast<char*>(work) + align256((long long)B * nt * 4));
+        slots = reinterpret_cast<double*>(reinterpret_cast<char*>(gemv) + align256((long long)B * 32 * TILE * 8));
+        CUDA_TRY(cudaMemsetAsync(counters, 0, (size_t)B * nt * 4, st));
+    }
     int smem_diag = MAIN_SMEM_BYTES, smem_panel = MAIN_SMEM_BYTES;
     if (gen) {
         const int fb = feat_smem_bytes(dpad);
@@ -506,13 +571,15 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
                                                                       invdiag, y, z, logdet_half, zz, info);
         if (j + 1 < nt) {
             const int lookahead = (j >= 1) ? 1 : 0;
-            dim3 grid(nt - 1 - j + lookahead, B);
+            const int ntile_x = nt - 1 - j + lookahead;
+            const int S = work ? choose_split((long long)B * ntile_x, j, sms, potrf_slot_tiles(B, nt, sms)) : 1;
+            dim3 grid(ntile_x * S, B);
             if (gen)
                 potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag,
-                                                                             lookahead, y ? z : nullptr);
+                                                                             lookahead, y ? z : nullptr, S, slots, gemv, counters);
             else
                 potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag,
-                                                                              lookahead, y ? z : nullptr);
+                                                                              lookahead, y ? z : nullptr, S, slots, gemv, counters);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -972,6 +1039,103 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
     }
 }
 
+// Column mode of U = L^-T for FEW experts: one launch per block column i, tiles j < i, k-range of i-j blocks split so that
+// every CTA gets about `target` blocks (split-K with last-arriver fix-up).  Task mode above has a serial chain of
+// O(nt^2) tiles per row; with B*(nt-1) < 2*SMs tasks that chain, not the SM count, sets the time (B=1, n=16384: 140 ms).
+__global__ void __launch_bounds__(NTHREADS, 1)
+trtri_col_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ invdiagT, int npad, int i,
+                 int target, double* __restrict__ sk_slots, int* __restrict__ sk_counters, int slots_per_expert) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    __shared__ int s_flag;
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
+    const int nt = npad / TILE;
+    const int b = blockIdx.y;
+    // blockIdx.x -> (row tile j, part, S_j); slot offset = number of parts of the tiles before j
+    int bx = blockIdx.x, j = 0, S = 1, slot_off = 0;
+    for (; j < i; ++j) {
+        S = (i - j + target - 1) / target;
+        if (bx < S) break;
+        bx -= S;
+        slot_off += S;
+    }
+    const int part = bx, depth = i - j;
+    const int q0 = (int)((long long)part * depth / S), q1 = (int)((long long)(part + 1) * depth / S);
+    double* Lb = L + (long long)b * npad * npad;
+    const double* Ujj = invdiagT + ((long long)b * nt + j) * TILE * TILE;
+    double* Urow = Lb + ((long long)j * TILE) * npad;
+    const double* Li = Lb + ((long long)i * TILE) * npad;
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    // k-block 0 of the range is U_jj (from invdiagT), k-blocks 1.. are U[j, j+1..] in the block-upper part of L
+    Seg s0{Ujj, TILE, Li + (long long)j * TILE, npad, (q0 == 0) ? TILE / KC : 0};
+    const int r0 = (q0 == 0) ? 1 : q0;
+    Seg s1{Urow + (long long)(j + r0) * TILE, npad, Li + (long long)(j + r0) * TILE, npad, (q1 - r0) * (TILE / KC)};
+    mainloop<false>(acc, s0, s1, smem, nh, pipe);
+    if (S > 1 && !splitk_combine(acc, sk_slots + ((long long)b * slots_per_expert + slot_off) * TILE * TILE, part, S,
+                                 sk_counters + (long long)b * nt + j, &s_flag))
+        return;
+    double* Uji = Urow + (long long)i * TILE;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            *reinterpret_cast<double2*>(Uji + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+    __threadfence_block();
+    __syncthreads();
+    zero_acc(acc);
+    Seg s2{Uji, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
+    mainloop<false>(acc, s2, none, smem, nh, pipe);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            *reinterpret_cast<double2*>(Uji + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+}
+
+// U = L^-T for all experts: persistent task mode when there are enough (expert, row) tasks to fill the GPU, column mode
+// with split-K otherwise.  `work`: [256 B task counter][B*nt ints][slot tiles] (see trtri_work_bytes).
+static long long trtri_slot_tiles(int nt, int sms) { return 2LL * sms + nt; }
+static long long trtri_work_bytes(int B, int npad, int sms) {
+    const int nt = npad / TILE;
+    return 256 + align256((long long)B * nt * 4) + (long long)B * trtri_slot_tiles(nt, sms) * TILE * TILE * 8;
+}
+static int launch_trtri(double* L, const double* invdiag, const double* invdiagT, int B, int npad, void* work, cudaStream_t st) {
+    const int nt = npad / TILE;
+    if (nt <= 1) return GPR_OK;
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    int* task_counter = reinterpret_cast<int*>(work);
+    const long long ntasks = (long long)B * (nt - 1);
+    if (ntasks >= 2LL * sms) {
+        CUDA_TRY(cudaMemsetAsync(task_counter, 0, 256, st));
+        CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
+        trtri_kernel<<<sms, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, task_counter);
+        CUDA_TRY(cudaGetLastError());
+        return GPR_OK;
+    }
+    int* counters = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + 256);
+    double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(counters) + align256((long long)B * nt * 4));
+    const int spe = (int)trtri_slot_tiles(nt, sms);
+    CUDA_TRY(cudaMemsetAsync(counters, 0, (size_t)B * nt * 4, st));
+    CUDA_TRY(opt_in_smem(trtri_col_kernel, MAIN_SMEM_BYTES));
+    for (int i = 1; i < nt; ++i) {
+        const long long blocks = (long long)i * (i + 1) / 2;               // k-blocks of this column, per expert
+        long long target = (blocks * B + 2LL * sms - 1) / (2LL * sms);      // ~2 CTAs per SM over all experts
+        if (target < 1) target = 1;
+        int nparts = 0;
+        for (int j = 0; j < i; ++j) nparts += (int)((i - j + target - 1) / target);
+        trtri_col_kernel<<<dim3(nparts, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, npad, i, (int)target, slots, counters, spe);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdiagT, const double* __restrict__ a,
                   const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
@@ -1089,7 +1253,9 @@ static inline long long lml_feat_bytes(int dpad) { return (long long)TILE * XLD 
 extern "C" long long gpr_lml_grad_scratch_bytes(int B, int npad, int d) {
     const long long nt = npad / TILE;
     const long long ntiles = nt * (nt + 1) / 2;
-    return 256 + (long long)B * nt * TILE * TILE * 8 + (long long)B * ntiles * (d + 2) * 8;
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) sms = 148;
+    return trtri_work_bytes(B, npad, sms) + (long long)B * nt * TILE * TILE * 8 + align256((long long)B * ntiles * (d + 2) * 8);
 }
 
 extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
@@ -1104,18 +1270,14 @@ extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, c
     const int nt = npad / TILE;
     const int ntiles = nt * (nt + 1) / 2;
     const int P = d + 1 + (has_noise ? 1 : 0);
-    int* counter = reinterpret_cast<int*>(scratch);
-    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + trtri_work_bytes(B, npad, sms));
     double* partials = invdiagT + (long long)B * nt * TILE * TILE;
-    CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
     transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
-    if (nt > 1) {
-        CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
-        int sms = gpr_device_sm_count();
-        if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
-        const long long ntasks = (long long)B * (nt - 1);
-        const int grid = (int)(ntasks < sms ? ntasks : sms);
-        trtri_kernel<<<grid, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, counter);
+    {
+        const int rc = launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st);
+        if (rc != GPR_OK) return rc;
     }
     const int smem = (int)(smem_l > MAIN_SMEM_BYTES ? smem_l : MAIN_SMEM_BYTES);
     CUDA_TRY(opt_in_smem(lauum_grad_kernel, smem));
@@ -1168,23 +1330,24 @@ lauum_store_kernel(const double* __restrict__ L, const double* __restrict__ invd
             }
 }
 
-extern "C" long long gpr_potri_scratch_bytes(int B, int npad) { return 256 + (long long)B * (npad / TILE) * TILE * TILE * 8; }
+extern "C" long long gpr_potri_scratch_bytes(int B, int npad) {
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) sms = 148;
+    return trtri_work_bytes(B, npad, sms) + (long long)B * (npad / TILE) * TILE * TILE * 8;
+}
 
 extern "C" int gpr_potri_batched(double* L, const double* invdiag, int B, int n, int npad, double* Kinv, int ldo, void* scratch,
                                  void* stream) {
     ARG_CHECK(L && invdiag && Kinv && scratch && B > 0 && n > 0 && npad % TILE == 0 && npad >= n && ldo >= n);
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = npad / TILE;
-    int* counter = reinterpret_cast<int*>(scratch);
-    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
-    CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + trtri_work_bytes(B, npad, sms));
     transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
-    if (nt > 1) {
-        CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
-        int sms = gpr_device_sm_count();
-        if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
-        const long long ntasks = (long long)B * (nt - 1);
-        trtri_kernel<<<(int)(ntasks < sms ? ntasks : sms), NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, counter);
+    {
+        const int rc = launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st);
+        if (rc != GPR_OK) return rc;
     }
     CUDA_TRY(opt_in_smem(lauum_store_kernel, MAIN_SMEM_BYTES));
     lauum_store_kernel<<<dim3(nt * (nt + 1) / 2, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiagT, n, npad, Kinv, ldo);

@@ -172,8 +172,9 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     logdet_half = torch.empty(B, dtype=F64, device=dev)
     zz = torch.empty(B, dtype=F64, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
+    work = _work("potrf", int(_lib.load().gpr_potrf_work_bytes(B, npad)), dev)
     _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
-              _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _stream())
+              _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream())
     _count(2 * nt - 1)
     alpha = None
     if want_alpha:
@@ -196,8 +197,9 @@ def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
     if y is not None:
         z = torch.empty(B, npad, dtype=F64, device=dev)
         zz = torch.empty(B, dtype=F64, device=dev)
+    work = _work("potrf", int(_lib.load().gpr_potrf_work_bytes(B, npad)), dev)
     _lib.call("gpr_potrf_batched", _p(K), 0, None, None, None, 0, None, B, npad, npad, 0,
-              _p(invdiag), _p(y), _p(z), _p(logdet_half), _p(zz), _p(info), _stream())
+              _p(invdiag), _p(y), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream())
     _count(2 * nt - 1)
     return invdiag, z, logdet_half, zz, info
 
@@ -205,12 +207,17 @@ def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
 _scratch_cache = {}
 
 
-def _scratch(nbytes: int, dev: torch.device) -> torch.Tensor:
-    key = (dev.index, "predict")
+def _work(kind: str, nbytes: int, dev: torch.device) -> torch.Tensor:
+    """Grow-only per-device workspace (the library never allocates; calls on one stream are ordered)."""
+    key = (dev.index, kind)
     buf = _scratch_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         _scratch_cache[key] = buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     return buf
+
+
+def _scratch(nbytes: int, dev: torch.device) -> torch.Tensor:
+    return _work("predict", nbytes, dev)
 
 
 def predict(st: FitState, xs: torch.Tensor, want_var: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

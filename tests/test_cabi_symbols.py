@@ -35,7 +35,7 @@ def test_bad_arguments_are_status_codes_not_crashes():
     lib = _lib.load()
     rc = lib.gpr_se_scale(None, 0, None, 0, 1, 1, 1, 128, 4, None, None, None)
     assert rc == -1 and b"bad argument" in lib.gpr_last_error()
-    rc = lib.gpr_potrf_batched(None, 0, None, None, None, 0, None, 1, 100, 100, 0, None, None, None, None, None, None, None)
+    rc = lib.gpr_potrf_batched(None, 0, None, None, None, 0, None, 1, 100, 100, 0, None, None, None, None, None, None, None, None)
     assert rc == -1
 
 
