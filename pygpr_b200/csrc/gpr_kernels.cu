@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pygpr_b200.h"
@@ -243,7 +244,7 @@ struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-war
 #pragma unroll
         for (int r = 0; r < 8; ++r) part[r] = 0.0;
     }
-    __device__ __forceinline__ void pre(int c) { zk = z ? z[c * KC + (threadIdx.x & 15)] : 0.0; }
+    __device__ __forceinline__ void pre(int c) { zk = z ? __ldcg(z + c * KC + (threadIdx.x & 15)) : 0.0; }  // L2: other CTAs write z
     __device__ __forceinline__ void post(const double* sA, int) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const double* p = sA + (warp * 16 + (lane >> 4) * 8) * SLD + (lane & 15);
@@ -266,39 +267,20 @@ struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-war
     }
 };
 
+// Tail of a diagonal-tile task, shared by the per-column kernel and the dataflow kernel: T = K_jj - acc (- dpart) ->
+// potf2 + trti2 in registers -> L_jj, inv(L_jj), log-determinant / info, forward-solve block z_j.
+// Scalars that several CTAs update in turn (logdet_half, zz, info) and z go through L2 (__ldcg/__stcg): in the dataflow
+// kernel consecutive block columns of one expert run on different SMs and L1 is not coherent.
 template <bool GEN>
-__global__ void __launch_bounds__(NTHREADS, 1)
-potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
-                  const double* __restrict__ hp, int hp_stride, const double* __restrict__ diag_add, int dpad,
-                  double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
-                  double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
-    extern __shared__ double smem[];
-    __shared__ unsigned long long pipe_bars[2 * STAGES];
-    Pipe pipe;
-    pipe_init(pipe, pipe_bars);
-    __shared__ double pub[3 * TILE];
-    __shared__ double svec[TILE];
-    __shared__ int s_fail;
-    const int b = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem, double* pub, double* svec, int* s_fail, double* Lb,
+                                            int b, int j, int n, int npad, const double* __restrict__ a,
+                                            const double* __restrict__ nrm, const double* __restrict__ hp, int hp_stride,
+                                            const double* __restrict__ diag_add, int dpad, double* invdiag, const double* y,
+                                            double* zb, double* logdet_half, double* zz, int* info, const double* dpart) {
+    const int tid = threadIdx.x;
     const int nt = npad / TILE;
-    double* Lb = L + (long long)b * npad * npad;
     double* Ljj = Lb + ((long long)j * TILE) * npad + j * TILE;
-    double* zb = y ? z + (long long)b * npad : nullptr;
-    if (tid == 0) s_fail = 1 << 30;
-
-    // product over the LAST block column only (k-block j-1); blocks 0..j-2 were summed by the look-ahead CTA
-    double acc[4][8][2];
-    zero_acc(acc);
-    GemvHook hook;
-    hook.init(zb && j > 0 ? zb + (long long)(j - 1) * TILE : nullptr);
-    const double* Arow = Lb + ((long long)j * TILE) * npad + (long long)(j > 0 ? j - 1 : 0) * TILE;
-    Seg s0{Arow, npad, Arow, npad, j > 0 ? TILE / KC : 0};
-    Seg s1{nullptr, 0, nullptr, 0, 0};
-    mainloop<true>(acc, s0, s1, smem, hook, pipe);
-    const bool have_part = j >= 2;
-    const double* dpart = Lb + ((long long)(j - 1) * TILE) * npad + (long long)j * TILE;  // upper block (j-1, j)
-    hook.reduce_to(svec, (have_part && zb) ? zb + (long long)j * TILE : nullptr);
-
+    if (tid == 0) *s_fail = 1 << 30;
     double* T = smem;  // full tile overlays the (drained) pipeline stages
     if (GEN) {
         double* fbase = smem + TILE * XLD;
@@ -316,7 +298,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
             double v;
             if (gr < n && gc < n) v = (r == c) ? kv + dadd : kv;
             else v = (r == c) ? 1.0 : 0.0;
-            if (have_part) v -= dpart[(long long)r * npad + c];
+            if ((dpart != nullptr)) v -= dpart[(long long)r * npad + c];
             T[r * XLD + c] = v - acc[mi][ni][e];
         });
     } else {
@@ -326,7 +308,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
             for (int ni = 0; ni < 8; ++ni) {
                 const int r = acc_row(mi), c = acc_col(ni, 0);
                 double2 k2 = *reinterpret_cast<const double2*>(Ljj + (long long)r * npad + c);
-                if (have_part) {
+                if ((dpart != nullptr)) {
                     const double2 p2 = *reinterpret_cast<const double2*>(dpart + (long long)r * npad + c);
                     k2.x -= p2.x;
                     k2.y -= p2.y;
@@ -338,7 +320,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     __syncthreads();
     DiagBlock blk;
     diag_block_coords(blk);
-    potf2_reg(T, pub, &s_fail, blk);
+    potf2_reg(T, pub, s_fail, blk);
 
     // write L_jj (strict upper zeroed) and accumulate sum log L_ii
     for (int id = tid; id < TILE * TILE; id += NTHREADS) {
@@ -350,10 +332,10 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
         for (int k = tid; k < TILE; k += 32) s += log(T[k * XLD + k]);
         s = warp_sum(s);
         if (tid == 0) {
-            if (logdet_half) logdet_half[b] = (j == 0 ? 0.0 : logdet_half[b]) + s;
+            if (logdet_half) __stcg(logdet_half + b, (j == 0 ? 0.0 : __ldcg(logdet_half + b)) + s);
             if (info) {
-                if (j == 0) info[b] = 0;
-                if (s_fail <= TILE && info[b] == 0) info[b] = j * TILE + s_fail;
+                if (j == 0 && *s_fail > TILE) __stcg(info + b, 0);
+                if (*s_fail <= TILE && (j == 0 || __ldcg(info + b) == 0)) __stcg(info + b, j * TILE + *s_fail);
             }
         }
     }
@@ -378,9 +360,43 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
         if (tid < 32 && zz) {
             double s = svec[tid] + svec[tid + 32] + svec[tid + 64] + svec[tid + 96];
             s = warp_sum(s);
-            if (tid == 0) zz[b] = (j == 0 ? 0.0 : zz[b]) + s;
+            if (tid == 0) __stcg(zz + b, (j == 0 ? 0.0 : __ldcg(zz + b)) + s);
         }
     }
+}
+
+template <bool GEN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
+                  const double* __restrict__ hp, int hp_stride, const double* __restrict__ diag_add, int dpad,
+                  double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
+                  double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
+    __shared__ double pub[3 * TILE];
+    __shared__ double svec[TILE];
+    __shared__ int s_fail;
+    const int b = blockIdx.x;
+    double* Lb = L + (long long)b * npad * npad;
+    double* zb = y ? z + (long long)b * npad : nullptr;
+
+    // product over the LAST block column only (k-block j-1); blocks 0..j-2 were summed by the look-ahead CTA
+    double acc[4][8][2];
+    zero_acc(acc);
+    GemvHook hook;
+    hook.init(zb && j > 0 ? zb + (long long)(j - 1) * TILE : nullptr);
+    const double* Arow = Lb + ((long long)j * TILE) * npad + (long long)(j > 0 ? j - 1 : 0) * TILE;
+    Seg s0{Arow, npad, Arow, npad, j > 0 ? TILE / KC : 0};
+    Seg s1{nullptr, 0, nullptr, 0, 0};
+    mainloop<true>(acc, s0, s1, smem, hook, pipe);
+    const bool have_part = j >= 2;
+    const double* dpart = Lb + ((long long)(j - 1) * TILE) * npad + (long long)j * TILE;  // upper block (j-1, j)
+    hook.reduce_to(svec, (have_part && zb) ? zb + (long long)j * TILE : nullptr);
+
+    diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, n, npad, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, zb,
+                     logdet_half, zz, info, have_part ? dpart : nullptr);
 }
 
 // grid.x = (nt-1-j) row tiles, plus one look-ahead CTA per expert when lookahead != 0 (j >= 1, j+1 < nt):
@@ -496,6 +512,215 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
                 make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3 (dataflow form): the whole batched factorisation in ONE persistent launch.  Tile tasks are handed out by an atomic
+// counter in an order in which every dependency has a smaller index (block column by block column; inside a column
+// the B diagonal tasks first, then the panel tiles expert by expert), and per-(expert, row tile) progress counters
+// replace the launch boundaries:   progress[b][i] = number of finished tiles in block row i  (j+1 after tile (i, j),
+// i+1 after the diagonal task of row i).  A task only ever waits for tasks that a RUNNING CTA already holds, so the
+// scheme cannot deadlock whatever the number of resident CTAs.  What it buys over one diag + one panel launch per
+// column: no ragged last wave per column, the potf2/trti2 of the diagonal tile (tensor-idle, ~6 tile products long)
+// overlaps other experts' products instead of serialising the column, and no look-ahead round trip through HBM.
+//   D(b, j):  T = K_jj - L[j,0:j] L[j,0:j]^T  -> potf2/trti2 -> L_jj, inv(L_jj), z_j      waits (j, j-1) for the last block
+//   P(b,i,j): X = K_ij - L[i,0:j] L[j,0:j]^T ; waits for D(b, j) only before  L_ij = X inv(L_jj)^T
+// Waits are bounded (DF_SPIN_LIMIT polls): on a time-out the kernel raises the abort flag, every CTA drains, and
+// info[0] = -1 tells the host; the bound is a guard against a wedged GPU, not part of the protocol.
+// ---------------------------------------------------------------------------------------------
+constexpr long long DF_SPIN_LIMIT = 1LL << 22;
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// All threads call.  Thread 0 polls, the CTA barrier hands its acquire to everyone.  false = aborted.
+__device__ __forceinline__ bool df_wait(const int* flag, int need, int* abort_flag, int* info, int* s_ok) {
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        if (ld_acquire_gpu(flag) < need) {
+            long long spins = 0;
+            for (;;) {
+                __nanosleep(100);
+                if (ld_acquire_gpu(flag) >= need) break;
+                if (++spins > DF_SPIN_LIMIT || *reinterpret_cast<volatile int*>(abort_flag)) {
+                    atomicExch(abort_flag, 1);
+                    if (info) __stcg(info, -1);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        *s_ok = ok;
+    }
+    __syncthreads();
+    const bool ok = *s_ok != 0;
+    __syncthreads();  // *s_ok is rewritten by the next wait
+    return ok;
+}
+
+struct PotrfArgs {
+    double* L;
+    int B, npad, n;
+    const double *a, *nrm, *hp;
+    int hp_stride;
+    const double* diag_add;
+    int dpad;
+    double* invdiag;
+    const double* y;
+    double* z;
+    double* logdet_half;
+    double* zz;
+    int* info;
+    int* ctl;       // [0] next task, [1] abort flag
+    int* progress;  // [B, nt]
+};
+
+// The two task bodies are separate NON-inlined functions so that each gets the register allocation of a stand-alone
+// kernel (inlined into the persistent loop the four mainloop copies spilled and grew by ~100 instructions per chunk).
+// Both return the pipeline's chunk counter modulo 2*STAGES (all that stage/parity selection needs), or -1 on abort.
+template <bool GEN>
+__device__ __forceinline__ int df_diag_task(const PotrfArgs& A, int b, int j, unsigned g_in, unsigned bars) {
+    extern __shared__ double smem[];
+    __shared__ double pub[3 * TILE];
+    __shared__ double svec[TILE];
+    __shared__ int s_fail, s_ok;
+    Pipe pipe{bars, g_in};
+    const int npad = A.npad, nt = npad / TILE;
+    double* Lb = A.L + (long long)b * npad * npad;
+    double* zb = A.y ? A.z + (long long)b * npad : nullptr;
+    int* prog = A.progress + (long long)b * nt;
+    int* abort_flag = A.ctl + 1;
+    const double* Arow = Lb + ((long long)j * TILE) * npad;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    double acc[4][8][2];
+    zero_acc(acc);
+    GemvHook hook;
+    hook.init(zb);
+    if (j >= 2) {  // k-blocks 0..j-2 are older than the previous column
+        if (!df_wait(prog + j, j - 1, abort_flag, A.info, &s_ok)) return -1;
+        Seg s0{Arow, npad, Arow, npad, (j - 1) * (TILE / KC)};
+        mainloop<true>(acc, s0, none, smem, hook, pipe);
+    }
+    if (j >= 1) {  // the last k-block is tile (j, j-1) of the previous column
+        if (!df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;
+        hook.z = zb ? zb + (long long)(j - 1) * TILE : nullptr;
+        const double* Alast = Arow + (long long)(j - 1) * TILE;
+        Seg s0{Alast, npad, Alast, npad, TILE / KC};
+        mainloop<true>(acc, s0, none, smem, hook, pipe);
+    }
+    hook.reduce_to(svec, nullptr);
+    diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, A.n, npad, A.a, A.nrm, A.hp, A.hp_stride, A.diag_add, A.dpad, A.invdiag,
+                     A.y, zb, A.logdet_half, A.zz, A.info, nullptr);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(prog + j, j + 1);
+    return (int)(pipe.g % (2 * STAGES));
+}
+
+template <bool GEN>
+__device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, int j, unsigned g_in, unsigned bars) {
+    extern __shared__ double smem[];
+    __shared__ int s_ok;
+    Pipe pipe{bars, g_in};
+    const int tid = threadIdx.x;
+    const int npad = A.npad, nt = npad / TILE, n = A.n, dpad = A.dpad;
+    double* Lb = A.L + (long long)b * npad * npad;
+    int* prog = A.progress + (long long)b * nt;
+    int* abort_flag = A.ctl + 1;
+    double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    double acc[4][8][2];
+    zero_acc(acc);
+    if (j > 0) {
+        if (!df_wait(prog + i, j, abort_flag, A.info, &s_ok)) return -1;  // L[i, 0:j]
+        if (!df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;  // L[j, 0:j]
+        Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
+        mainloop<false>(acc, s0, none, smem, nh, pipe);
+    }
+    if (GEN) {
+        FeatSmem f = carve_feat(smem, dpad);
+        load_feat_tile(f.sR, f.sld, A.a + ((long long)b * npad + i * TILE) * dpad, dpad);
+        load_feat_tile(f.sC, f.sld, A.a + ((long long)b * npad + j * TILE) * dpad, dpad);
+        cp_async_commit();
+        if (tid < TILE) {
+            f.nR[tid] = A.nrm[(long long)b * npad + i * TILE + tid];
+            f.nC[tid] = A.nrm[(long long)b * npad + j * TILE + tid];
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        const double sig = A.hp[(long long)b * A.hp_stride];
+        gen_se_tile(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig * sig, [&](int mi, int ni, int e, double kv) {
+            const int gr = i * TILE + acc_row(mi), gc = j * TILE + acc_col(ni, e);
+            acc[mi][ni][e] = ((gr < n && gc < n) ? kv : 0.0) - acc[mi][ni][e];
+        });
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+                *reinterpret_cast<double2*>(Lij + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    } else {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                double2* p = reinterpret_cast<double2*>(Lij + (long long)acc_row(mi) * npad + acc_col(ni, 0));
+                double2 k2 = *p;
+                k2.x -= acc[mi][ni][0];
+                k2.y -= acc[mi][ni][1];
+                *p = k2;
+            }
+    }
+    __threadfence_block();
+    if (!df_wait(prog + j, j + 1, abort_flag, A.info, &s_ok)) return -1;  // inv(L_jj); the barrier inside also publishes X
+    zero_acc(acc);
+    Seg s1{Lij, npad, A.invdiag + ((long long)b * nt + j) * TILE * TILE, TILE, TILE / KC};
+    mainloop<false>(acc, s1, none, smem, nh, pipe);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+            *reinterpret_cast<double2*>(Lij + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu(prog + i, j + 1);
+    return (int)(pipe.g % (2 * STAGES));
+}
+
+// One CTA per task, NOT a persistent loop: the task index is a ticket drawn at CTA start (so "waits only on tickets held by
+// running CTAs" holds whatever order the hardware dispatches blocks in), and the body is straight-line code like the
+// per-column kernels (inside a persistent loop ptxas spilled into all four mainloop copies, +100 instructions per chunk).
+template <bool GEN>
+__global__ void __launch_bounds__(NTHREADS, 1) potrf_dataflow_kernel(const __grid_constant__ PotrfArgs A) {
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    __shared__ int s_col, s_local;
+    Pipe pipe;
+    if (threadIdx.x == 0) {
+        const int B = A.B, nt = A.npad / TILE;
+        const int task = atomicAdd(A.ctl, 1);
+        int col = 0, col_start = 0;  // tasks of block column `col` are [col_start, col_start + B (nt - col))
+        while (task >= col_start + B * (nt - col)) {
+            col_start += B * (nt - col);
+            ++col;
+        }
+        s_col = col;
+        s_local = task - col_start;
+    }
+    pipe_init(pipe, pipe_bars);  // ends with a CTA barrier
+    const int col = s_col, local = s_local;
+    if (local < A.B) {
+        df_diag_task<GEN>(A, local, col, 0u, pipe.bars);
+    } else {
+        const int per = A.npad / TILE - 1 - col;
+        df_panel_task<GEN>(A, (local - A.B) / per, col + 1 + (local - A.B) % per, col, 0u, pipe.bars);
+    }
+}
+
 // Split factor for a launch of `tiles` equal-depth tiles of `depth` k-blocks.  Two effects are traded: (i) a launch with
 // fewer tiles than SMs leaves SMs idle, (ii) a launch of a few waves wastes up to one wave in the ragged tail.  Cost
 // model in tile units (one 128^3 product): waves * (depth/S + epilogue) + fix-up; S = 1..8, slices keep >= 1 block.
@@ -525,7 +750,7 @@ extern "C" long long gpr_potrf_work_bytes(int B, int npad) {
     int sms = gpr_device_sm_count();
     if (sms <= 0) sms = 148;
     const int nt = npad / TILE;
-    return align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
+    return 256 + align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
 }
 
 extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
@@ -548,6 +773,38 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
         gemv = reinterpret_cast<double*>(reinterpret_cast<char*>(work) + align256((long long)B * nt * 4));
         slots = reinterpret_cast<double*>(reinterpret_cast<char*>(gemv) + align256((long long)B * 32 * TILE * 8));
         CUDA_TRY(cudaMemsetAsync(counters, 0, (size_t)B * nt * 4, st));
+    }
+    // single-launch dataflow form when there are enough tile tasks per block column to keep the SMs busy across the
+    // dependency chain of any one expert; the per-column form with split-K for few experts (PYGPR_POTRF_MODE overrides)
+    {
+        const char* mode = getenv("PYGPR_POTRF_MODE");
+        const long long total = (long long)B * nt * (nt + 1) / 2;
+        // measured on B200 (tools/potrf_modes.py): dataflow wins from ~8 experts up (+8 % at B=32..63), ties at 4, loses below
+        bool dataflow = work && nt >= 2 && B >= 6 && total < (1LL << 30);
+        if (mode && !strcmp(mode, "columns")) dataflow = false;
+        if (mode && !strcmp(mode, "dataflow") && work && total < (1LL << 30)) dataflow = true;
+        if (dataflow) {
+            int smem_df = MAIN_SMEM_BYTES;
+            if (gen) {
+                const int fb = feat_smem_bytes(dpad);
+                if (TILE * XLD * 8 + fb > 227 * 1024)
+                    return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
+                if (TILE * XLD * 8 + fb > smem_df) smem_df = TILE * XLD * 8 + fb;
+            }
+            int* ctl = reinterpret_cast<int*>(work);
+            PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, ctl + 64};
+            CUDA_TRY(cudaMemsetAsync(work, 0, 256 + (size_t)B * nt * 4, st));
+            const int grid = (int)total;  // one CTA per tile task
+            if (gen) {
+                CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<true>, smem_df));
+                potrf_dataflow_kernel<true><<<grid, NTHREADS, smem_df, st>>>(A);
+            } else {
+                CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<false>, smem_df));
+                potrf_dataflow_kernel<false><<<grid, NTHREADS, smem_df, st>>>(A);
+            }
+            CUDA_TRY(cudaGetLastError());
+            return GPR_OK;
+        }
     }
     int smem_diag = MAIN_SMEM_BYTES, smem_panel = MAIN_SMEM_BYTES;
     if (gen) {
