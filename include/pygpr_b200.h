@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 1
+#define GPR_ABI_VERSION 2
 
 typedef enum {
     GPR_OK = 0,
@@ -112,10 +112,13 @@ long long gpr_potrf_work_bytes(int B, int npad);
 
 /*
  * alpha = L^-T z  (backward half of cholesky_solve, gpr.py:70-72).  HBM-bound: reads L once.
- *   z [B,npad] in, alpha [B,npad] out (may alias z)
+ *   z [B,npad] in, alpha [B,npad] out (may alias z only when work == NULL)
+ *   work  >= gpr_trsv_work_bytes(B) or NULL.  With a workspace and fewer experts than SMs the solve runs as a
+ *         cooperative launch of several column-owner CTAs per expert (one CTA per expert cannot saturate HBM).
  */
 int gpr_trsv_backward(const double* L, const double* invdiag, int B, int npad,
-                      const double* z, double* alpha, void* stream);
+                      const double* z, double* alpha, void* work, void* stream);
+long long gpr_trsv_work_bytes(int B);
 
 /*
  * Batched prediction: mean and variance of every expert at m test points, in one persistent kernel.

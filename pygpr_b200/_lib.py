@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygpr_b200.so")
 
 TILE = 128
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes).  Pointers are passed as integers (tensor.data_ptr()).
 _P, _I, _LL = c_void_p, c_int, c_longlong
@@ -29,7 +29,8 @@ SIGNATURES = {
     "gpr_se_kernel_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpr_potrf_work_bytes": (c_longlong, [_I, _I]),
-    "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
+    "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    "gpr_trsv_work_bytes": (c_longlong, [_I]),
     "gpr_predict": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "gpr_lml_grad": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "gpr_predict_full_scratch_bytes": (c_longlong, [_I, _I, _I]),

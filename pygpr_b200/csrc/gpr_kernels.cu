@@ -915,13 +915,124 @@ __global__ void __launch_bounds__(NTHREADS) trsv_backward_kernel(const double* _
     }
 }
 
+// Few experts: one CTA per expert cannot pull more than a few % of HBM bandwidth (B=1, n=16384: 35 ms for 1 GB).
+// Column-owner form with G CTAs per expert: CTA c owns the block columns j = c (mod G) and keeps their running
+// right-hand sides  r_j = z_j - sum_{i>j, alpha_i known} L_ij^T alpha_i  in shared memory.  As soon as alpha_i is
+// published (per-expert counter, release/acquire) every owner subtracts its tiles of block row i; the owner of block
+// i-1 does that tile first, solves  alpha_{i-1} = inv(L_{i-1,i-1})^T r_{i-1}  and publishes before touching the rest.
+// The CTAs of one expert wait for each other, so the launch is cooperative (all CTAs co-resident or the launch fails).
+__global__ void __launch_bounds__(NTHREADS)
+trsv_backward_owner_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad, const double* __restrict__ z,
+                           double* __restrict__ alpha, int* __restrict__ done, int* __restrict__ abort_flag) {
+    extern __shared__ double srhs[];  // [owned blocks][128] running right-hand sides
+    __shared__ double part[NTHREADS / 32][TILE];
+    __shared__ double sal[TILE];
+    __shared__ int s_ok;
+    const int c = blockIdx.x, G = gridDim.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nt = npad / TILE;
+    const double* Lb = L + (long long)b * npad * npad;
+    const double* zb = z + (long long)b * npad;
+    double* ab = alpha + (long long)b * npad;
+    int* flag = done + b;  // number of alpha blocks published so far (blocks nt-1, nt-2, ... in that order)
+    for (int j = c; j < nt; j += G)
+        if (tid < TILE) srhs[(j / G) * TILE + tid] = zb[j * TILE + tid];
+    __syncthreads();
+
+    // alpha_j = inv(L_jj)^T r_j : alpha_j[col] = sum_{k >= col} inv[k][col] r_j[k]; publish
+    auto solve_publish = [&](int j) {
+        const double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
+        const double* r = srhs + (j / G) * TILE;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int k = warp; k < TILE; k += NTHREADS / 32) {
+            const double* p = inv + k * TILE + 4 * lane;
+            const double2 v0 = *reinterpret_cast<const double2*>(p), v1 = *reinterpret_cast<const double2*>(p + 2);
+            const double rk = r[k];
+            s0 += v0.x * rk; s1 += v0.y * rk; s2 += v1.x * rk; s3 += v1.y * rk;
+        }
+        part[warp][4 * lane + 0] = s0; part[warp][4 * lane + 1] = s1;
+        part[warp][4 * lane + 2] = s2; part[warp][4 * lane + 3] = s3;
+        __syncthreads();
+        if (tid < TILE) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NTHREADS / 32; ++w) s += part[w][tid];
+            __stcg(ab + j * TILE + tid, s);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu(flag, nt - j);
+    };
+
+    if ((nt - 1) % G == c) solve_publish(nt - 1);
+    for (int i = nt - 1; i >= 1; --i) {
+        if (c >= i) break;  // no owned block column left of block row i
+        if (!df_wait(flag, nt - i, abort_flag, nullptr, &s_ok)) return;
+        if (tid < TILE) sal[tid] = __ldcg(ab + i * TILE + tid);
+        __syncthreads();
+        // owned j < i, descending: j = i-1 first when it is ours (it is on the critical path)
+        int j = i - 1 - ((i - 1 - c) % G + G) % G;  // largest j <= i-1 with j = c (mod G)
+        for (; j >= 0; j -= G) {
+            // s[col] = sum_r L[i*128 + r, j*128 + col] alpha_i[r]; lane owns 4 columns, warps stride the rows
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            const double* tile = Lb + ((long long)i * TILE) * npad + (long long)j * TILE + 4 * lane;
+#pragma unroll 4
+            for (int r = warp; r < TILE; r += NTHREADS / 32) {
+                const double* p = tile + (long long)r * npad;
+                const double2 v0 = __ldcg(reinterpret_cast<const double2*>(p)), v1 = __ldcg(reinterpret_cast<const double2*>(p + 2));
+                const double al = sal[r];
+                s0 += v0.x * al; s1 += v0.y * al; s2 += v1.x * al; s3 += v1.y * al;
+            }
+            part[warp][4 * lane + 0] = s0; part[warp][4 * lane + 1] = s1;
+            part[warp][4 * lane + 2] = s2; part[warp][4 * lane + 3] = s3;
+            __syncthreads();
+            if (tid < TILE) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NTHREADS / 32; ++w) s += part[w][tid];
+                srhs[(j / G) * TILE + tid] -= s;
+            }
+            __syncthreads();
+            if (j == i - 1) solve_publish(j);
+        }
+    }
+}
+
+extern "C" long long gpr_trsv_work_bytes(int B) { return 256 + align256((long long)B * 4); }
+
 extern "C" int gpr_trsv_backward(const double* L, const double* invdiag, int B, int npad, const double* z, double* alpha,
-                                 void* stream) {
+                                 void* work, void* stream) {
     ARG_CHECK(L && invdiag && z && alpha && B > 0 && npad > 0 && npad % TILE == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    const char* mode = getenv("PYGPR_TRSV_MODE");
+    bool owner = work && B < sms && nt >= 4 && z != alpha;
+    if (mode && !strcmp(mode, "single")) owner = false;
+    if (owner) {
+        int G = (2 * sms) / B;
+        if (G > nt) G = nt;
+        const int own = (nt + G - 1) / G;
+        const size_t smem = (size_t)own * TILE * 8;
+        int dev = 0, per_sm = 0, coop = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        if (smem > 48 * 1024) CUDA_TRY(opt_in_smem(trsv_backward_owner_kernel, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_backward_owner_kernel, NTHREADS, smem));
+        if (coop && G >= 2 && (long long)per_sm * sms >= (long long)G * B) {
+            int* abort_flag = reinterpret_cast<int*>(work);
+            int* done = abort_flag + 64;
+            CUDA_TRY(cudaMemsetAsync(work, 0, 256 + (size_t)B * 4, st));
+            void* args[] = {(void*)&L, (void*)&invdiag, (void*)&npad, (void*)&z, (void*)&alpha, (void*)&done, (void*)&abort_flag};
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void*)trsv_backward_owner_kernel, dim3(G, B), dim3(NTHREADS), args, smem, st));
+            return GPR_OK;
+        }
+    }
     const int smem = npad * 8;
     if (smem > 200 * 1024) return fail(GPR_ERR_UNSUPPORTED, "matrix order too large for the single-CTA backward solve%s (npad=%lld)", "", npad);
     CUDA_TRY(opt_in_smem(trsv_backward_kernel, smem));
-    trsv_backward_kernel<<<B, NTHREADS, smem, (cudaStream_t)stream>>>(L, invdiag, npad, z, alpha);
+    trsv_backward_kernel<<<B, NTHREADS, smem, st>>>(L, invdiag, npad, z, alpha);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }

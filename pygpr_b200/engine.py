@@ -179,7 +179,8 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     alpha = None
     if want_alpha:
         alpha = torch.empty(B, npad, dtype=F64, device=dev)
-        _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _stream())
+        twork = _work("trsv", int(_lib.load().gpr_trsv_work_bytes(B)), dev)
+        _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _p(twork), _stream())
         _count(1)
     return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior)
 

@@ -156,3 +156,19 @@ def test_dataflow_info_and_repeat(eng, orc, monkeypatch):
     eng.potrf_inplace(a)
     eng.potrf_inplace(b)
     assert torch.equal(torch.tril(a), torch.tril(b))
+
+
+@pytest.mark.parametrize("B,n,d", [(1, 1500, 4), (3, 1100, 8), (5, 520, 3), (40, 640, 4)])
+def test_backward_solve_forms(eng, orc, monkeypatch, B, n, d):
+    """alpha = L^-T z: the cooperative column-owner form (several CTAs per expert, used for few experts) and the
+    one-CTA-per-expert form agree with each other and with the reference's cholesky_solve (gpr.py:70-72)."""
+    x, y, xs, hp = _data(9, B, n, d, 8, per_expert=True)
+    monkeypatch.setenv("PYGPR_TRSV_MODE", "single")
+    a1 = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True).alpha.clone()
+    monkeypatch.setenv("PYGPR_TRSV_MODE", "auto")
+    a2 = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True).alpha.clone()
+    torch.cuda.synchronize()
+    _, alpha_ref = orc.gp_fit(SPEC, hp, x, y)
+    assert_close(a1[:, :n].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha (one CTA per expert)")
+    assert_close(a2[:, :n].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha (column owners)")
+    assert_close(a2.cpu().numpy(), a1.cpu().numpy(), 1e-12, "forms agree")
