@@ -149,7 +149,7 @@ def run_reference(args):
     from oracle import pygpr_oracle as orc
     w = workload(args.small)
     nc = w["M_sub"] - 1
-    nc_s, m_s = (2, 1024) if not args.small else (4, 256)
+    nc_s, m_s = (4, 4096) if not args.small else (4, 256)
     torch.set_num_threads(os.cpu_count() or 1)
     fit_s, _, fits, (xl, yl, xg, yg, hp_g, hp_l) = cpu_sample(w, m_s, nc_s)
     xs = test_points(m_s, w["d"])
@@ -238,12 +238,10 @@ def main():
 
     # ---- fit: batched Cholesky (+ fused forward solve, backward solve), timed once after a warm-up pass -------------
     n_l, n_g, nc_loc = 2 * w["m0"], w["m0"], hi - lo
-    model.gpg.update(); model.gpl.update(); barrier()
-    model.gpl.need_upd = True; model.gpg.need_upd = True
-    model.gpl._state = None  # release the first factor before allocating the second (137 GB at N=1)
-    torch.cuda.empty_cache()
+    model.update(); barrier()
+    model.gpl.need_upd = True; model.gpg.need_upd = True   # the refit reuses the factor buffers (137 GB at N=1): no cudaMalloc in the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(); e0.record(); model.gpg.update(); model.gpl.update(); e1.record(); barrier()
+    barrier(); e0.record(); model.update(); e1.record(); barrier()
     fit_ms = max_over_ranks(e0.elapsed_time(e1))
     fit_flops = nc_total * n_l ** 3 / 3.0 + world * n_g ** 3 / 3.0  # the comm expert is replicated on every rank
     st = model.gpl._state
@@ -255,10 +253,11 @@ def main():
     pk_ms = []
 
     def step_device():
-        mg, vg = eng.predict(model.gpg._state, xs_dev, True)
+        # communication expert on a side stream, local experts on this one (engine.predict_pair); k0..k1 brackets the
+        # local experts' persistent kernel, which shares the SMs with the communication expert's ceil(m/128) tasks
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        ml, vl = eng.predict(st, xs_dev, True)
+        (mg, vg), (ml, vl) = eng.predict_pair(model.gpg._state, st, xs_dev)
         k1.record()
         pk_ms.append((k0, k1))
         S, _, _ = eng.grbcm_partial(ml, vl, vg[0], lo)
@@ -305,11 +304,12 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    pred_flops_kernel = nc_loc * float(n_l) ** 2 * m          # algorithmic N^2 per test point per expert
-    roof = {"bound": "tensor", "kernel": "predict_kernel", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
+    pred_flops_kernel = (nc_loc * float(n_l) ** 2 + float(n_g) ** 2) * m   # algorithmic N^2 per test point per expert
+    roof = {"bound": "tensor", "kernel": "predict_kernel (local experts; the communication expert's launch overlaps it on a side stream)", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf,
-            # dram__bytes_read+write of this launch from profiles/r01_ncu_predict_kernel_bench_scale.json (valid for the default 1-GPU config)
-            "traffic": 3.123e12 if (world == 1 and not args.small and m == 4096) else None,
+            # dram__bytes_read + dram__bytes_write of this launch (2.533 TB + 68.7 GB) from the ncu --set full capture in
+            # profiles/r01_s2_ncu_predict_kernel_bench_scale.json (valid for the default 1-GPU config only)
+            "traffic": 2.602e12 if (world == 1 and not args.small and m == 4096) else None,
             "peak_source": "cuBLAS dgemm 8192^3 (A B^T) measured in this run on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
             "kernel_ms": kern_ms, "flops_per_launch": pred_flops_kernel}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -330,7 +330,7 @@ def main():
                             "cholesky_plus_grad_tflops": (gflops + fit_flops) / (grad_ms + fit_ms) * 1e-9}
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        nc_s, m_s = (2, 1024) if not args.small else (4, 256)
+        nc_s, m_s = (4, 4096) if not args.small else (4, 256)
         fit_s, pred_s, _, _ = cpu_sample(w, m_s, nc_s)
         work_full = nc_total * n_l ** 2 + n_g ** 2
         work_s = nc_s * n_l ** 2 + n_g ** 2

@@ -131,6 +131,12 @@ class FitState:
         """NLML = 1/2 y^T alpha + sum log L_ii + n/2 log 2 pi   (loss.py:49-51); y^T alpha = z.z"""
         return 0.5 * self.zz + self.logdet_half + 0.5 * self.n * math.log(2.0 * math.pi)
 
+    def record_stream(self, stream) -> None:
+        """The state was produced on another stream: tell the caching allocator that `stream` uses its buffers too."""
+        for t in (self.hp, self.a, self.nrm, self.L, self.invdiag, self.z, self.alpha, self.logdet_half, self.zz, self.info, self.prior):
+            if t is not None:
+                t.record_stream(stream)
+
     def check(self) -> None:
         """Mirror tc.cholesky's RuntimeError on a non-PD matrix (gpr.py:69)."""
         bad = torch.nonzero(self.info)
@@ -150,7 +156,7 @@ def split_hp(hp: torch.Tensor, d: int, has_noise: bool, jitter: float = JITTER):
 
 
 def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, want_alpha: bool = True,
-        jitter: float = JITTER, L_out: Optional[torch.Tensor] = None) -> FitState:
+        jitter: float = JITTER, L_out: Optional[torch.Tensor] = None, ws_tag: str = "") -> FitState:
     """Batched Exact_GP.update (gpr.py:65-74) for cov = Compose([SE, WN]) or SE alone.
 
     K is never materialised: tiles are generated inside the factorisation (gen=1).
@@ -172,14 +178,14 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     logdet_half = torch.empty(B, dtype=F64, device=dev)
     zz = torch.empty(B, dtype=F64, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
-    work = _work("potrf", int(_lib.load().gpr_potrf_work_bytes(B, npad)), dev)
+    work = _work("potrf" + ws_tag, int(_lib.load().gpr_potrf_work_bytes(B, npad)), dev)   # ws_tag: a fit on another stream
     _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
               _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream())
     _count(2 * nt - 1)
     alpha = None
     if want_alpha:
         alpha = torch.empty(B, npad, dtype=F64, device=dev)
-        twork = _work("trsv", int(_lib.load().gpr_trsv_work_bytes(B)), dev)
+        twork = _work("trsv" + ws_tag, int(_lib.load().gpr_trsv_work_bytes(B)), dev)
         _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _p(twork), _stream())
         _count(1)
     return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior)
@@ -217,23 +223,50 @@ def _work(kind: str, nbytes: int, dev: torch.device) -> torch.Tensor:
     return buf
 
 
-def _scratch(nbytes: int, dev: torch.device) -> torch.Tensor:
-    return _work("predict", nbytes, dev)
-
-
-def predict(st: FitState, xs: torch.Tensor, want_var: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind: str = "predict"
+            ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """mean [B, m] and variance [B, m] of every expert at xs [m, d]  (gpr.py:76-106)."""
     assert st.alpha is not None
     m = xs.shape[0]
     dev = xs.device
     mean = torch.empty(st.B, m, dtype=F64, device=dev)
     var = torch.empty(st.B, m, dtype=F64, device=dev) if want_var else None
-    scratch = _scratch(int(_lib.load().gpr_predict_scratch_bytes(st.npad)), dev)
+    scratch = _work(scratch_kind, int(_lib.load().gpr_predict_scratch_bytes(st.npad)), dev)
     _lib.call("gpr_predict", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
               _p(st.prior), _p(xs), st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), int(want_var),
               _p(scratch), _stream())
     _count(1)
     return mean, var
+
+
+_side_streams = {}
+
+
+def side_stream(dev: torch.device):
+    """One high-priority side stream per device for the communication expert's work (its few CTAs then get an SM as
+    soon as one frees up, instead of queueing behind the local experts' launch)."""
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(dev, priority=-1)
+    return side
+
+
+def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
+    """GRBCM.predict's two predictions (gr_bcm.py:152-153) issued so that they overlap: the communication expert has only
+    ceil(m/128) tile tasks (a fraction of the SMs), so its kernel goes first on a side stream and the persistent kernel of
+    the local experts fills the remaining SMs at once and the rest as they drain — its tasks come off an atomic counter,
+    so the pair is work-conserving.  Returns ((mean_g, var_g), (mean_l, var_l)), all ordered on the current stream."""
+    dev = xs.device
+    main = torch.cuda.current_stream(dev)
+    side = side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        mg, vg = predict(st_g, xs, True, scratch_kind="predict_side")
+    ml, vl = predict(st_l, xs, True)
+    main.wait_stream(side)
+    mg.record_stream(main)
+    vg.record_stream(main)
+    return (mg, vg), (ml, vl)
 
 
 def lml_grad(st: FitState) -> torch.Tensor:

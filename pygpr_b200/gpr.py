@@ -115,18 +115,29 @@ class Exact_GP(GPR):
             y = y.expand(B, -1).contiguous()
         return x, y, hp
 
+    def _launch_update(self, ws_tag: str = "") -> None:
+        """Queue the factorisation on the current stream without reading anything back (GRBCM overlaps two of them)."""
+        spec = fused_spec(self.cov)
+        if spec is None:
+            raise _unsupported(self.cov)
+        x, y, hp = self._device_inputs()
+        assert hp.shape[-1] == self.cov.get_params_shape(self.x)[-1]
+        # refit in place: the old factor's buffer (it can fill most of HBM) is handed back to fit()
+        old, self._state = self._state, None
+        npad = engine.round_up(x.shape[1], engine.TILE)
+        L_buf = old.L if old is not None and tuple(old.L.shape) == (x.shape[0], npad, npad) and old.L.device == x.device else None
+        del old
+        self._state = engine.fit(x, y, hp, spec[0], L_out=L_buf, ws_tag=ws_tag)   # gpr.py:67-72
+
+    def _finish_update(self) -> None:
+        self._state.check()                                   # tc.cholesky raises on a non-PD matrix, gpr.py:69
+        self._krn = self._wt = self._krnchd = NotImplemented
+        self.need_upd = False
+
     def update(self) -> None:
         if self.need_upd:
-            spec = fused_spec(self.cov)
-            if spec is None:
-                raise _unsupported(self.cov)
-            x, y, hp = self._device_inputs()
-            assert hp.shape[-1] == self.cov.get_params_shape(self.x)[-1]
-            self._state = None                                # free the old factor first (it can fill most of HBM)
-            self._state = engine.fit(x, y, hp, spec[0])      # gpr.py:67-72
-            self._state.check()
-            self._krn = self._wt = self._krnchd = NotImplemented
-            self.need_upd = False
+            self._launch_update()
+            self._finish_update()
         return None
 
     def predict(self, xp: Tensor, var: str = "full") -> Sequence[Tensor]:

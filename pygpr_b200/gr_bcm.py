@@ -78,9 +78,39 @@ class GRBCM(GPR):
     def _aggregate_full(self, ys_g, covars_g, ys_l, covars_l):
         return engine.grbcm_aggregate_full(self, ys_g, covars_g, ys_l, covars_l)
 
+    def update(self):
+        """Fit both models (the reference does it lazily inside the two predict calls, gr_bcm.py:152-153 -> gpr.py:78).
+        When both are stale the communication expert (one matrix: dozens of small dependent launches) is factorised on a
+        high-priority side stream while the local experts' launch runs on the current one."""
+        g, l = self.gpg, self.gpl
+        if not (g.need_upd and l.need_upd):
+            g.update()
+            l.update()
+            return None
+        dev = engine.device()
+        main = torch.cuda.current_stream(dev)
+        side = engine.side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            g._launch_update(ws_tag="_side")
+        l._launch_update()
+        main.wait_stream(side)
+        g._state.record_stream(main)
+        g._finish_update()
+        l._finish_update()
+        return None
+
     def predict(self, xs, var="diag"):
-        ys_g, covars_g = self.gpg.predict(xs, var=var)        # gr_bcm.py:152
-        ys_l, covars_l = self.gpl.predict(xs, var=var)        # gr_bcm.py:153
+        if var == "diag":
+            # gr_bcm.py:152-153 with the two predictions overlapped on the device (engine.predict_pair)
+            self.update()
+            xd = engine._dev(xs).reshape(-1, xs.shape[-1])
+            (mg, vg), (ml, vl) = engine.predict_pair(self.gpg._state, self.gpl._state, xd)
+            ys_g, covars_g = _back(mg.squeeze(), self.gpg.x), self.gpg._shape_out(vg)
+            ys_l, covars_l = _back(ml.squeeze(), self.gpl.x), self.gpl._shape_out(vl)
+        else:
+            ys_g, covars_g = self.gpg.predict(xs, var=var)    # gr_bcm.py:152
+            ys_l, covars_l = self.gpl.predict(xs, var=var)    # gr_bcm.py:153
         if self.nc == 1:
             ys_l = ys_l.reshape(1, -1)
         return self.aggregate(ys_g, covars_g, ys_l, covars_l, var=var)  # gr_bcm.py:155
