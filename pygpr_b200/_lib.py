@@ -55,11 +55,12 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PYGPR_B200_LIB", LIB_PATH)   # developer knob: A/B a differently built library
+    if not os.path.exists(path):
         raise ImportError(
             "pygpr_b200: %s not found. Build it with `python pygpr_b200/csrc/build.py` "
-            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            "(or __graft_entry__.build()). There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means the .so is stale
         fn.restype = res

@@ -23,6 +23,7 @@ constexpr int NTHREADS = 256;                  // 8 warps: 4 (rows) x 2 (cols), 
 constexpr int STAGE_DOUBLES = 2 * TILE * SLD;  // A chunk tile + B chunk tile
 constexpr int MAIN_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163,840 B
 constexpr int XLD = 132;                       // row stride of a full 128x128 smem tile (132 mod 16 = 4)
+static_assert((KC / 4) % 2 == 0, "fragment double buffering across chunks needs an even number of k4 blocks");
 static_assert(TILE * XLD * 8 <= MAIN_SMEM_BYTES, "full tile must overlay the pipeline stages");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -112,7 +113,8 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][8][2]) {
 // for a stage that every warp left a whole chunk ago, and warps drift apart instead of hitting LDS/LDGSTS in lockstep.
 constexpr int PREFETCH = STAGES - 2;
 
-template <bool SAME_AB, typename HOOK>
+// XPF: fetch the first fragments of chunk c+1 during the last k4 block of chunk c (measured per kernel, see the XPF_* constants).
+template <bool SAME_AB, bool XPF = false, typename HOOK>
 __device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, const Seg& s1, double* smem, HOOK& hook,
                                          Pipe& pipe) {
     const int tid = threadIdx.x;
@@ -154,36 +156,86 @@ __device__ __forceinline__ void mainloop(double (&acc)[4][8][2], const Seg& s0, 
 
     const int aoff = (wm * 32 + g) * SLD + t;
     const int boff = (wn * 64 + g) * SLD + t;
-    for (int c = 0; c < total; ++c) {
-        const unsigned gc = g0 + c;
-        const unsigned st = gc % STAGES;
-        mbar_wait(pipe.bars + 8 * st, (gc / STAGES) & 1);
-        const double* sA = smem + st * STAGE_DOUBLES;
-        const double* sB = SAME_AB ? sA : sA + TILE * SLD;
-        hook.pre(c);
+    if constexpr (XPF) {
+        // Fragments are double buffered in registers ACROSS chunk boundaries (v4): the k4 block 0 of chunk c+1 is fetched
+        // during block 3 of chunk c (after checking that chunk c+1 has landed, which it has two chunks ahead of need), so a
+        // warp never sits between the barrier wait and its first LDS with an empty tensor pipe behind it.
         double fa[2][4], fb[2][8];
+        if (total > 0) {
+            mbar_wait(pipe.bars + 8 * (g0 % STAGES), (g0 / STAGES) & 1);
+            const double* sA = smem + (g0 % STAGES) * STAGE_DOUBLES;
+            const double* sB = SAME_AB ? sA : sA + TILE * SLD;
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) fa[0][mi] = sA[aoff + mi * 8 * SLD];
+            for (int mi = 0; mi < 4; ++mi) fa[0][mi] = sA[aoff + mi * 8 * SLD];
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) fb[0][ni] = sB[boff + ni * 8 * SLD];
-#pragma unroll
-        for (int kk = 0; kk < KC / 4; ++kk) {
-            const int cur = kk & 1, nxt = cur ^ 1;
-            if (kk + 1 < KC / 4) {
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi) fa[nxt][mi] = sA[aoff + mi * 8 * SLD + (kk + 1) * 4];
-#pragma unroll
-                for (int ni = 0; ni < 8; ++ni) fb[nxt][ni] = sB[boff + ni * 8 * SLD + (kk + 1) * 4];
-            }
-            issue_slice(c + PREFETCH, kk);
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[cur][mi], fb[cur][ni]);
+            for (int ni = 0; ni < 8; ++ni) fb[0][ni] = sB[boff + ni * 8 * SLD];
         }
-        hook.post(sA, c);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pipe.bars + 8 * (STAGES + st));
+        for (int c = 0; c < total; ++c) {
+            const unsigned gc = g0 + c;
+            const unsigned st = gc % STAGES;
+            const double* sA = smem + st * STAGE_DOUBLES;
+            const double* sB = SAME_AB ? sA : sA + TILE * SLD;
+            hook.pre(c);
+#pragma unroll
+            for (int kk = 0; kk < KC / 4; ++kk) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < KC / 4) {
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) fa[nxt][mi] = sA[aoff + mi * 8 * SLD + (kk + 1) * 4];
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) fb[nxt][ni] = sB[boff + ni * 8 * SLD + (kk + 1) * 4];
+                } else if (c + 1 < total) {
+                    const unsigned gn = gc + 1;
+                    mbar_wait(pipe.bars + 8 * (gn % STAGES), (gn / STAGES) & 1);
+                    const double* nA = smem + (gn % STAGES) * STAGE_DOUBLES;
+                    const double* nB = SAME_AB ? nA : nA + TILE * SLD;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) fa[nxt][mi] = nA[aoff + mi * 8 * SLD];
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) fb[nxt][ni] = nB[boff + ni * 8 * SLD];
+                }
+                issue_slice(c + PREFETCH, kk);
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[cur][mi], fb[cur][ni]);
+            }
+            hook.post(sA, c);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pipe.bars + 8 * (STAGES + st));
+        }
+    } else {
+        for (int c = 0; c < total; ++c) {
+            const unsigned gc = g0 + c;
+            const unsigned st = gc % STAGES;
+            mbar_wait(pipe.bars + 8 * st, (gc / STAGES) & 1);
+            const double* sA = smem + st * STAGE_DOUBLES;
+            const double* sB = SAME_AB ? sA : sA + TILE * SLD;
+            hook.pre(c);
+            double fa[2][4], fb[2][8];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) fa[0][mi] = sA[aoff + mi * 8 * SLD];
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) fb[0][ni] = sB[boff + ni * 8 * SLD];
+#pragma unroll
+            for (int kk = 0; kk < KC / 4; ++kk) {
+                const int cur = kk & 1, nxt = cur ^ 1;
+                if (kk + 1 < KC / 4) {
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) fa[nxt][mi] = sA[aoff + mi * 8 * SLD + (kk + 1) * 4];
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) fb[nxt][ni] = sB[boff + ni * 8 * SLD + (kk + 1) * 4];
+                }
+                issue_slice(c + PREFETCH, kk);
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[cur][mi], fb[cur][ni]);
+            }
+            hook.post(sA, c);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pipe.bars + 8 * (STAGES + st));
+        }
     }
     pipe.g = g0 + total;
     __syncthreads();

@@ -11,6 +11,16 @@
 
 using namespace gpr;
 
+// Cross-chunk fragment prefetch of the mainloop, chosen per kernel family from same-box A/B runs (tools/_ab.sh):
+// it helps the long single-product loops of the prediction (+1.5 %) and costs the factorisation ~1 %.
+#ifndef GPR_XPF_MASK
+#define GPR_XPF_MASK 2
+#endif
+constexpr bool XPF_POTRF = (GPR_XPF_MASK & 1) != 0;
+constexpr bool XPF_PREDICT = (GPR_XPF_MASK & 2) != 0;
+constexpr bool XPF_TRTRI = (GPR_XPF_MASK & 4) != 0;
+constexpr bool XPF_LAUUM = (GPR_XPF_MASK & 8) != 0;
+
 // ---------------------------------------------------------------------------------------------
 // error plumbing (no exceptions cross the C boundary)
 // ---------------------------------------------------------------------------------------------
@@ -390,7 +400,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     const double* Arow = Lb + ((long long)j * TILE) * npad + (long long)(j > 0 ? j - 1 : 0) * TILE;
     Seg s0{Arow, npad, Arow, npad, j > 0 ? TILE / KC : 0};
     Seg s1{nullptr, 0, nullptr, 0, 0};
-    mainloop<true>(acc, s0, s1, smem, hook, pipe);
+    mainloop<true, XPF_POTRF>(acc, s0, s1, smem, hook, pipe);
     const bool have_part = j >= 2;
     const double* dpart = Lb + ((long long)(j - 1) * TILE) * npad + (long long)j * TILE;  // upper block (j-1, j)
     hook.reduce_to(svec, (have_part && zb) ? zb + (long long)j * TILE : nullptr);
@@ -431,7 +441,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
         GemvHook hook;
         hook.init(z ? z + (long long)b * npad + (long long)kb0 * TILE : nullptr);
         Seg s0{Arow, npad, Arow, npad, (kb1 - kb0) * (TILE / KC)};
-        mainloop<true>(acc, s0, none, smem, hook, pipe);
+        mainloop<true, XPF_POTRF>(acc, s0, none, smem, hook, pipe);
         double* zdst = z ? z + (long long)b * npad + (long long)(j + 1) * TILE : nullptr;
         if (S > 1) {
             double* gv = sk_gemv + (long long)b * S * TILE;
@@ -460,7 +470,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
     NoHook nh;
     Seg s0{Lb + ((long long)i * TILE) * npad + (long long)kb0 * TILE, npad, Lb + ((long long)j * TILE) * npad + (long long)kb0 * TILE, npad,
            (kb1 - kb0) * (TILE / KC)};
-    mainloop<false>(acc, s0, none, smem, nh, pipe);
+    mainloop<false, XPF_POTRF>(acc, s0, none, smem, nh, pipe);
     if (S > 1 && !splitk_combine(acc, slots, part, S, counter, &s_flag)) return;
 
     if (GEN) {
@@ -503,7 +513,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
     // triangular solve as a product with the inverted diagonal block:  L_ij = Xhat * inv(L_jj)^T
     zero_acc(acc);
     Seg s1{Lij, npad, invdiag + ((long long)b * nt + j) * TILE * TILE, TILE, TILE / KC};
-    mainloop<false>(acc, s1, none, smem, nh, pipe);
+    mainloop<false, XPF_POTRF>(acc, s1, none, smem, nh, pipe);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -602,14 +612,14 @@ __device__ __forceinline__ int df_diag_task(const PotrfArgs& A, int b, int j, un
     if (j >= 2) {  // k-blocks 0..j-2 are older than the previous column
         if (!df_wait(prog + j, j - 1, abort_flag, A.info, &s_ok)) return -1;
         Seg s0{Arow, npad, Arow, npad, (j - 1) * (TILE / KC)};
-        mainloop<true>(acc, s0, none, smem, hook, pipe);
+        mainloop<true, XPF_POTRF>(acc, s0, none, smem, hook, pipe);
     }
     if (j >= 1) {  // the last k-block is tile (j, j-1) of the previous column
         if (!df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;
         hook.z = zb ? zb + (long long)(j - 1) * TILE : nullptr;
         const double* Alast = Arow + (long long)(j - 1) * TILE;
         Seg s0{Alast, npad, Alast, npad, TILE / KC};
-        mainloop<true>(acc, s0, none, smem, hook, pipe);
+        mainloop<true, XPF_POTRF>(acc, s0, none, smem, hook, pipe);
     }
     hook.reduce_to(svec, nullptr);
     diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, A.n, npad, A.a, A.nrm, A.hp, A.hp_stride, A.diag_add, A.dpad, A.invdiag,
@@ -639,7 +649,7 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
         if (!df_wait(prog + i, j, abort_flag, A.info, &s_ok)) return -1;  // L[i, 0:j]
         if (!df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;  // L[j, 0:j]
         Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
-        mainloop<false>(acc, s0, none, smem, nh, pipe);
+        mainloop<false, XPF_POTRF>(acc, s0, none, smem, nh, pipe);
     }
     if (GEN) {
         FeatSmem f = carve_feat(smem, dpad);
@@ -679,7 +689,7 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
     if (!df_wait(prog + j, j + 1, abort_flag, A.info, &s_ok)) return -1;  // inv(L_jj); the barrier inside also publishes X
     zero_acc(acc);
     Seg s1{Lij, npad, A.invdiag + ((long long)b * nt + j) * TILE * TILE, TILE, TILE / KC};
-    mainloop<false>(acc, s1, none, smem, nh, pipe);
+    mainloop<false, XPF_POTRF>(acc, s1, none, smem, nh, pipe);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -1049,7 +1059,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
                const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
                const double* __restrict__ prior, const double* __restrict__ xs, int B, int n, int npad, int d, int dpad, int m,
                double* __restrict__ mean, double* __restrict__ var, int want_var, double* __restrict__ scratch,
-               int* __restrict__ counter, double* __restrict__ vt_out) {
+               int* __restrict__ counter, double* __restrict__ vt_out, int feat_own) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -1065,6 +1075,9 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
     double* sT = smem + MAIN_SMEM_BYTES / 8;  // [128 x sld]
     double* nT = sT + TILE * sld;             // [128]
     double* sAl = nT + TILE;                  // [128] alpha block of the current step
+    // feat_own: the training-block features of step i get their own region and are fetched BEFORE the step's long product
+    // (they land while it runs); otherwise they are staged in the drained pipeline buffers after it (large d)
+    double* sCown = sAl + TILE;               // [128 x sld] + [128] norms
     double* Vt = scratch + (long long)blockIdx.x * TILE * npad;   // replaced per task when V^T is kept (vt_out)
     NoHook nh;
     Seg none{nullptr, 0, nullptr, 0, 0};
@@ -1099,18 +1112,28 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             double acc[4][8][2];
             zero_acc(acc);
             __syncthreads();  // V^T columns written by the previous step are visible; staged features are free
+            // K*(test tile, train block i) from smem-staged features
+            double* sC = feat_own ? sCown : smem;
+            double* nC = sC + TILE * sld;
+            if (feat_own) {
+                load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+                cp_async_commit();
+                if (tid < TILE) {
+                    nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
+                    sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
+                }
+            }
             if (want_var && i > 0) {
                 Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
-                mainloop<false>(acc, s0, none, smem, nh, pipe);
+                mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
             }
-            // K*(test tile, train block i) in smem-staged features
-            double* sC = smem;
-            double* nC = sC + TILE * sld;
-            load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
-            cp_async_commit();
-            if (tid < TILE) {
-                nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
-                sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
+            if (!feat_own) {
+                load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+                cp_async_commit();
+                if (tid < TILE) {
+                    nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
+                    sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
+                }
             }
             cp_async_wait<0>();
             __syncthreads();
@@ -1132,7 +1155,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             __syncthreads();
             zero_acc(acc);
             Seg s1{Vi, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
-            mainloop<false>(acc, s1, none, smem, nh, pipe);
+            mainloop<false, XPF_PREDICT>(acc, s1, none, smem, nh, pipe);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -1169,6 +1192,8 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
 }
 
 static inline long long predict_smem_bytes(int dpad) { return MAIN_SMEM_BYTES + (long long)(TILE * feat_sld(dpad) + 2 * TILE) * 8; }
+// with a private region for the training-block features (+ norms) when it still fits in 227 KB
+static inline long long predict_smem_bytes_own(int dpad) { return predict_smem_bytes(dpad) + (long long)(TILE * feat_sld(dpad) + TILE) * 8; }
 
 extern "C" long long gpr_predict_scratch_bytes(int npad) {
     int sms = gpr_device_sm_count();
@@ -1182,9 +1207,11 @@ extern "C" int gpr_predict(const double* L, const double* invdiag, const double*
     ARG_CHECK(L && invdiag && a && nrm && alpha && hp && xs && mean && scratch);
     ARG_CHECK(!want_var || (var && prior));
     ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
-    const long long smem = predict_smem_bytes(dpad);
+    long long smem = predict_smem_bytes(dpad);
     if (smem > 227 * 1024 || (TILE * feat_sld(dpad) + TILE) * 8 > MAIN_SMEM_BYTES)
         return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused prediction%s (dpad=%lld)", "", dpad);
+    const int feat_own = predict_smem_bytes_own(dpad) <= 227 * 1024 ? 1 : 0;
+    if (feat_own) smem = predict_smem_bytes_own(dpad);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(opt_in_smem(predict_kernel, (int)smem));
     int sms = gpr_device_sm_count();
@@ -1197,7 +1224,7 @@ extern "C" int gpr_predict(const double* L, const double* invdiag, const double*
     double* slabs = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
     CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
     predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
-                                                      mean, var, want_var, slabs, counter, nullptr);
+                                                      mean, var, want_var, slabs, counter, nullptr, feat_own);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }
@@ -1222,7 +1249,7 @@ covar_full_kernel(const double* __restrict__ vt, const double* __restrict__ as, 
     NoHook nh;
     Seg none{nullptr, 0, nullptr, 0, 0};
     Seg s0{Vb + (long long)ti * TILE * npad, npad, Vb + (long long)tj * TILE * npad, npad, npad / KC};
-    mainloop<false>(acc, s0, none, smem, nh, pipe);
+    mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
     FeatSmem f = carve_feat(smem, dpad);
     load_feat_tile(f.sR, f.sld, as + ((long long)b * mpad + ti * TILE) * dpad, dpad);
     load_feat_tile(f.sC, f.sld, as + ((long long)b * mpad + tj * TILE) * dpad, dpad);
@@ -1254,9 +1281,11 @@ extern "C" int gpr_predict_full(const double* L, const double* invdiag, const do
     ARG_CHECK(L && invdiag && a && nrm && alpha && hp && prior && xs && as && nrms && mean && var && cov && scratch);
     ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
     ARG_CHECK(mpad % TILE == 0 && mpad >= m && mpad - m < TILE);
-    const long long smem = predict_smem_bytes(dpad);
+    long long smem = predict_smem_bytes(dpad);
     if (smem > 227 * 1024 || feat_smem_bytes(dpad) > MAIN_SMEM_BYTES)
         return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused prediction%s (dpad=%lld)", "", dpad);
+    const int feat_own = predict_smem_bytes_own(dpad) <= 227 * 1024 ? 1 : 0;
+    if (feat_own) smem = predict_smem_bytes_own(dpad);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(opt_in_smem(predict_kernel, (int)smem));
     CUDA_TRY(opt_in_smem(covar_full_kernel, MAIN_SMEM_BYTES));
@@ -1269,7 +1298,7 @@ extern "C" int gpr_predict_full(const double* L, const double* invdiag, const do
     double* vt = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
     CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
     predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
-                                                      mean, var, 1, vt, counter, vt);
+                                                      mean, var, 1, vt, counter, vt, feat_own);
     covar_full_kernel<<<dim3(mt, mt, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(vt, as, nrms, hp, hp_stride, noise_var, m, mpad, npad, dpad, cov);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
@@ -1383,7 +1412,7 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
             const double* Li = Lb + ((long long)i * TILE) * npad;
             Seg s0{Ujj, TILE, Li + (long long)j * TILE, npad, TILE / KC};
             Seg s1{Urow + (long long)(j + 1) * TILE, npad, Li + (long long)(j + 1) * TILE, npad, (i - j - 1) * (TILE / KC)};
-            mainloop<false>(acc, s0, s1, smem, nh, pipe);
+            mainloop<false, XPF_TRTRI>(acc, s0, s1, smem, nh, pipe);
             double* Uji = Urow + (long long)i * TILE;
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
@@ -1395,7 +1424,7 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
             __syncthreads();
             zero_acc(acc);
             Seg s2{Uji, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
-            mainloop<false>(acc, s2, none, smem, nh, pipe);
+            mainloop<false, XPF_TRTRI>(acc, s2, none, smem, nh, pipe);
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -1442,7 +1471,7 @@ trtri_col_kernel(double* __restrict__ L, const double* __restrict__ invdiag, con
     Seg s0{Ujj, TILE, Li + (long long)j * TILE, npad, (q0 == 0) ? TILE / KC : 0};
     const int r0 = (q0 == 0) ? 1 : q0;
     Seg s1{Urow + (long long)(j + r0) * TILE, npad, Li + (long long)(j + r0) * TILE, npad, (q1 - r0) * (TILE / KC)};
-    mainloop<false>(acc, s0, s1, smem, nh, pipe);
+    mainloop<false, XPF_TRTRI>(acc, s0, s1, smem, nh, pipe);
     if (S > 1 && !splitk_combine(acc, sk_slots + ((long long)b * slots_per_expert + slot_off) * TILE * TILE, part, S,
                                  sk_counters + (long long)b * nt + j, &s_flag))
         return;
@@ -1457,7 +1486,7 @@ trtri_col_kernel(double* __restrict__ L, const double* __restrict__ invdiag, con
     __syncthreads();
     zero_acc(acc);
     Seg s2{Uji, npad, invdiag + ((long long)b * nt + i) * TILE * TILE, TILE, TILE / KC};
-    mainloop<false>(acc, s2, none, smem, nh, pipe);
+    mainloop<false, XPF_TRTRI>(acc, s2, none, smem, nh, pipe);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -1530,7 +1559,7 @@ lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdi
     NoHook nh;
     Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, TILE / KC};
     Seg s1{Ui + (long long)(i + 1) * TILE, npad, Uj + (long long)(i + 1) * TILE, npad, (nt - 1 - i) * (TILE / KC)};
-    mainloop<false>(acc, s0, s1, smem, nh, pipe);
+    mainloop<false, XPF_LAUUM>(acc, s0, s1, smem, nh, pipe);
 
     // epilogue: M = (K^-1 - alpha_i alpha_j^T) o K_se  -> smem tile
     double* Ms = smem;
@@ -1682,7 +1711,7 @@ lauum_store_kernel(const double* __restrict__ L, const double* __restrict__ invd
     NoHook nh;
     Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, TILE / KC};
     Seg s1{Ui + (long long)(i + 1) * TILE, npad, Uj + (long long)(i + 1) * TILE, npad, (nt - 1 - i) * (TILE / KC)};
-    mainloop<false>(acc, s0, s1, smem, nh, pipe);
+    mainloop<false, XPF_LAUUM>(acc, s0, s1, smem, nh, pipe);
     double* ob = out + (long long)b * ldo * ldo;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
