@@ -243,8 +243,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); e0.record(); model.update(); e1.record(); barrier()
     fit_ms = max_over_ranks(e0.elapsed_time(e1))
-    fit_flops = nc_total * n_l ** 3 / 3.0 + world * n_g ** 3 / 3.0  # the comm expert is replicated on every rank
     st = model.gpl._state
+    # One hyper-parameter vector for the committee (the GRBCM paper's setting and this workload's): every local expert's
+    # factor starts with the communication expert's 4096 x 4096 factor, which is computed once and reused
+    # (gpr_potrf_batched_shared / gpr_predict_shared).  The flop counts below are those of that algorithm; the counts of
+    # SURVEY 8(d), which treat the experts as unrelated matrices, are reported next to them as "*_unshared_count".
+    shared = st.shared_from is not None
+    fit_flops_unshared = nc_total * n_l ** 3 / 3.0 + world * n_g ** 3 / 3.0  # the comm expert is replicated on every rank
+    fit_flops = nc_total * (n_l ** 3 - n_g ** 3) / 3.0 + world * n_g ** 3 / 3.0 if shared else fit_flops_unshared
 
     # ---- steps: GRBCM.predict on m test points, factors resident -----------------------------------------------------
     xs_host = test_points(m, d).pin_memory()
@@ -304,22 +310,29 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    pred_flops_kernel = (nc_loc * float(n_l) ** 2 + float(n_g) ** 2) * m   # algorithmic N^2 per test point per expert
+    # algorithmic flops per launch pair: N^2 per test point per expert; with the shared leading block the first
+    # n_g rows of every expert's substitution are the communication expert's and are done once
+    pred_flops_unshared = (nc_loc * float(n_l) ** 2 + float(n_g) ** 2) * m
+    pred_flops_kernel = (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m if shared else pred_flops_unshared
     roof = {"bound": "tensor", "kernel": "predict_kernel (local experts; the communication expert's launch overlaps it on a side stream)", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf,
             # dram__bytes_read + dram__bytes_write of this launch (2.533 TB + 68.7 GB) from the ncu --set full capture in
             # profiles/r01_s2_ncu_predict_kernel_bench_scale.json (valid for the default 1-GPU config only)
-            "traffic": 2.602e12 if (world == 1 and not args.small and m == 4096) else None,
+            "traffic": 2.602e12 if (world == 1 and not args.small and m == 4096 and not shared) else None,
+            "shared_leading_block": shared, "unshared_count_tflops": pred_flops_unshared / kern_ms * 1e-9,
             "peak_source": "cuBLAS dgemm 8192^3 (A B^T) measured in this run on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
             "kernel_ms": kern_ms, "flops_per_launch": pred_flops_kernel}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": w["name"], "m_per_step": m, "experts_per_rank": nc_loc,
                                             "l2": "per-step working set (factors %.1f GB) exceeds the 126 MB L2" % (nc_loc * n_l * n_l * 8 / 1e9),
-                                            "parallelism": "experts sharded over %d GPU(s); all-reduce of [3,m] sums" % world},
+                                            "parallelism": "experts sharded over %d GPU(s); all-reduce of [3,m] sums" % world,
+                                            "shared_leading_block": shared},
             "roofline": roof,
             "fit": {"ms": fit_ms, "tflops": fit_flops / fit_ms * 1e-9, "frac_of_peak": fit_flops / fit_ms * 1e-9 / (peak_tf * world),
-                    "flops": fit_flops, "what": "batched Cholesky N^3/3 per expert incl. kernel build, forward+backward solve"},
+                    "flops": fit_flops, "unshared_count_tflops": fit_flops_unshared / fit_ms * 1e-9,
+                    "what": "batched Cholesky incl. kernel build, forward+backward solve; N^3/3 per expert, minus the shared "
+                            "communication block (n_g^3/3 per expert) when one hyper-parameter vector is shared"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m * d * 8, "d2h_bytes_per_step": 2 * m * 8,
                     "ms_per_step": e2e_ms}}

@@ -111,6 +111,20 @@ int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, co
 long long gpr_potrf_work_bytes(int B, int npad);
 
 /*
+ * The same factorisation for experts that all start with the SAME ng rows under the SAME hyper-parameters — GRBCM's local
+ * experts, whose training sets are the communication set followed by their own block (gr_bcm.py:19-26), when one
+ * hyper-parameter vector is shared.  The leading ng x ng block of every K is then the communication expert's matrix, so its
+ * factor (Lg, invdiag_g from gpr_potrf_batched on (xg, yg), gr_bcm.py:28) is read, not recomputed: only block rows >= ng/128
+ * are produced (7/8 of the flops at ng = n/2).  The caller pre-loads z[b, 0:ng], logdet_half[b], zz[b], info[b] with the
+ * communication expert's values (they are accumulated onto) and copies Lg / invdiag_g into the leading blocks of L / invdiag
+ * if a later call (gpr_trsv_backward, gpr_lml_grad, ...) needs the full factor.  ng must be a multiple of 128.
+ */
+int gpr_potrf_batched_shared(double* L, const double* a, const double* nrm, const double* hp, int hp_stride,
+                             const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y,
+                             double* z, double* logdet_half, double* zz, int* info, void* work, void* stream, int ng,
+                             const double* Lg, int npad_g, const double* invdiag_g);
+
+/*
  * alpha = L^-T z  (backward half of cholesky_solve, gpr.py:70-72).  HBM-bound: reads L once.
  *   z [B,npad] in, alpha [B,npad] out (may alias z only when work == NULL)
  *   work  >= gpr_trsv_work_bytes(B) or NULL.  With a workspace and fewer experts than SMs the solve runs as a
@@ -134,6 +148,23 @@ int gpr_predict(const double* L, const double* invdiag, const double* a, const d
                 const double* alpha, const double* hp, int hp_stride, const double* prior,
                 const double* xs, int B, int n, int npad, int d, int dpad, int m,
                 double* mean, double* var, int want_var, void* scratch, void* stream);
+
+/* gpr_predict that also keeps  V^T = K* L^-T  in vt [B, ceil(m/128), 128, npad] (rows >= m of the last tile are padding). */
+int gpr_predict_keep(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                     const double* hp, int hp_stride, const double* prior, const double* xs, int B, int n, int npad,
+                     int d, int dpad, int m, double* mean, double* var, double* vt, void* scratch, void* stream);
+
+/*
+ * Prediction of experts that share their first ng training rows and their hyper-parameters with a communication expert
+ * (see gpr_potrf_batched_shared).  vt_g / mean_g / var_g come from gpr_predict_keep on the communication expert for the same
+ * test points; z = L^-1 y of the local experts [B, npad].  Each expert is evaluated as an update of the communication
+ * expert:  mean = mean_g + V_l^T z_l ,  var = var_g - |V_l|^2  — identical to gpr_predict's K* alpha and prior - |V|^2
+ * (gpr.py:79-106) because the first ng rows of V and z are the communication expert's; 3/4 of the flops at ng = n/2.
+ */
+int gpr_predict_shared(const double* L, const double* invdiag, const double* a, const double* nrm, const double* z,
+                       const double* hp, int hp_stride, const double* xs, int B, int n, int npad, int d, int dpad, int m,
+                       double* mean, double* var, void* scratch, void* stream, int ng, const double* vt_g, int npad_g,
+                       const double* mean_g, const double* var_g);
 
 /*
  * Negative log marginal likelihood gradient without forming dK:

@@ -44,6 +44,9 @@ def hp_well(B, d, sig_n=0.3, jitter_seed=None):
     return hp
 
 
+ONLY = sys.argv[1:]   # optional name filters: regenerate only the matching fixtures (the others stay byte-identical)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -53,6 +56,8 @@ def main():
     # ---- covariance kernels: SE, WN, SE+WN, SE+SE+WN; batched and unbatched; cross kernels ----
     for name, B, n, d, m, keep_dk in [("covar_b1_n37_d3", 1, 37, 3, 11, True), ("covar_b4_n130_d5", 4, 130, 5, 29, False),
                                       ("covar_b3_n40_d16", 3, 40, 16, 150, True)]:
+        if ONLY and not any(o in name for o in ONLY):
+            continue
         x, _, xs = make_data(11, B, n, d, m)
         out = {"x": _np(x), "xs": _np(xs)}
         g = torch.Generator().manual_seed(5)
@@ -80,6 +85,8 @@ def main():
         ("gp_b3_n384_d8", 3, 384, 8, 130, (0.0, 1.0), "well"),
     ]
     for name, B, n, d, m, (lo, hi), kind in cases:
+        if ONLY and not any(o in name for o in ONLY):
+            continue
         x, y, xs = make_data(3, B, n, d, m, lo, hi)
         if lo == 0.0 and hi == 10.0:
             y = torch.sin(x.sum(-1))  # config 1: y = sin(x), no noise
@@ -112,7 +119,13 @@ def main():
     # ---- GRBCM ----
     for name, nc, nls, ng, d, m, kind in [("grbcm_nc4_nls64_ng32_d3", 4, 64, 32, 3, 50, "well"),
                                           ("grbcm_nc7_nls100_ng60_d5_perexpert", 7, 100, 60, 5, 40, "jit"),
-                                          ("grbcm_nc3_nls200_ng184_d16", 3, 200, 184, 16, 33, "well")]:
+                                          ("grbcm_nc3_nls200_ng184_d16", 3, 200, 184, 16, 33, "well"),
+                                          # tile-aligned communication sets + one shared hyper-parameter vector: the cases
+                                          # the shared-leading-block path of pygpr_b200 takes (gpr_potrf_batched_shared)
+                                          ("grbcm_nc5_nls150_ng128_d4_sharedhp", 5, 150, 128, 4, 70, "well"),
+                                          ("grbcm_nc6_nls200_ng256_d8_sharedhp", 6, 200, 256, 8, 45, "well")]:
+        if ONLY and not any(o in name for o in ONLY):
+            continue
         xl, yl, xs = make_data(21, nc, nls, d, m)
         xg, yg, _ = make_data(22, 1, ng, d, 1)
         xg, yg = xg[0], yg[0]

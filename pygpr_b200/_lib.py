@@ -22,6 +22,8 @@ SIGNATURES = {
     "gpr_last_error": (c_char_p, []),
     "gpr_device_sm_count": (c_int, []),
     "gpr_predict_scratch_bytes": (c_longlong, [_I]),
+    "gpr_predict_keep": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gpr_predict_shared": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "gpr_lml_grad_scratch_bytes": (c_longlong, [_I, _I, _I]),
     "gpr_se_scale": (c_int, [_P, _LL, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "gpr_se_build": (c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
@@ -29,6 +31,7 @@ SIGNATURES = {
     "gpr_se_kernel_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpr_potrf_work_bytes": (c_longlong, [_I, _I]),
+    "gpr_potrf_batched_shared": (c_int, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gpr_trsv_work_bytes": (c_longlong, [_I]),
     "gpr_predict": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),

@@ -18,7 +18,10 @@ namespace gpr {
 constexpr int TILE = 128;                      // CTA tile edge
 constexpr int KC = 16;                         // k-chunk (doubles) per pipeline stage = 128 B rows
 constexpr int SLD = 20;                        // smem row stride of a chunk tile; 20 mod 16 = 4 -> conflict-free 64-bit fragment loads
-constexpr int STAGES = 4;
+#ifndef GPR_STAGES
+#define GPR_STAGES 4
+#endif
+constexpr int STAGES = GPR_STAGES;
 constexpr int NTHREADS = 256;                  // 8 warps: 4 (rows) x 2 (cols), warp tile 32 x 64
 constexpr int STAGE_DOUBLES = 2 * TILE * SLD;  // A chunk tile + B chunk tile
 constexpr int MAIN_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163,840 B

@@ -286,9 +286,12 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
                                             int b, int j, int n, int npad, const double* __restrict__ a,
                                             const double* __restrict__ nrm, const double* __restrict__ hp, int hp_stride,
                                             const double* __restrict__ diag_add, int dpad, double* invdiag, const double* y,
-                                            double* zb, double* logdet_half, double* zz, int* info, const double* dpart) {
+                                            double* zb, double* logdet_half, double* zz, int* info, const double* dpart,
+                                            bool first = false, bool use_first = false) {
+    // first: this is the expert's first diagonal task (logdet / z.z / info start here).  Default (use_first == false): j == 0.
     const int tid = threadIdx.x;
     const int nt = npad / TILE;
+    const bool start = use_first ? first : (j == 0);
     double* Ljj = Lb + ((long long)j * TILE) * npad + j * TILE;
     if (tid == 0) *s_fail = 1 << 30;
     double* T = smem;  // full tile overlays the (drained) pipeline stages
@@ -342,10 +345,10 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
         for (int k = tid; k < TILE; k += 32) s += log(T[k * XLD + k]);
         s = warp_sum(s);
         if (tid == 0) {
-            if (logdet_half) __stcg(logdet_half + b, (j == 0 ? 0.0 : __ldcg(logdet_half + b)) + s);
+            if (logdet_half) __stcg(logdet_half + b, (start ? 0.0 : __ldcg(logdet_half + b)) + s);
             if (info) {
-                if (j == 0 && *s_fail > TILE) __stcg(info + b, 0);
-                if (*s_fail <= TILE && (j == 0 || __ldcg(info + b) == 0)) __stcg(info + b, j * TILE + *s_fail);
+                if (start && *s_fail > TILE) __stcg(info + b, 0);
+                if (*s_fail <= TILE && (start || __ldcg(info + b) == 0)) __stcg(info + b, j * TILE + *s_fail);
             }
         }
     }
@@ -370,7 +373,7 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
         if (tid < 32 && zz) {
             double s = svec[tid] + svec[tid + 32] + svec[tid + 64] + svec[tid + 96];
             s = warp_sum(s);
-            if (tid == 0) __stcg(zz + b, (j == 0 ? 0.0 : __ldcg(zz + b)) + s);
+            if (tid == 0) __stcg(zz + b, (start ? 0.0 : __ldcg(zz + b)) + s);
         }
     }
 }
@@ -586,6 +589,13 @@ struct PotrfArgs {
     int* info;
     int* ctl;       // [0] next task, [1] abort flag
     int* progress;  // [B, nt]
+    // Shared leading block (GRBCM with one hyper-parameter vector, gr_bcm.py:19-29): the first gt block rows/columns of every
+    // expert are the communication set, so L[0:gt, 0:gt] and inv(L_jj), j < gt, equal the communication expert's factor.
+    // They are read from (Lg, invdiag_g) and never computed; tasks exist only for block rows i >= gt.  gt = 0: off.
+    int gt;
+    const double* Lg;
+    int npad_g;
+    const double* invdiag_g;
 };
 
 // The two task bodies are separate NON-inlined functions so that each gets the register allocation of a stand-alone
@@ -622,8 +632,9 @@ __device__ __forceinline__ int df_diag_task(const PotrfArgs& A, int b, int j, un
         mainloop<true, XPF_POTRF>(acc, s0, none, smem, hook, pipe);
     }
     hook.reduce_to(svec, nullptr);
+    // with a shared leading block the host pre-loads logdet_half / zz with the communication expert's sums: never "start"
     diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, A.n, npad, A.a, A.nrm, A.hp, A.hp_stride, A.diag_add, A.dpad, A.invdiag,
-                     A.y, zb, A.logdet_half, A.zz, A.info, nullptr);
+                     A.y, zb, A.logdet_half, A.zz, A.info, nullptr, A.gt == 0 && j == 0, true);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_gpu(prog + j, j + 1);
@@ -645,10 +656,12 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
     Seg none{nullptr, 0, nullptr, 0, 0};
     double acc[4][8][2];
     zero_acc(acc);
+    const bool shared_col = j < A.gt;  // block column of the communication set: L[j, 0:j] and inv(L_jj) come from (Lg, invdiag_g)
     if (j > 0) {
         if (!df_wait(prog + i, j, abort_flag, A.info, &s_ok)) return -1;  // L[i, 0:j]
-        if (!df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;  // L[j, 0:j]
-        Seg s0{Lb + ((long long)i * TILE) * npad, npad, Lb + ((long long)j * TILE) * npad, npad, j * (TILE / KC)};
+        if (!shared_col && !df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;  // L[j, 0:j]
+        const double* Brow = shared_col ? A.Lg + ((long long)j * TILE) * A.npad_g : Lb + ((long long)j * TILE) * npad;
+        Seg s0{Lb + ((long long)i * TILE) * npad, npad, Brow, shared_col ? (long long)A.npad_g : (long long)npad, j * (TILE / KC)};
         mainloop<false, XPF_POTRF>(acc, s0, none, smem, nh, pipe);
     }
     if (GEN) {
@@ -686,9 +699,11 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
             }
     }
     __threadfence_block();
-    if (!df_wait(prog + j, j + 1, abort_flag, A.info, &s_ok)) return -1;  // inv(L_jj); the barrier inside also publishes X
+    if (shared_col) __syncthreads();  // publishes X to the CTA (df_wait's barrier does it otherwise)
+    else if (!df_wait(prog + j, j + 1, abort_flag, A.info, &s_ok)) return -1;  // inv(L_jj)
     zero_acc(acc);
-    Seg s1{Lij, npad, A.invdiag + ((long long)b * nt + j) * TILE * TILE, TILE, TILE / KC};
+    const double* invj = shared_col ? A.invdiag_g + (long long)j * TILE * TILE : A.invdiag + ((long long)b * nt + j) * TILE * TILE;
+    Seg s1{Lij, npad, invj, TILE, TILE / KC};
     mainloop<false, XPF_POTRF>(acc, s1, none, smem, nh, pipe);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
@@ -711,22 +726,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf_dataflow_kernel(const __gri
     __shared__ int s_col, s_local;
     Pipe pipe;
     if (threadIdx.x == 0) {
-        const int B = A.B, nt = A.npad / TILE;
+        const int B = A.B, nt = A.npad / TILE, gt = A.gt;
         const int task = atomicAdd(A.ctl, 1);
-        int col = 0, col_start = 0;  // tasks of block column `col` are [col_start, col_start + B (nt - col))
-        while (task >= col_start + B * (nt - col)) {
-            col_start += B * (nt - col);
+        // tasks of block column `col`: B diagonal tasks (col >= gt only) then B * (number of rows below max(col, gt-1)) panel tiles
+        int col = 0, col_start = 0;
+        for (;;) {
+            const int ntask = col < gt ? B * (nt - gt) : B * (nt - col);
+            if (task < col_start + ntask) break;
+            col_start += ntask;
             ++col;
         }
         s_col = col;
         s_local = task - col_start;
     }
     pipe_init(pipe, pipe_bars);  // ends with a CTA barrier
-    const int col = s_col, local = s_local;
-    if (local < A.B) {
+    const int col = s_col, local = s_local, nt = A.npad / TILE;
+    if (col < A.gt) {  // shared block column: panel tiles of the rows below the shared block only
+        const int per = nt - A.gt;
+        df_panel_task<GEN>(A, local / per, A.gt + local % per, col, 0u, pipe.bars);
+    } else if (local < A.B) {
         df_diag_task<GEN>(A, local, col, 0u, pipe.bars);
     } else {
-        const int per = A.npad / TILE - 1 - col;
+        const int per = nt - 1 - col;
         df_panel_task<GEN>(A, (local - A.B) / per, col + 1 + (local - A.B) % per, col, 0u, pipe.bars);
     }
 }
@@ -763,9 +784,10 @@ extern "C" long long gpr_potrf_work_bytes(int B, int npad) {
     return 256 + align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
 }
 
-extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
-                                 const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y,
-                                 double* z, double* logdet_half, double* zz, int* info, void* work, void* stream) {
+static int potrf_impl(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
+                      const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y, double* z,
+                      double* logdet_half, double* zz, int* info, void* work, void* stream, int gt, const double* Lg, int npad_g,
+                      const double* invdiag_g) {
     ARG_CHECK(L && invdiag);
     ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n);
     ARG_CHECK(!gen || (a && nrm && hp && dpad > 0 && dpad % 4 == 0));
@@ -788,11 +810,15 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
     // dependency chain of any one expert; the per-column form with split-K for few experts (PYGPR_POTRF_MODE overrides)
     {
         const char* mode = getenv("PYGPR_POTRF_MODE");
-        const long long total = (long long)B * nt * (nt + 1) / 2;
+        const long long total = (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
         // measured on B200 (tools/potrf_modes.py): dataflow wins from ~8 experts up (+8 % at B=32..63), ties at 4, loses below
         bool dataflow = work && nt >= 2 && B >= 6 && total < (1LL << 30);
         if (mode && !strcmp(mode, "columns")) dataflow = false;
         if (mode && !strcmp(mode, "dataflow") && work && total < (1LL << 30)) dataflow = true;
+        if (gt > 0) {  // the shared leading block exists in the dataflow form only
+            if (!work || total >= (1LL << 30)) return fail(GPR_ERR_BAD_ARG, "shared leading block needs a workspace%s", "");
+            dataflow = true;
+        }
         if (dataflow) {
             int smem_df = MAIN_SMEM_BYTES;
             if (gen) {
@@ -802,7 +828,8 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
                 if (TILE * XLD * 8 + fb > smem_df) smem_df = TILE * XLD * 8 + fb;
             }
             int* ctl = reinterpret_cast<int*>(work);
-            PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, ctl + 64};
+            PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, ctl + 64,
+                        gt, Lg, npad_g, invdiag_g};
             CUDA_TRY(cudaMemsetAsync(work, 0, 256 + (size_t)B * nt * 4, st));
             const int grid = (int)total;  // one CTA per tile task
             if (gen) {
@@ -851,6 +878,23 @@ extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const doub
     }
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
+}
+
+extern "C" int gpr_potrf_batched(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
+                                 const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y,
+                                 double* z, double* logdet_half, double* zz, int* info, void* work, void* stream) {
+    return potrf_impl(L, gen, a, nrm, hp, hp_stride, diag_add, B, n, npad, dpad, invdiag, y, z, logdet_half, zz, info, work, stream, 0,
+                      nullptr, 0, nullptr);
+}
+
+extern "C" int gpr_potrf_batched_shared(double* L, const double* a, const double* nrm, const double* hp, int hp_stride,
+                                        const double* diag_add, int B, int n, int npad, int dpad, double* invdiag, const double* y,
+                                        double* z, double* logdet_half, double* zz, int* info, void* work, void* stream, int ng,
+                                        const double* Lg, int npad_g, const double* invdiag_g) {
+    ARG_CHECK(Lg && invdiag_g && work && ng > 0 && ng % TILE == 0 && ng < n && npad_g >= ng && npad_g % TILE == 0);
+    ARG_CHECK(y && z && logdet_half && zz && info);
+    return potrf_impl(L, 1, a, nrm, hp, hp_stride, diag_add, B, n, npad, dpad, invdiag, y, z, logdet_half, zz, info, work, stream,
+                      ng / TILE, Lg, npad_g, invdiag_g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1054,12 +1098,28 @@ extern "C" int gpr_trsv_backward(const double* L, const double* invdiag, int B, 
 // (never in HBM), the mean  K* alpha  and the variance reduction  sum V^2  fused into the epilogues.
 // V^T lives in a per-CTA scratch slab [128, npad] that only this CTA touches.
 // ---------------------------------------------------------------------------------------------
+// SHARED (GRBCM with one hyper-parameter vector): the first gt block rows of every expert are the communication set, so
+// the first gt substitution steps of a test tile are the same for all experts — they ARE the communication expert's
+// V_g^T (kept by its own prediction, [m tiles][128][npad_g]).  A task then starts at step gt, multiplies against V_g^T for the
+// k-blocks < gt, and reports the expert as an update of the communication expert:
+//     mean = mean_g + V_l^T z_l      (K* alpha = V^T z, and V_g^T z_g is the communication expert's mean)
+//     var  = var_g  - |V_l|^2        (var_g = prior - |V_g|^2)
+// which removes 1/4 of the flops at ng = n/2 (and all K* tiles of the shared block).  `alpha` carries z in this mode.
+struct PredShared {
+    int gt;
+    const double* Vg;
+    int npad_g;
+    const double* mean_g;
+    const double* var_g;
+};
+
+template <bool SHARED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ a,
                const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
                const double* __restrict__ prior, const double* __restrict__ xs, int B, int n, int npad, int d, int dpad, int m,
                double* __restrict__ mean, double* __restrict__ var, int want_var, double* __restrict__ scratch,
-               int* __restrict__ counter, double* __restrict__ vt_out, int feat_own) {
+               int* __restrict__ counter, double* __restrict__ vt_out, int feat_own, const PredShared sh) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -1108,7 +1168,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
         }
         double macc[4] = {0, 0, 0, 0}, vacc[4] = {0, 0, 0, 0};
 
-        for (int i = 0; i < nt; ++i) {
+        for (int i = SHARED ? sh.gt : 0; i < nt; ++i) {
             double acc[4][8][2];
             zero_acc(acc);
             __syncthreads();  // V^T columns written by the previous step are visible; staged features are free
@@ -1123,7 +1183,12 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
                     sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
                 }
             }
-            if (want_var && i > 0) {
+            if (SHARED) {
+                const double* Li = Lb + ((long long)i * TILE) * npad;
+                Seg s0{sh.Vg + (long long)ct * TILE * sh.npad_g, sh.npad_g, Li, npad, sh.gt * (TILE / KC)};
+                Seg s1{Vt + (long long)sh.gt * TILE, npad, Li + (long long)sh.gt * TILE, npad, (i - sh.gt) * (TILE / KC)};
+                mainloop<false, XPF_PREDICT>(acc, s0, s1, smem, nh, pipe);
+            } else if (want_var && i > 0) {
                 Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
                 mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
             }
@@ -1141,7 +1206,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             gen_se_tile(sT, sC, sld, nT, nC, dpad, sig2, [&](int mi, int ni, int e, double kv) {
                 const int c = acc_col(ni, e);
                 if (i * TILE + c >= n) kv = 0.0;  // padding columns carry no covariance
-                macc[mi] += kv * sAl[c];
+                if (!SHARED) macc[mi] += kv * sAl[c];
                 acc[mi][ni][e] = kv - acc[mi][ni][e];
             });
             if (!want_var) continue;
@@ -1161,6 +1226,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni) {
                     vacc[mi] += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+                    if (SHARED) macc[mi] += acc[mi][ni][0] * sAl[acc_col(ni, 0)] + acc[mi][ni][1] * sAl[acc_col(ni, 1)];  // V^T z
                     *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
                         make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                 }
@@ -1184,8 +1250,13 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
         if (tid < TILE) {
             const int gr = ct * TILE + tid;
             if (gr < m) {
-                mean[(long long)b * m + gr] = red[0][0][tid] + red[0][1][tid];
-                if (want_var) var[(long long)b * m + gr] = prior[b] - (red[1][0][tid] + red[1][1][tid]);
+                if (SHARED) {
+                    mean[(long long)b * m + gr] = sh.mean_g[gr] + (red[0][0][tid] + red[0][1][tid]);
+                    var[(long long)b * m + gr] = sh.var_g[gr] - (red[1][0][tid] + red[1][1][tid]);
+                } else {
+                    mean[(long long)b * m + gr] = red[0][0][tid] + red[0][1][tid];
+                    if (want_var) var[(long long)b * m + gr] = prior[b] - (red[1][0][tid] + red[1][1][tid]);
+                }
             }
         }
     }
@@ -1201,11 +1272,12 @@ extern "C" long long gpr_predict_scratch_bytes(int npad) {
     return (long long)sms * TILE * npad * 8 + 256;
 }
 
-extern "C" int gpr_predict(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
-                           const double* hp, int hp_stride, const double* prior, const double* xs, int B, int n, int npad,
-                           int d, int dpad, int m, double* mean, double* var, int want_var, void* scratch, void* stream) {
+static int predict_impl(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                        const double* hp, int hp_stride, const double* prior, const double* xs, int B, int n, int npad, int d,
+                        int dpad, int m, double* mean, double* var, int want_var, void* scratch, void* stream, double* vt_out,
+                        const PredShared* shp) {
     ARG_CHECK(L && invdiag && a && nrm && alpha && hp && xs && mean && scratch);
-    ARG_CHECK(!want_var || (var && prior));
+    ARG_CHECK(!want_var || (var && (prior || shp)));
     ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
     long long smem = predict_smem_bytes(dpad);
     if (smem > 227 * 1024 || (TILE * feat_sld(dpad) + TILE) * 8 > MAIN_SMEM_BYTES)
@@ -1213,7 +1285,6 @@ extern "C" int gpr_predict(const double* L, const double* invdiag, const double*
     const int feat_own = predict_smem_bytes_own(dpad) <= 227 * 1024 ? 1 : 0;
     if (feat_own) smem = predict_smem_bytes_own(dpad);
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(opt_in_smem(predict_kernel, (int)smem));
     int sms = gpr_device_sm_count();
     if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
     const int mt = (m + TILE - 1) / TILE;
@@ -1223,10 +1294,44 @@ extern "C" int gpr_predict(const double* L, const double* invdiag, const double*
     int* counter = reinterpret_cast<int*>(scratch);
     double* slabs = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
     CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
-    predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
-                                                      mean, var, want_var, slabs, counter, nullptr, feat_own);
+    if (shp) {
+        CUDA_TRY(opt_in_smem(predict_kernel<true>, (int)smem));
+        predict_kernel<true><<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad,
+                                                                m, mean, var, 1, slabs, counter, nullptr, feat_own, *shp);
+    } else {
+        CUDA_TRY(opt_in_smem(predict_kernel<false>, (int)smem));
+        predict_kernel<false><<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad,
+                                                                 m, mean, var, want_var, vt_out ? vt_out : slabs, counter, vt_out, feat_own,
+                                                                 PredShared{0, nullptr, 0, nullptr, nullptr});
+    }
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
+}
+
+extern "C" int gpr_predict(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                           const double* hp, int hp_stride, const double* prior, const double* xs, int B, int n, int npad,
+                           int d, int dpad, int m, double* mean, double* var, int want_var, void* scratch, void* stream) {
+    return predict_impl(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m, mean, var, want_var, scratch,
+                        stream, nullptr, nullptr);
+}
+
+// gpr_predict that also keeps V^T = K* L^-T  [B, ceil(m/128), 128, npad]  (the shared prefix of gpr_predict_shared)
+extern "C" int gpr_predict_keep(const double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                                const double* hp, int hp_stride, const double* prior, const double* xs, int B, int n, int npad,
+                                int d, int dpad, int m, double* mean, double* var, double* vt, void* scratch, void* stream) {
+    ARG_CHECK(vt);
+    return predict_impl(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m, mean, var, 1, scratch, stream, vt,
+                        nullptr);
+}
+
+extern "C" int gpr_predict_shared(const double* L, const double* invdiag, const double* a, const double* nrm, const double* z,
+                                  const double* hp, int hp_stride, const double* xs, int B, int n, int npad, int d, int dpad, int m,
+                                  double* mean, double* var, void* scratch, void* stream, int ng, const double* vt_g, int npad_g,
+                                  const double* mean_g, const double* var_g) {
+    ARG_CHECK(vt_g && mean_g && var_g && z && var && ng > 0 && ng % TILE == 0 && ng < n && npad_g >= ng && npad_g % TILE == 0);
+    PredShared sh{ng / TILE, vt_g, npad_g, mean_g, var_g};
+    return predict_impl(L, invdiag, a, nrm, z, hp, hp_stride, nullptr, xs, B, n, npad, d, dpad, m, mean, var, 1, scratch, stream, nullptr,
+                        &sh);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1287,7 +1392,7 @@ extern "C" int gpr_predict_full(const double* L, const double* invdiag, const do
     const int feat_own = predict_smem_bytes_own(dpad) <= 227 * 1024 ? 1 : 0;
     if (feat_own) smem = predict_smem_bytes_own(dpad);
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(opt_in_smem(predict_kernel, (int)smem));
+    CUDA_TRY(opt_in_smem(predict_kernel<false>, (int)smem));
     CUDA_TRY(opt_in_smem(covar_full_kernel, MAIN_SMEM_BYTES));
     int sms = gpr_device_sm_count();
     if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
@@ -1297,8 +1402,9 @@ extern "C" int gpr_predict_full(const double* L, const double* invdiag, const do
     int* counter = reinterpret_cast<int*>(scratch);
     double* vt = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 256);
     CUDA_TRY(cudaMemsetAsync(counter, 0, 256, st));
-    predict_kernel<<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
-                                                      mean, var, 1, vt, counter, vt, feat_own);
+    predict_kernel<false><<<grid, NTHREADS, (int)smem, st>>>(L, invdiag, a, nrm, alpha, hp, hp_stride, prior, xs, B, n, npad, d, dpad, m,
+                                                             mean, var, 1, vt, counter, vt, feat_own,
+                                                             PredShared{0, nullptr, 0, nullptr, nullptr});
     covar_full_kernel<<<dim3(mt, mt, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(vt, as, nrms, hp, hp_stride, noise_var, m, mpad, npad, dpad, cov);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;

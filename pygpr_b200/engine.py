@@ -126,6 +126,7 @@ class FitState:
     zz: torch.Tensor          # [B]
     info: torch.Tensor        # [B] int32
     prior: torch.Tensor       # [B] sig^2 + sig_n^2
+    shared_from: Optional["FitState"] = None   # communication expert whose factor is the leading block of every expert here
 
     def nlml(self) -> torch.Tensor:
         """NLML = 1/2 y^T alpha + sum log L_ii + n/2 log 2 pi   (loss.py:49-51); y^T alpha = z.z"""
@@ -155,12 +156,24 @@ def split_hp(hp: torch.Tensor, d: int, has_noise: bool, jitter: float = JITTER):
     return torch.full_like(sig2, jitter), sig2.contiguous()
 
 
+def can_share(shared: Optional[FitState], n: int, d: int, has_noise: bool) -> bool:
+    """Shape conditions for the shared leading block (the caller vouches that rows 0:ng of every expert are the
+    communication set and that all hyper-parameter rows equal the communication expert's)."""
+    return (shared is not None and shared.B == 1 and shared.alpha is not None and shared.n % TILE == 0 and shared.n < n
+            and shared.d == d and shared.has_noise == has_noise)
+
+
 def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, want_alpha: bool = True,
-        jitter: float = JITTER, L_out: Optional[torch.Tensor] = None, ws_tag: str = "") -> FitState:
+        jitter: float = JITTER, L_out: Optional[torch.Tensor] = None, ws_tag: str = "",
+        shared: Optional[FitState] = None) -> FitState:
     """Batched Exact_GP.update (gpr.py:65-74) for cov = Compose([SE, WN]) or SE alone.
 
     K is never materialised: tiles are generated inside the factorisation (gen=1).
     x:[B,n,d], y:[B,n], hp:[B,P] — CUDA float64 contiguous.
+
+    shared: the fitted communication expert when every expert's first ``shared.n`` rows are its training set and every
+    hyper-parameter row equals its own (GRBCM with one shared vector): its factor is then the leading block of every
+    expert's factor and is reused instead of recomputed (gpr_potrf_batched_shared).
     """
     B, n, d = x.shape
     assert hp.shape == (B, d + 1 + int(has_noise)), (hp.shape, B, d, has_noise)
@@ -179,16 +192,31 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     zz = torch.empty(B, dtype=F64, device=dev)
     info = torch.empty(B, dtype=torch.int32, device=dev)
     work = _work("potrf" + ws_tag, int(_lib.load().gpr_potrf_work_bytes(B, npad)), dev)   # ws_tag: a fit on another stream
-    _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
-              _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream())
-    _count(2 * nt - 1)
+    if shared is not None:
+        assert can_share(shared, n, d, has_noise)
+        ng, gt = shared.n, shared.n // TILE
+        z[:, :ng] = shared.z[0, :ng]                      # the forward solve, log-determinant and y^T K^-1 y continue
+        logdet_half[:] = shared.logdet_half[0]            # from the communication expert's values
+        zz[:] = shared.zz[0]
+        info[:] = shared.info[0]
+        _lib.call("gpr_potrf_batched_shared", _p(L), _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
+                  _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream(), ng,
+                  _p(shared.L), shared.npad, _p(shared.invdiag))
+        # the leading block itself, for the kernels that walk the whole factor (backward solve, gradient, full covariance)
+        L[:, :ng, :ng] = shared.L[0, :ng, :ng]
+        invdiag[:, :gt] = shared.invdiag[0, :gt]
+        _count(1)
+    else:
+        _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
+                  _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream())
+        _count(2 * nt - 1)
     alpha = None
     if want_alpha:
         alpha = torch.empty(B, npad, dtype=F64, device=dev)
         twork = _work("trsv" + ws_tag, int(_lib.load().gpr_trsv_work_bytes(B)), dev)
         _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _p(twork), _stream())
         _count(1)
-    return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior)
+    return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior, shared)
 
 
 def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
@@ -261,6 +289,8 @@ def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     their own time (measured at 32 experts, the 8-GPU share of config 4: 281 -> 273 ms per 4096 test points).
     Returns ((mean_g, var_g), (mean_l, var_l)), all ordered on the current stream."""
     dev = xs.device
+    if st_l.shared_from is st_g:
+        return predict_shared(st_g, st_l, xs)
     main = torch.cuda.current_stream(dev)
     side = side_stream(dev, high_priority=False)
     side.wait_stream(main)                    # inputs are ready; taken BEFORE the big launch so the side stream does not wait for it
@@ -270,6 +300,32 @@ def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     main.wait_stream(side)
     mg.record_stream(main)
     vg.record_stream(main)
+    return (mg, vg), (ml, vl)
+
+
+def predict_shared(st_g: FitState, st_l: FitState, xs: torch.Tensor):
+    """The two predictions of GRBCM.predict when the local experts were fitted on top of the communication expert's factor
+    (fit(shared=st_g)): the communication expert's V_g^T = K*_g L_g^-T is kept and every local expert continues the
+    substitution from block row ng/128 (gpr_predict_keep + gpr_predict_shared).  Same return value as predict_pair."""
+    assert st_l.shared_from is st_g and st_g.B == 1
+    m = xs.shape[0]
+    dev = xs.device
+    lib = _lib.load()
+    mt = (m + TILE - 1) // TILE
+    mg = torch.empty(1, m, dtype=F64, device=dev)
+    vg = torch.empty(1, m, dtype=F64, device=dev)
+    vt = _work("predict_vt", mt * TILE * st_g.npad * 8, dev)
+    scratch_g = _work("predict_side", int(lib.gpr_predict_scratch_bytes(st_g.npad)), dev)
+    _lib.call("gpr_predict_keep", _p(st_g.L), _p(st_g.invdiag), _p(st_g.a), _p(st_g.nrm), _p(st_g.alpha), _p(st_g.hp),
+              st_g.hp.shape[-1], _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt),
+              _p(scratch_g), _stream())
+    ml = torch.empty(st_l.B, m, dtype=F64, device=dev)
+    vl = torch.empty(st_l.B, m, dtype=F64, device=dev)
+    scratch = _work("predict", int(lib.gpr_predict_scratch_bytes(st_l.npad)), dev)
+    _lib.call("gpr_predict_shared", _p(st_l.L), _p(st_l.invdiag), _p(st_l.a), _p(st_l.nrm), _p(st_l.z), _p(st_l.hp),
+              st_l.hp.shape[-1], _p(xs), st_l.B, st_l.n, st_l.npad, st_l.d, st_l.dpad, m, _p(ml), _p(vl), _p(scratch), _stream(),
+              st_g.n, _p(vt), st_g.npad, _p(mg), _p(vg))
+    _count(2)
     return (mg, vg), (ml, vl)
 
 

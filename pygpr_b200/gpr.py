@@ -115,7 +115,7 @@ class Exact_GP(GPR):
             y = y.expand(B, -1).contiguous()
         return x, y, hp
 
-    def _launch_update(self, ws_tag: str = "") -> None:
+    def _launch_update(self, ws_tag: str = "", shared=None) -> None:
         """Queue the factorisation on the current stream without reading anything back (GRBCM overlaps two of them)."""
         spec = fused_spec(self.cov)
         if spec is None:
@@ -127,7 +127,9 @@ class Exact_GP(GPR):
         npad = engine.round_up(x.shape[1], engine.TILE)
         L_buf = old.L if old is not None and tuple(old.L.shape) == (x.shape[0], npad, npad) and old.L.device == x.device else None
         del old
-        self._state = engine.fit(x, y, hp, spec[0], L_out=L_buf, ws_tag=ws_tag)   # gpr.py:67-72
+        if shared is not None and not engine.can_share(shared, x.shape[1], x.shape[2], spec[0]):
+            shared = None
+        self._state = engine.fit(x, y, hp, spec[0], L_out=L_buf, ws_tag=ws_tag, shared=shared)   # gpr.py:67-72
 
     def _finish_update(self) -> None:
         self._state.check()                                   # tc.cholesky raises on a non-PD matrix, gpr.py:69

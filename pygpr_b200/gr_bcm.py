@@ -5,7 +5,7 @@ import torch
 
 from . import dist as gdist
 from . import engine
-from .covar import _back
+from .covar import _back, fused_spec
 from .gpr import GPR, Exact_GP
 
 
@@ -83,6 +83,18 @@ class GRBCM(GPR):
         When both are stale the communication expert (one matrix: dozens of small dependent launches) is factorised on a
         high-priority side stream while the local experts' launch runs on the current one."""
         g, l = self.gpg, self.gpl
+        if self._shares_hyperparameters():
+            # one hyper-parameter vector for the whole committee: the local experts' factors start with the communication
+            # expert's (gr_bcm.py:19-26 puts its training set first in every expert), so it is fitted first and reused
+            if g.need_upd:
+                g.update()
+                l.need_upd = True
+            if l.need_upd:
+                l._launch_update(shared=g._state)
+                l._finish_update()
+            return None
+        if l._state is not None and l._state.shared_from is not None and not l.need_upd and g.need_upd:
+            l.need_upd = True                                 # the local factors were built on a communication factor that is stale
         if not (g.need_upd and l.need_upd):
             g.update()
             l.update()
@@ -99,6 +111,22 @@ class GRBCM(GPR):
         g._finish_update()
         l._finish_update()
         return None
+
+    def _shares_hyperparameters(self) -> bool:
+        """True when every local expert's hyper-parameter row equals the communication expert's vector (the GRBCM paper's
+        setting, and what GRBCM_MLE trains) and the communication set is tile aligned — the conditions of the shared
+        leading block (engine.fit(shared=...))."""
+        import os
+        g, l = self.gpg, self.gpl
+        if os.environ.get("PYGPR_GRBCM_SHARE", "1") == "0":   # A/B knob: treat the experts as unrelated matrices
+            return False
+        if fused_spec(g.cov) is None or self.ng % engine.TILE != 0 or self.nsc < 1:
+            return False
+        pg = g.params.detach().reshape(-1)
+        pl = l.params.detach().reshape(-1, l.params.shape[-1])
+        if pl.shape[-1] != pg.shape[0]:
+            return False
+        return bool((pl.to(pg.device) == pg).all())
 
     def predict(self, xs, var="diag"):
         if var == "diag":
