@@ -314,7 +314,9 @@ def main():
     # n_g rows of every expert's substitution are the communication expert's and are done once
     pred_flops_unshared = (nc_loc * float(n_l) ** 2 + float(n_g) ** 2) * m
     pred_flops_kernel = (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m if shared else pred_flops_unshared
-    roof = {"bound": "tensor", "kernel": "predict_kernel (local experts; the communication expert's launch overlaps it on a side stream)", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
+    roof = {"bound": "tensor", "kernel": ("predict_kernel<shared> (local experts continue the communication expert's substitution; its V_g^T comes "
+                                         "from vt_gemm_kernel inside the same bracket)") if shared else
+            "predict_kernel (local experts; the communication expert's launch overlaps it on a side stream)", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf,
             # dram__bytes_read + dram__bytes_write of this launch (2.533 TB + 68.7 GB) from the ncu --set full capture in
             # profiles/r01_s2_ncu_predict_kernel_bench_scale.json (valid for the default 1-GPU config only)

@@ -167,6 +167,23 @@ int gpr_predict_shared(const double* L, const double* invdiag, const double* a, 
                        const double* mean_g, const double* var_g);
 
 /*
+ * X[b] = L[b]^-1 (lower triangular, row-major, [B, npad, npad]) from a factor of gpr_potrf_batched; overwrites the strict
+ * block-upper part of L with L^-T on the way (like gpr_potri_batched).  scratch >= gpr_potri_scratch_bytes(B, npad).
+ */
+int gpr_tril_inverse(double* L, const double* invdiag, int B, int npad, double* X, void* scratch, void* stream);
+
+/*
+ * gpr_predict_keep in GEMM form:  V^T = K* X^T  with X = L^-1 from gpr_tril_inverse — (m/128) x (n/128) independent tiles
+ * instead of ceil(m/128) serial substitutions, for the single communication expert whose V^T every local expert waits for.
+ *   mean = V^T z (= K* alpha, gpr.py:79-85),  var = prior - |V|^2 (gpr.py:96-106),  vt [B, ceil(m/128), 128, npad]
+ *   z = L^-1 y [B, npad];  scratch >= gpr_predict_gemm_scratch_bytes(B, npad, dpad, m)
+ */
+int gpr_predict_gemm(const double* X, const double* a, const double* nrm, const double* z, const double* hp, int hp_stride,
+                     const double* prior, const double* xs, int B, int n, int npad, int d, int dpad, int m, double* mean,
+                     double* var, double* vt, void* scratch, void* stream);
+long long gpr_predict_gemm_scratch_bytes(int B, int npad, int dpad, int m);
+
+/*
  * Negative log marginal likelihood gradient without forming dK:
  *   U = L^-T (blocked, DMMA) written into the strict block-upper part of L's buffer, then
  *   K^-1 = U U^T tile by tile with a fused epilogue reducing  W = K^-1 - alpha alpha^T  against

@@ -1792,6 +1792,160 @@ extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Communication expert in GEMM form (shared-leading-block prediction).  The substitution of predict_kernel gives one
+// serial task per 128 test points — ceil(m/128) busy SMs while the local experts wait for V_g^T.  With X = L^-1 formed once
+// per fit (gpr_tril_inverse: L^-T by the blocked trtri, transposed into a lower-triangular row-major matrix), the same
+// V_g^T = K* X^T is a triangular GEMM with (m/128) x (n/128) independent tiles:
+//   vt_gemm_kernel     : V^T[ct, :, j] = sum_{k <= j} K*[ct, k] X[j, k]^T  + per-row partials of |V|^2 and V^T z
+//   vt_finalize_kernel : mean = sum_j partials (= V^T z = K* alpha),  var = prior - sum_j |V_j|^2   (fixed order, no atomics)
+// ---------------------------------------------------------------------------------------------
+__global__ void tril_from_upper_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad,
+                                       double* __restrict__ X) {
+    // X[r][c] = U[c][r] for block row > block column (U = L^-T sits in the strict block-upper part of L), diagonal blocks
+    // from invdiag, zero above.  32 x 32 tiles through shared memory.
+    __shared__ double t[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int br = r0 / TILE, bc = c0 / TILE, nt = npad / TILE;
+    const double* Lb = L + (long long)b * npad * npad;
+    double* Xb = X + (long long)b * npad * npad;
+    if (bc > br) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) Xb[(long long)(r0 + r) * npad + c0 + threadIdx.x] = 0.0;
+    } else if (bc == br) {
+        const double* inv = invdiag + ((long long)b * nt + br) * TILE * TILE;
+        for (int r = threadIdx.y; r < 32; r += blockDim.y)
+            Xb[(long long)(r0 + r) * npad + c0 + threadIdx.x] = inv[(r0 - br * TILE + r) * TILE + (c0 - bc * TILE + threadIdx.x)];
+    } else {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = Lb[(long long)(c0 + r) * npad + r0 + threadIdx.x];
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) Xb[(long long)(r0 + r) * npad + c0 + threadIdx.x] = t[threadIdx.x][r];
+    }
+}
+
+extern "C" int gpr_tril_inverse(double* L, const double* invdiag, int B, int npad, double* X, void* scratch, void* stream) {
+    ARG_CHECK(L && invdiag && X && scratch && B > 0 && npad > 0 && npad % TILE == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + trtri_work_bytes(B, npad, sms));
+    transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
+    {
+        const int rc = launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st);
+        if (rc != GPR_OK) return rc;
+    }
+    tril_from_upper_kernel<<<dim3(npad / 32, npad / 32, B), dim3(32, 8), 0, st>>>(L, invdiag, npad, X);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+vt_gemm_kernel(const double* __restrict__ Ks, const double* __restrict__ X, const double* __restrict__ z, int npad, int mpad,
+               double* __restrict__ vt, double* __restrict__ pv, double* __restrict__ pm) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    __shared__ double zj[TILE];
+    __shared__ double red[2][2][TILE];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
+    const int nt = npad / TILE;
+    const int j = nt - 1 - blockIdx.x, ct = blockIdx.y, b = blockIdx.z;  // long k-ranges first
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < TILE) zj[tid] = z[(long long)b * npad + j * TILE + tid];
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    Seg s0{Ks + ((long long)b * mpad + (long long)ct * TILE) * npad, npad, X + (long long)b * npad * npad + ((long long)j * TILE) * npad, npad,
+           (j + 1) * (TILE / KC)};
+    mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
+    double* Vt = vt + (((long long)b * (mpad / TILE) + ct) * TILE) * npad + (long long)j * TILE;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        double vv = 0.0, mv = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+            vv += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+            mv += acc[mi][ni][0] * zj[acc_col(ni, 0)] + acc[mi][ni][1] * zj[acc_col(ni, 1)];
+            *reinterpret_cast<double2*>(Vt + (long long)acc_row(mi) * npad + acc_col(ni, 0)) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+        vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+        vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+        mv += __shfl_xor_sync(0xffffffffu, mv, 1);
+        mv += __shfl_xor_sync(0xffffffffu, mv, 2);
+        if ((lane & 3) == 0) {
+            red[0][warp >> 2][acc_row(mi)] = mv;
+            red[1][warp >> 2][acc_row(mi)] = vv;
+        }
+    }
+    __syncthreads();
+    if (tid < TILE) {
+        const long long o = ((long long)b * nt + j) * mpad + (long long)ct * TILE + tid;
+        pm[o] = red[0][0][tid] + red[0][1][tid];
+        pv[o] = red[1][0][tid] + red[1][1][tid];
+    }
+}
+
+__global__ void vt_finalize_kernel(const double* __restrict__ pv, const double* __restrict__ pm, const double* __restrict__ prior,
+                                   int nt, int mpad, int m, double* __restrict__ mean, double* __restrict__ var) {
+    const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double sm = 0.0, sv = 0.0;
+    for (int j = 0; j < nt; ++j) {
+        sm += pm[((long long)b * nt + j) * mpad + r];
+        sv += pv[((long long)b * nt + j) * mpad + r];
+    }
+    mean[(long long)b * m + r] = sm;
+    var[(long long)b * m + r] = prior[b] - sv;
+}
+
+static inline long long predict_gemm_layout(int B, int npad, int dpad, int mpad, long long* o_nrm, long long* o_ks, long long* o_pv,
+                                            long long* o_pm) {
+    long long off = align256((long long)B * mpad * dpad * 8);  // scaled test points
+    *o_nrm = off; off += align256((long long)B * mpad * 8);
+    *o_ks = off;  off += align256((long long)B * mpad * npad * 8);
+    *o_pv = off;  off += align256((long long)B * (npad / TILE) * mpad * 8);
+    *o_pm = off;  off += align256((long long)B * (npad / TILE) * mpad * 8);
+    return off;
+}
+
+extern "C" long long gpr_predict_gemm_scratch_bytes(int B, int npad, int dpad, int m) {
+    const int mpad = (m + TILE - 1) / TILE * TILE;
+    long long a, b, c, d;
+    return predict_gemm_layout(B, npad, dpad, mpad, &a, &b, &c, &d);
+}
+
+extern "C" int gpr_predict_gemm(const double* X, const double* a, const double* nrm, const double* z, const double* hp, int hp_stride,
+                                const double* prior, const double* xs, int B, int n, int npad, int d, int dpad, int m, double* mean,
+                                double* var, double* vt, void* scratch, void* stream) {
+    ARG_CHECK(X && a && nrm && z && hp && prior && xs && mean && var && vt && scratch);
+    ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
+    const int fsm = feat_smem_bytes(dpad);
+    if (fsm > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused SE tile%s (dpad=%lld)", "", dpad);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mpad = (m + TILE - 1) / TILE * TILE, nt = npad / TILE;
+    long long o_nrm, o_ks, o_pv, o_pm;
+    predict_gemm_layout(B, npad, dpad, mpad, &o_nrm, &o_ks, &o_pv, &o_pm);
+    char* base = reinterpret_cast<char*>(scratch);
+    double* as = reinterpret_cast<double*>(base);
+    double* nrms = reinterpret_cast<double*>(base + o_nrm);
+    double* Ks = reinterpret_cast<double*>(base + o_ks);
+    double* pv = reinterpret_cast<double*>(base + o_pv);
+    double* pm = reinterpret_cast<double*>(base + o_pm);
+    // scaled test points (shared xs, per-expert length-scales), K* [B, mpad, npad] (padding rows / columns zero)
+    se_scale_kernel<<<dim3((mpad + 127) / 128, B), 128, 0, st>>>(xs, 0, hp, hp_stride, m, d, mpad, dpad, as, nrms);
+    CUDA_TRY(cudaMemsetAsync(Ks, 0, (size_t)B * mpad * npad * 8, st));
+    CUDA_TRY(opt_in_smem(se_tile_kernel, fsm));
+    se_tile_kernel<<<dim3(nt, mpad / TILE, B), NTHREADS, fsm, st>>>(as, nrms, mpad, a, nrm, npad, hp, hp_stride, nullptr, m, n, dpad, Ks,
+                                                                    npad, (long long)mpad * npad, 1, 0, 0);
+    CUDA_TRY(opt_in_smem(vt_gemm_kernel, MAIN_SMEM_BYTES));
+    vt_gemm_kernel<<<dim3(nt, mpad / TILE, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(Ks, X, z, npad, mpad, vt, pv, pm);
+    vt_finalize_kernel<<<dim3((m + 127) / 128, B), 128, 0, st>>>(pv, pm, prior, nt, mpad, m, mean, var);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // N1: explicit inverse from the Cholesky factor (tc.cholesky_solve(identity) / cholesky_inverse, gr_bcm.py:101-112)
 //   gpr_potri_batched = transpose_invdiag + trtri_kernel (U = L^-T into the block-upper part of L) + lauum_store_kernel
 //   (K^-1 = U U^T, both triangles written).  grbcm_full_combine: prec = sum_c Kinv_c o (beta_c[i] + beta_c[j]) / 2.

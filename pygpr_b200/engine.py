@@ -127,6 +127,7 @@ class FitState:
     info: torch.Tensor        # [B] int32
     prior: torch.Tensor       # [B] sig^2 + sig_n^2
     shared_from: Optional["FitState"] = None   # communication expert whose factor is the leading block of every expert here
+    Linv: Optional[torch.Tensor] = None        # [B, npad, npad] L^-1 (tril_inverse), cached for the GEMM-form prediction
 
     def nlml(self) -> torch.Tensor:
         """NLML = 1/2 y^T alpha + sum log L_ii + n/2 log 2 pi   (loss.py:49-51); y^T alpha = z.z"""
@@ -303,6 +304,17 @@ def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     return (mg, vg), (ml, vl)
 
 
+def tril_inverse(st: FitState) -> torch.Tensor:
+    """L^-1 of a fitted state (cached).  Overwrites the strict block-upper part of st.L with L^-T, like lml_grad."""
+    if st.Linv is None:
+        X = torch.empty(st.B, st.npad, st.npad, dtype=F64, device=st.L.device)
+        scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(st.B, st.npad)), dtype=torch.uint8, device=st.L.device)
+        _lib.call("gpr_tril_inverse", _p(st.L), _p(st.invdiag), st.B, st.npad, _p(X), _p(scratch), _stream())
+        _count(3)
+        st.Linv = X
+    return st.Linv
+
+
 def predict_shared(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     """The two predictions of GRBCM.predict when the local experts were fitted on top of the communication expert's factor
     (fit(shared=st_g)): the communication expert's V_g^T = K*_g L_g^-T is kept and every local expert continues the
@@ -315,10 +327,16 @@ def predict_shared(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     mg = torch.empty(1, m, dtype=F64, device=dev)
     vg = torch.empty(1, m, dtype=F64, device=dev)
     vt = _work("predict_vt", mt * TILE * st_g.npad * 8, dev)
-    scratch_g = _work("predict_side", int(lib.gpr_predict_scratch_bytes(st_g.npad)), dev)
-    _lib.call("gpr_predict_keep", _p(st_g.L), _p(st_g.invdiag), _p(st_g.a), _p(st_g.nrm), _p(st_g.alpha), _p(st_g.hp),
-              st_g.hp.shape[-1], _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt),
-              _p(scratch_g), _stream())
+    if st_g.Linv is not None:   # GEMM form: (m/128) x (ng/128) independent tiles instead of m/128 serial substitutions
+        scratch_g = _work("predict_gemm", int(lib.gpr_predict_gemm_scratch_bytes(1, st_g.npad, st_g.dpad, m)), dev)
+        _lib.call("gpr_predict_gemm", _p(st_g.Linv), _p(st_g.a), _p(st_g.nrm), _p(st_g.z), _p(st_g.hp), st_g.hp.shape[-1],
+                  _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt), _p(scratch_g), _stream())
+        _count(3)
+    else:
+        scratch_g = _work("predict_side", int(lib.gpr_predict_scratch_bytes(st_g.npad)), dev)
+        _lib.call("gpr_predict_keep", _p(st_g.L), _p(st_g.invdiag), _p(st_g.a), _p(st_g.nrm), _p(st_g.alpha), _p(st_g.hp),
+                  st_g.hp.shape[-1], _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt),
+                  _p(scratch_g), _stream())
     ml = torch.empty(st_l.B, m, dtype=F64, device=dev)
     vl = torch.empty(st_l.B, m, dtype=F64, device=dev)
     scratch = _work("predict", int(lib.gpr_predict_scratch_bytes(st_l.npad)), dev)

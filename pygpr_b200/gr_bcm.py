@@ -92,6 +92,8 @@ class GRBCM(GPR):
             if l.need_upd:
                 l._launch_update(shared=g._state)
                 l._finish_update()
+                if l._state.shared_from is g._state:
+                    engine.tril_inverse(g._state)            # once per fit: the communication expert predicts in GEMM form
             return None
         if l._state is not None and l._state.shared_from is not None and not l.need_upd and g.need_upd:
             l.need_upd = True                                 # the local factors were built on a communication factor that is stale
