@@ -1167,6 +1167,19 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             nT[tid] = s;
         }
         double macc[4] = {0, 0, 0, 0}, vacc[4] = {0, 0, 0, 0};
+        if (SHARED) {
+            // the communication expert's V_g^T tile becomes columns 0 .. gt*128 of this CTA's slab (a 128 x ng copy, ~0.1 % of
+            // the task) so that every step is ONE contiguous product like the unshared kernel; reading it through a second
+            // segment cost ~3 % (two sets of addresses in the copy-issue path of the mainloop)
+            const double* src = sh.Vg + (long long)ct * TILE * sh.npad_g;
+            const int w2 = sh.gt * (TILE / 2);  // 16-byte words per row
+            for (int id = tid; id < TILE * w2; id += NTHREADS) {
+                const int r = id / w2, c2 = id % w2;
+                *reinterpret_cast<double2*>(Vt + (long long)r * npad + 2 * c2) =
+                    __ldcg(reinterpret_cast<const double2*>(src + (long long)r * sh.npad_g + 2 * c2));
+            }
+            __threadfence_block();
+        }
 
         for (int i = SHARED ? sh.gt : 0; i < nt; ++i) {
             double acc[4][8][2];
@@ -1183,12 +1196,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
                     sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
                 }
             }
-            if (SHARED) {
-                const double* Li = Lb + ((long long)i * TILE) * npad;
-                Seg s0{sh.Vg + (long long)ct * TILE * sh.npad_g, sh.npad_g, Li, npad, sh.gt * (TILE / KC)};
-                Seg s1{Vt + (long long)sh.gt * TILE, npad, Li + (long long)sh.gt * TILE, npad, (i - sh.gt) * (TILE / KC)};
-                mainloop<false, XPF_PREDICT>(acc, s0, s1, smem, nh, pipe);
-            } else if (want_var && i > 0) {
+            if (SHARED || (want_var && i > 0)) {
                 Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
                 mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
             }
