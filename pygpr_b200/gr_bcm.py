@@ -1,6 +1,8 @@
 """Generalized Robust Bayesian Committee Machine with the reference's API (PyGPR/gr_bcm.py)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import dist as gdist
@@ -118,7 +120,6 @@ class GRBCM(GPR):
         """True when every local expert's hyper-parameter row equals the communication expert's vector (the GRBCM paper's
         setting, and what GRBCM_MLE trains) and the communication set is tile aligned — the conditions of the shared
         leading block (engine.fit(shared=...))."""
-        import os
         g, l = self.gpg, self.gpl
         if os.environ.get("PYGPR_GRBCM_SHARE", "1") == "0":   # A/B knob: treat the experts as unrelated matrices
             return False
@@ -254,9 +255,15 @@ class GRBCM_MLE:
         P = theta.shape[-1]
         acc = np.zeros(1 + P)
         step = self.chunk if self.chunk > 0 else max(g.nc, 1)
+        # the communication expert at theta: its NLML/gradient is added once below, and (one shared vector, tile-aligned
+        # communication set) its factor is the leading block of every local expert's factor (engine.fit(shared=...))
+        glob = MLE(g.gpg)
+        st_g = glob._fit(theta, want_alpha=True)
+        share = st_g if (g.ng % engine.TILE == 0 and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
         for s in range(0, g.nc, step):
             e = min(s + step, g.nc)
             part = MLE(Exact_GP(g.gpl.x[s:e], g.gpl.y[s:e], g.gpl.cov))
+            part.shared_state = share
             th = np.tile(theta, (e - s, 1))
             if want_grad:
                 l, j = part.loss_and_grad(th)
@@ -269,11 +276,11 @@ class GRBCM_MLE:
             t = engine._dev(t)
             gdist.all_reduce_sum_(t, g.group)         # [1+P] doubles
             acc = t.cpu().numpy()
-        glob = MLE(g.gpg)
+        l = float(st_g.nlml()[0])
         if want_grad:
-            l, j = glob.loss_and_grad(theta)
+            j = engine.lml_grad(st_g)[0].cpu().numpy()      # last: it overwrites the block-upper part of the shared factor
             return float(acc[0] + l), acc[1:] + j
-        return float(acc[0] + glob.loss(theta)), None
+        return float(acc[0] + l), None
 
     def loss(self, params):
         self.loss_value, _ = self._eval(params, False)

@@ -56,7 +56,10 @@ class MLE(Loss):
             x = x.expand(B, -1, -1).contiguous()
             y = y.expand(B, -1).contiguous()
         assert hp.shape[-1] == self.model.cov.get_params_shape(xs)[-1]
-        st = engine.fit(x, y, hp, spec[0], want_alpha=want_alpha)
+        shared = getattr(self, "shared_state", None)        # set by GRBCM_MLE: the communication expert fitted at these params
+        if shared is not None and not engine.can_share(shared, x.shape[1], x.shape[2], spec[0]):
+            shared = None
+        st = engine.fit(x, y, hp, spec[0], want_alpha=want_alpha, shared=shared)
         st.check()                                           # tc.cholesky raises on a non-PD matrix, loss.py:39
         return st
 

@@ -48,12 +48,27 @@ def main():
         model = P.GRBCM(x[1:], y[1:], x[0], y[0], cov)
         model.gpl.set_params(hp_well(M - 1, d)); model.gpg.set_params(hp_well(1, d)[0])
         def fit():
-            model.gpl.need_upd = True; model.gpg.need_upd = True; model.gpg.update(); model.gpl.update()
+            model.gpl.need_upd = True; model.gpg.need_upd = True; model.update()
         tf, _ = timed(fit, 2)
         tp, _ = timed(lambda: model.predict(xs, var="diag"), 2)
         flops = (M - 1) * (2 * m0) ** 3 / 3 + m0 ** 3 / 3
         print(json.dumps({"config": "3: GRBCM 64x2048 d=8 (63 experts of order 4096 + comm), m=4096", "fit_ms": tf * 1e3,
-                          "fit_tflops": flops / tf * 1e-12, "predict_ms": tp * 1e3, "pred_per_s": m / tp}), flush=True)
+                          "fit_tflops_unshared_count": flops / tf * 1e-12, "predict_ms": tp * 1e3, "pred_per_s": m / tp,
+                          "shared_leading_block": model.gpl._state.shared_from is not None}), flush=True)
+    if "5" in which:  # one GPU's slice of config 5: GRBCM training, experts of order 16384 (8192 comm + 8192 local), d=32
+        nc, m0, d = 16, 8192, 32
+        x = torch.rand(nc + 1, m0, d); y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(nc + 1, m0)
+        model = P.GRBCM(x[1:], y[1:], x[0], y[0], cov)
+        theta = hp_well(1, d)[0]
+        loss = P.GRBCM_MLE(model, chunk=0)
+        th = theta.numpy().astype(np.float64)
+        tl, l = timed(lambda: loss.loss(th), 1)
+        tg, lg = timed(lambda: loss.loss_and_grad(th), 1)
+        flops = nc * float(2 * m0) ** 3 + float(m0) ** 3
+        print(json.dumps({"config": "5 (slice): GRBCM_MLE summed NLML + gradient, %d experts of order 16384 + comm expert, d=32 "
+                                    "(one of 8 GPUs holds 64 of the 511)" % nc, "loss_ms": tl * 1e3, "loss_and_grad_ms": tg * 1e3,
+                          "loss_and_grad_tflops_unshared_count": flops / tg * 1e-12, "nlml": float(l),
+                          "grad_norm": float(np.linalg.norm(lg[1]))}), flush=True)
 
 if __name__ == "__main__":
     main()
