@@ -198,6 +198,15 @@ int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double
                  double* grad, void* scratch, void* stream);
 
 /*
+ * gpr_lml_grad for experts factorised by gpr_potrf_batched_shared, when the leading block copied into L also carries the
+ * communication expert's L_g^-T in its strict block-upper part (run gpr_potri_batched on the communication factor BEFORE
+ * copying it).  Kinv_g [ng, ldg] is that call's K_g^-1.  The shared blocks of L^-T and of K^-1 = U U^T are not recomputed.
+ */
+int gpr_lml_grad_shared(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                        const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                        double* grad, void* scratch, void* stream, int ng, const double* Kinv_g, int ldg);
+
+/*
  * GRBCM aggregation (diag), gr_bcm.py:116-149 (C15), split for expert sharding:
  *   partial : S[0,c] = sum_i beta_i, S[1,c] = sum_i beta_i/var_i, S[2,c] = sum_i beta_i mean_i/var_i
  *             over the nc_local experts held here; beta_i = 1 for global expert index 0

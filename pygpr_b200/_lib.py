@@ -28,6 +28,7 @@ SIGNATURES = {
     "gpr_predict_keep": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpr_predict_shared": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "gpr_lml_grad_scratch_bytes": (c_longlong, [_I, _I, _I]),
+    "gpr_lml_grad_shared": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I]),
     "gpr_se_scale": (c_int, [_P, _LL, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "gpr_se_build": (c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "gpr_se_cross": (c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),

@@ -1499,7 +1499,7 @@ __global__ void transpose_invdiag_kernel(const double* __restrict__ invdiag, dou
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ invdiagT, int B, int npad,
-             int* __restrict__ counter) {
+             int* __restrict__ counter, int gt) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -1519,7 +1519,8 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
         double* Lb = L + (long long)b * npad * npad;
         const double* Ujj = invdiagT + ((long long)b * nt + j) * TILE * TILE;
         double* Urow = Lb + ((long long)j * TILE) * npad;      // row tile j of U lives in the block-upper part
-        for (int i = j + 1; i < nt; ++i) {
+        // gt > 0 (shared leading block): U[j, i] for i < gt is the communication expert's L_g^-T, already in place
+        for (int i = (j + 1 > gt ? j + 1 : gt); i < nt; ++i) {
             double acc[4][8][2];
             zero_acc(acc);
             __syncthreads();
@@ -1616,7 +1617,8 @@ static long long trtri_work_bytes(int B, int npad, int sms) {
     const int nt = npad / TILE;
     return 256 + align256((long long)B * nt * 4) + (long long)B * trtri_slot_tiles(nt, sms) * TILE * TILE * 8;
 }
-static int launch_trtri(double* L, const double* invdiag, const double* invdiagT, int B, int npad, void* work, cudaStream_t st) {
+static int launch_trtri(double* L, const double* invdiag, const double* invdiagT, int B, int npad, void* work, cudaStream_t st,
+                        int gt = 0) {
     const int nt = npad / TILE;
     if (nt <= 1) return GPR_OK;
     int sms = gpr_device_sm_count();
@@ -1626,7 +1628,7 @@ static int launch_trtri(double* L, const double* invdiag, const double* invdiagT
     if (ntasks >= 2LL * sms) {
         CUDA_TRY(cudaMemsetAsync(task_counter, 0, 256, st));
         CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
-        trtri_kernel<<<sms, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, task_counter);
+        trtri_kernel<<<sms, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, task_counter, gt);
         CUDA_TRY(cudaGetLastError());
         return GPR_OK;
     }
@@ -1635,7 +1637,7 @@ static int launch_trtri(double* L, const double* invdiag, const double* invdiagT
     const int spe = (int)trtri_slot_tiles(nt, sms);
     CUDA_TRY(cudaMemsetAsync(counters, 0, (size_t)B * nt * 4, st));
     CUDA_TRY(opt_in_smem(trtri_col_kernel, MAIN_SMEM_BYTES));
-    for (int i = 1; i < nt; ++i) {
+    for (int i = (gt > 1 ? gt : 1); i < nt; ++i) {                       // block columns < gt of U are shared and in place
         const long long blocks = (long long)i * (i + 1) / 2;               // k-blocks of this column, per expert
         long long target = (blocks * B + 2LL * sms - 1) / (2LL * sms);      // ~2 CTAs per SM over all experts
         if (target < 1) target = 1;
@@ -1650,7 +1652,8 @@ static int launch_trtri(double* L, const double* invdiag, const double* invdiagT
 __global__ void __launch_bounds__(NTHREADS, 1)
 lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdiagT, const double* __restrict__ a,
                   const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
-                  int n, int npad, int d, int dpad, double* __restrict__ partials, int P) {
+                  int n, int npad, int d, int dpad, double* __restrict__ partials, int P, int gt, const double* __restrict__ Kinv_g,
+                  int ldg) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -1671,9 +1674,23 @@ lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdi
     double acc[4][8][2];
     zero_acc(acc);
     NoHook nh;
-    Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, TILE / KC};
-    Seg s1{Ui + (long long)(i + 1) * TILE, npad, Uj + (long long)(i + 1) * TILE, npad, (nt - 1 - i) * (TILE / KC)};
+    // Shared leading block (gt > 0): for a tile inside it the k-blocks < gt give the communication expert's K_g^-1 tile, which is
+    // the same for every expert — it is added from Kinv_g in the epilogue and only the k-blocks >= gt are multiplied here.
+    const bool in_shared = i < gt;
+    Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, in_shared ? 0 : TILE / KC};
+    const int k0 = in_shared ? gt : i + 1;
+    Seg s1{Ui + (long long)k0 * TILE, npad, Uj + (long long)k0 * TILE, npad, (nt - k0) * (TILE / KC)};
     mainloop<false, XPF_LAUUM>(acc, s0, s1, smem, nh, pipe);
+    if (in_shared) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                const double2 v = *reinterpret_cast<const double2*>(Kinv_g + ((long long)i * TILE + acc_row(mi)) * ldg + j * TILE + acc_col(ni, 0));
+                acc[mi][ni][0] += v.x;
+                acc[mi][ni][1] += v.y;
+            }
+    }
 
     // epilogue: M = (K^-1 - alpha_i alpha_j^T) o K_se  -> smem tile
     double* Ms = smem;
@@ -1769,9 +1786,9 @@ extern "C" long long gpr_lml_grad_scratch_bytes(int B, int npad, int d) {
     return trtri_work_bytes(B, npad, sms) + (long long)B * nt * TILE * TILE * 8 + align256((long long)B * ntiles * (d + 2) * 8);
 }
 
-extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
-                            const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
-                            double* grad, void* scratch, void* stream) {
+static int lml_grad_impl(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                         const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                         double* grad, void* scratch, void* stream, int gt, const double* Kinv_g, int ldg) {
     ARG_CHECK(L && invdiag && a && nrm && alpha && hp && grad && scratch);
     ARG_CHECK(B > 0 && n > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
     const long long smem_l = lml_feat_bytes(dpad);
@@ -1787,16 +1804,33 @@ extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, c
     double* partials = invdiagT + (long long)B * nt * TILE * TILE;
     transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
     {
-        const int rc = launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st);
+        const int rc = launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st, gt);
         if (rc != GPR_OK) return rc;
     }
     const int smem = (int)(smem_l > MAIN_SMEM_BYTES ? smem_l : MAIN_SMEM_BYTES);
     CUDA_TRY(opt_in_smem(lauum_grad_kernel, smem));
     lauum_grad_kernel<<<dim3(ntiles, B), NTHREADS, smem, st>>>(L, invdiagT, a, nrm, alpha, hp, hp_stride, n, npad, d, dpad,
-                                                               partials, P);
+                                                               partials, P, gt, Kinv_g, ldg);
     grad_finalize_kernel<<<B, ((P + 31) / 32) * 32, 0, st>>>(partials, ntiles, P, hp, hp_stride, d, grad);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
+}
+
+extern "C" int gpr_lml_grad(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                            const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                            double* grad, void* scratch, void* stream) {
+    return lml_grad_impl(L, invdiag, a, nrm, alpha, hp, hp_stride, has_noise, B, n, npad, d, dpad, grad, scratch, stream, 0, nullptr, 0);
+}
+
+// Gradient for experts factorised by gpr_potrf_batched_shared WHEN the leading block copied into L also carries the
+// communication expert's L_g^-T in its strict block-upper part (gpr_potri_batched / gpr_tril_inverse was run on the
+// communication factor before the copy).  Kinv_g [ng, ldg] = K_g^-1 from gpr_potri_batched.  1/8 fewer flops at ng = n/2.
+extern "C" int gpr_lml_grad_shared(double* L, const double* invdiag, const double* a, const double* nrm, const double* alpha,
+                                   const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                                   double* grad, void* scratch, void* stream, int ng, const double* Kinv_g, int ldg) {
+    ARG_CHECK(Kinv_g && ng > 0 && ng % TILE == 0 && ng < n && ldg >= ng && ldg % 2 == 0);
+    return lml_grad_impl(L, invdiag, a, nrm, alpha, hp, hp_stride, has_noise, B, n, npad, d, dpad, grad, scratch, stream, ng / TILE,
+                         Kinv_g, ldg);
 }
 
 // ---------------------------------------------------------------------------------------------

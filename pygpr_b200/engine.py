@@ -128,6 +128,8 @@ class FitState:
     prior: torch.Tensor       # [B] sig^2 + sig_n^2
     shared_from: Optional["FitState"] = None   # communication expert whose factor is the leading block of every expert here
     Linv: Optional[torch.Tensor] = None        # [B, npad, npad] L^-1 (tril_inverse), cached for the GEMM-form prediction
+    Kinv: Optional[torch.Tensor] = None        # [B, n, n] K^-1 (kinv), cached for the shared-block gradient
+    shared_upper: bool = False                 # the copied leading block also carries the communication expert's L_g^-T
 
     def nlml(self) -> torch.Tensor:
         """NLML = 1/2 y^T alpha + sum log L_ii + n/2 log 2 pi   (loss.py:49-51); y^T alpha = z.z"""
@@ -203,7 +205,9 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
         _lib.call("gpr_potrf_batched_shared", _p(L), _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
                   _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream(), ng,
                   _p(shared.L), shared.npad, _p(shared.invdiag))
-        # the leading block itself, for the kernels that walk the whole factor (backward solve, gradient, full covariance)
+        # the leading block itself, for the kernels that walk the whole factor (backward solve, gradient, full covariance);
+        # if L_g^-T was already formed in the communication factor's block-upper part (kinv / tril_inverse) it comes along
+        shared_upper = shared.Kinv is not None or shared.Linv is not None
         L[:, :ng, :ng] = shared.L[0, :ng, :ng]
         invdiag[:, :gt] = shared.invdiag[0, :gt]
         _count(1)
@@ -217,7 +221,9 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
         twork = _work("trsv" + ws_tag, int(_lib.load().gpr_trsv_work_bytes(B)), dev)
         _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _p(twork), _stream())
         _count(1)
-    return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior, shared)
+    st = FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior, shared)
+    st.shared_upper = shared is not None and shared_upper
+    return st
 
 
 def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
@@ -347,6 +353,17 @@ def predict_shared(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     return (mg, vg), (ml, vl)
 
 
+def kinv(st: FitState) -> torch.Tensor:
+    """K^-1 [B, n, n] of a fitted state (cached): tc.cholesky_inverse.  Leaves L^-T in the strict block-upper part of st.L."""
+    if st.Kinv is None:
+        out = torch.empty(st.B, st.n, st.n, dtype=F64, device=st.L.device)
+        scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(st.B, st.npad)), dtype=torch.uint8, device=st.L.device)
+        _lib.call("gpr_potri_batched", _p(st.L), _p(st.invdiag), st.B, st.n, st.npad, _p(out), st.n, _p(scratch), _stream())
+        _count(3)
+        st.Kinv = out
+    return st.Kinv
+
+
 def lml_grad(st: FitState) -> torch.Tensor:
     """d NLML / d hp [B, P] from a finished fit (destroys the strict block-upper part of st.L)   loss.py:59-128."""
     assert st.alpha is not None
@@ -354,6 +371,13 @@ def lml_grad(st: FitState) -> torch.Tensor:
     grad = torch.empty(st.B, P, dtype=F64, device=st.L.device)
     nbytes = int(_lib.load().gpr_lml_grad_scratch_bytes(st.B, st.npad, st.d))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=st.L.device)
+    sg = st.shared_from
+    if sg is not None and st.shared_upper and sg.Kinv is not None:
+        # shared leading block: neither L_g^-T nor K_g^-1 is recomputed per expert (gpr_lml_grad_shared)
+        _lib.call("gpr_lml_grad_shared", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
+                  int(st.has_noise), st.B, st.n, st.npad, st.d, st.dpad, _p(grad), _p(scratch), _stream(), sg.n, _p(sg.Kinv), sg.n)
+        _count(4)
+        return grad
     _lib.call("gpr_lml_grad", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
               int(st.has_noise), st.B, st.n, st.npad, st.d, st.dpad, _p(grad), _p(scratch), _stream())
     _count(4 if st.npad > TILE else 3)

@@ -260,6 +260,8 @@ class GRBCM_MLE:
         glob = MLE(g.gpg)
         st_g = glob._fit(theta, want_alpha=True)
         share = st_g if (g.ng % engine.TILE == 0 and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
+        if share is not None and want_grad:
+            engine.kinv(st_g)      # K_g^-1 and L_g^-T once: the experts' gradients reuse both (gpr_lml_grad_shared)
         for s in range(0, g.nc, step):
             e = min(s + step, g.nc)
             part = MLE(Exact_GP(g.gpl.x[s:e], g.gpl.y[s:e], g.gpl.cov))

@@ -172,3 +172,31 @@ def test_backward_solve_forms(eng, orc, monkeypatch, B, n, d):
     assert_close(a1[:, :n].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha (one CTA per expert)")
     assert_close(a2[:, :n].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha (column owners)")
     assert_close(a2.cpu().numpy(), a1.cpu().numpy(), 1e-12, "forms agree")
+
+
+@pytest.mark.parametrize("nc,nls,ng,d", [(7, 200, 256, 5), (40, 768, 384, 3)])   # column-mode / task-mode L^-T
+def test_shared_block_fit_and_gradient(eng, orc, nc, nls, ng, d):
+    """Experts that start with the same ng rows under one hyper-parameter vector: factor, NLML and gradient built on top of the
+    communication expert's factor / L_g^-T / K_g^-1 equal the stand-alone ones and the reference's (loss.py:92-128)."""
+    g = torch.Generator().manual_seed(31)
+    xg = torch.rand(ng, d, generator=g, dtype=torch.float64)
+    yg = torch.sin(xg.sum(-1)) + 0.1 * torch.randn(ng, generator=g, dtype=torch.float64)
+    xl = torch.rand(nc, nls, d, generator=g, dtype=torch.float64)
+    yl = torch.sin(xl.sum(-1)) + 0.1 * torch.randn(nc, nls, generator=g, dtype=torch.float64)
+    x, y = orc.grbcm_inputs(xl, yl, xg, yg)
+    hp = torch.empty(nc, d + 2, dtype=torch.float64)
+    hp[:, 0] = 1.1; hp[:, 1:d + 1] = 2.0 / math.sqrt(d); hp[:, d + 1] = 0.3
+    st_g = eng.fit(xg[None].cuda(), yg[None].cuda(), hp[:1].cuda(), True)
+    eng.kinv(st_g)
+    st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True, shared=st_g)
+    assert st.shared_from is st_g and st.shared_upper and int(st.info.abs().sum()) == 0
+    st0 = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True)
+    n = x.shape[1]
+    assert_close(torch.tril(st.L[:, :n, :n]).cpu().numpy(), torch.tril(st0.L[:, :n, :n]).cpu().numpy(), 1e-11, "L")
+    assert_close(st.nlml().cpu().numpy(), st0.nlml().cpu().numpy(), 1e-12, "nlml")
+    g1, g0 = eng.lml_grad(st).cpu(), eng.lml_grad(st0).cpu()
+    assert_close(g1.numpy(), g0.numpy(), 1e-10, "gradient (shared block) == gradient (stand-alone)")
+    if n <= 600:
+        loss_o, grad_o = orc.mle_loss_and_grad(SPEC, hp, x, y)
+        assert_close(st.nlml().cpu().numpy(), loss_o.numpy(), TOL, "nlml vs reference")
+        assert_close(g1.numpy(), grad_o.numpy(), TOL, "gradient vs reference")
