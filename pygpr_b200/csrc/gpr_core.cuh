@@ -266,6 +266,37 @@ __device__ __forceinline__ void load_feat_tile(double* s, int sld, const double*
     }
 }
 
+// exp(-d) for the squared-exponential epilogue, d >= 0 up to rounding (covar.py:147-149: mul_(-1).exp_()).
+// libdevice's exp() costs ~65 SASS instructions per value with its range handling; 64 values per thread per 128x128 tile
+// made the K / K* tile generation ~5 % of the prediction kernel.  Here: n = round(-d log2 e) by the 1.5*2^52 shifter,
+// r = -d - n ln2 (two-piece ln2), degree-12 Taylor on |r| <= ln2/2 (truncation 1.7e-16), 2^n added into the exponent
+// field.  Relative error < 4e-16 over the whole range (tests/test_gpu_engine.py::test_se_kernels holds K to 1e-13
+// against the CPU oracle); arguments above 690 (results below 2^-995) are flushed to 0.
+__device__ __forceinline__ double exp_neg(double d) {
+    const double t = d * -1.4426950408889634074;
+    const double shifter = 6755399441055744.0;
+    const double tn = t + shifter;
+    const int n = __double2loint(tn);
+    const double nf = tn - shifter;
+    double r = fma(nf, -6.93147180369123816490e-01, -d);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;           // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);       // 1/11!
+    p = fma(p, r, 2.75573192239858906526e-07);       // 1/10!
+    p = fma(p, r, 2.75573192239858906526e-06);       // 1/9!
+    p = fma(p, r, 2.48015873015873015873e-05);       // 1/8!
+    p = fma(p, r, 1.98412698412698412698e-04);       // 1/7!
+    p = fma(p, r, 1.38888888888888888889e-03);       // 1/6!
+    p = fma(p, r, 8.33333333333333333333e-03);       // 1/5!
+    p = fma(p, r, 4.16666666666666666667e-02);       // 1/4!
+    p = fma(p, r, 1.66666666666666666667e-01);       // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return d > 690.0 ? 0.0 : v;   // 2^-995: far below anything a kernel matrix entry can contribute; also guards the int range of n
+}
+
 // Squared-exponential tile in GEMM form, covar.py:102-149:  sqd = (|aR|^2 + |aC|^2) - 2 aR.aC ;  k = sig2 exp(-sqd)
 // The cross term runs on DMMA.  f(mi, ni, e, kval) is called for every accumulator element of the thread.
 // RAW: hand the squared distance itself to f (no exponential).
@@ -295,8 +326,46 @@ __device__ __forceinline__ void gen_se_tile(const double* sR, const double* sC, 
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             const double d0 = -2.0 * G[mi][0] + (nr[mi] + nc0), d1 = -2.0 * G[mi][1] + (nr[mi] + nc1);
-            f(mi, ni, 0, RAW ? d0 : sig2 * exp(-d0));
-            f(mi, ni, 1, RAW ? d1 : sig2 * exp(-d1));
+            f(mi, ni, 0, RAW ? d0 : sig2 * exp_neg(d0));
+            f(mi, ni, 1, RAW ? d1 : sig2 * exp_neg(d1));
+        }
+    }
+}
+
+// The same tile, produced INTO the accumulators (which must be zero): the cross term runs like one mainloop chunk — 12 LDS.64 +
+// 32 independent DMMA per k4 step instead of gen_se_tile's per-column-block chains of 4 dependent DMMAs behind their loads — and
+// every element is then replaced by f(mi, ni, e, k).  Used to seed a product  acc = -K* + sum V L^T  (predict_kernel).
+template <typename F>
+__device__ __forceinline__ void se_seed_acc(double (&acc)[4][8][2], const double* sR, const double* sC, int sld, const double* nR,
+                                            const double* nC, int dpad, double sig2, F&& f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const double* pa = sR + (wm * 32 + g) * sld + t;
+    const double* pb = sC + (wn * 64 + g) * sld + t;
+    for (int k = 0; k < dpad; k += 4) {
+        double fa[4], fb[8];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) fa[mi] = pa[mi * 8 * sld + k];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) fb[ni] = pb[ni * 8 * sld + k];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[mi], fb[ni]);
+    }
+    double nr[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) nr[mi] = nR[wm * 32 + mi * 8 + g];
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        const int c0 = wn * 64 + ni * 8 + 2 * t;
+        const double nc0 = nC[c0], nc1 = nC[c0 + 1];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const double d0 = -2.0 * acc[mi][ni][0] + (nr[mi] + nc0), d1 = -2.0 * acc[mi][ni][1] + (nr[mi] + nc1);
+            acc[mi][ni][0] = f(mi, ni, 0, sig2 * exp_neg(d0));
+            acc[mi][ni][1] = f(mi, ni, 1, sig2 * exp_neg(d1));
         }
     }
 }

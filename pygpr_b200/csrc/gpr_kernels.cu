@@ -1137,7 +1137,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
     double* sAl = nT + TILE;                  // [128] alpha block of the current step
     // feat_own: the training-block features of step i get their own region and are fetched BEFORE the step's long product
     // (they land while it runs); otherwise they are staged in the drained pipeline buffers after it (large d)
-    double* sCown = sAl + TILE;               // [128 x sld] + [128] norms
+    double* sCown = sAl + TILE;               // [128 x sld] + [128] norms + [128] second alpha buffer (feat_own only)
     double* Vt = scratch + (long long)blockIdx.x * TILE * npad;   // replaced per task when V^T is kept (vt_out)
     NoHook nh;
     Seg none{nullptr, 0, nullptr, 0, 0};
@@ -1181,49 +1181,82 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
             __threadfence_block();
         }
 
-        for (int i = SHARED ? sh.gt : 0; i < nt; ++i) {
+        const int i0 = SHARED ? sh.gt : 0;
+        // feat_own: features / norms / alpha block of step i are fetched during step i-1 into their own region
+        // (alpha double buffered: the shared form still reads block i after the next fetch has been issued)
+        double* sAl2 = sCown + TILE * sld + TILE;
+        auto fetch_feat = [&](int i) {
+            load_feat_tile(sCown, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+            cp_async_commit();
+            if (tid < TILE) {
+                sCown[TILE * sld + tid] = nrm[(long long)b * npad + i * TILE + tid];
+                ((i & 1) ? sAl2 : sAl)[tid] = alpha[(long long)b * npad + i * TILE + tid];
+            }
+        };
+        if (feat_own) {
+            __syncthreads();   // the previous task's last step is done with the region
+            fetch_feat(i0);
+        }
+
+        for (int i = i0; i < nt; ++i) {
             double acc[4][8][2];
             zero_acc(acc);
-            __syncthreads();  // V^T columns written by the previous step are visible; staged features are free
-            // K*(test tile, train block i) from smem-staged features
-            double* sC = feat_own ? sCown : smem;
-            double* nC = sC + TILE * sld;
-            if (feat_own) {
-                load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
-                cp_async_commit();
-                if (tid < TILE) {
-                    nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
-                    sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
-                }
-            }
-            if (SHARED || (want_var && i > 0)) {
-                Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
-                mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
-            }
-            if (!feat_own) {
-                load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
-                cp_async_commit();
-                if (tid < TILE) {
-                    nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
-                    sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
-                }
-            }
-            cp_async_wait<0>();
-            __syncthreads();
             double* Vi = Vt + i * TILE;
-            gen_se_tile(sT, sC, sld, nT, nC, dpad, sig2, [&](int mi, int ni, int e, double kv) {
-                const int c = acc_col(ni, e);
-                if (i * TILE + c >= n) kv = 0.0;  // padding columns carry no covariance
-                if (!SHARED) macc[mi] += kv * sAl[c];
-                acc[mi][ni][e] = kv - acc[mi][ni][e];
-            });
-            if (!want_var) continue;
+            const double* sAli = (feat_own && (i & 1)) ? sAl2 : sAl;
+            if (feat_own) {
+                // K* tile FIRST, straight into the accumulators as -K*, then  acc += V^T[:, 0:i] L[i, 0:i]^T  on top: X = -acc
+                cp_async_wait<0>();
+                __syncthreads();  // features of step i landed; V^T columns written by the previous step are visible
+                se_seed_acc(acc, sT, sCown, sld, nT, sCown + TILE * sld, dpad, sig2, [&](int mi, int ni, int e, double kv) {
+                    const int c = acc_col(ni, e);
+                    if (i * TILE + c >= n) kv = 0.0;  // padding columns carry no covariance
+                    if (!SHARED) macc[mi] += kv * sAli[c];
+                    return -kv;
+                });
+                __syncthreads();  // every warp is done with the feature region
+                if (i + 1 < nt) fetch_feat(i + 1);
+                if (!want_var) continue;
+                if (SHARED || i > 0) {
+                    Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
+                    mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
+                }
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 8; ++ni)
-                    *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
-                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                    for (int ni = 0; ni < 8; ++ni)
+                        *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                            make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+            } else {
+                __syncthreads();  // V^T columns written by the previous step are visible; staged features are free
+                if (SHARED || (want_var && i > 0)) {
+                    Seg s0{Vt, npad, Lb + ((long long)i * TILE) * npad, npad, i * (TILE / KC)};
+                    mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
+                }
+                // K*(test tile, train block i) from features staged in the drained pipeline buffers
+                double* sC = smem;
+                double* nC = sC + TILE * sld;
+                load_feat_tile(sC, sld, a + ((long long)b * npad + i * TILE) * dpad, dpad);
+                cp_async_commit();
+                if (tid < TILE) {
+                    nC[tid] = nrm[(long long)b * npad + i * TILE + tid];
+                    sAl[tid] = alpha[(long long)b * npad + i * TILE + tid];
+                }
+                cp_async_wait<0>();
+                __syncthreads();
+                gen_se_tile(sT, sC, sld, nT, nC, dpad, sig2, [&](int mi, int ni, int e, double kv) {
+                    const int c = acc_col(ni, e);
+                    if (i * TILE + c >= n) kv = 0.0;  // padding columns carry no covariance
+                    if (!SHARED) macc[mi] += kv * sAl[c];
+                    acc[mi][ni][e] = kv - acc[mi][ni][e];
+                });
+                if (!want_var) continue;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni)
+                        *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
+                            make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
             __threadfence_block();
             __syncthreads();
             zero_acc(acc);
@@ -1234,7 +1267,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni) {
                     vacc[mi] += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
-                    if (SHARED) macc[mi] += acc[mi][ni][0] * sAl[acc_col(ni, 0)] + acc[mi][ni][1] * sAl[acc_col(ni, 1)];  // V^T z
+                    if (SHARED) macc[mi] += acc[mi][ni][0] * sAli[acc_col(ni, 0)] + acc[mi][ni][1] * sAli[acc_col(ni, 1)];  // V^T z
                     *reinterpret_cast<double2*>(Vi + (long long)acc_row(mi) * npad + acc_col(ni, 0)) =
                         make_double2(acc[mi][ni][0], acc[mi][ni][1]);
                 }
@@ -1272,7 +1305,7 @@ predict_kernel(const double* __restrict__ L, const double* __restrict__ invdiag,
 
 static inline long long predict_smem_bytes(int dpad) { return MAIN_SMEM_BYTES + (long long)(TILE * feat_sld(dpad) + 2 * TILE) * 8; }
 // with a private region for the training-block features (+ norms) when it still fits in 227 KB
-static inline long long predict_smem_bytes_own(int dpad) { return predict_smem_bytes(dpad) + (long long)(TILE * feat_sld(dpad) + TILE) * 8; }
+static inline long long predict_smem_bytes_own(int dpad) { return predict_smem_bytes(dpad) + (long long)(TILE * feat_sld(dpad) + 2 * TILE) * 8; }
 
 extern "C" long long gpr_predict_scratch_bytes(int npad) {
     int sms = gpr_device_sm_count();
