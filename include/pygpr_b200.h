@@ -125,6 +125,19 @@ int gpr_potrf_batched_shared(double* L, const double* a, const double* nrm, cons
                              const double* Lg, int npad_g, const double* invdiag_g);
 
 /*
+ * gpr_potrf_batched (communication expert, B = 1) and gpr_potrf_batched_shared (local experts) as ONE launch: the
+ * communication expert's tile tasks lead every shared block column and the local tiles wait on its progress counters, so
+ * its serial chain of ng/128 block columns runs under the local experts' work.  *_g arguments as for gpr_potrf_batched with
+ * B = 1 (hp_g: one row); outputs of both models as in the two separate calls; z[b, 0:ng] is filled by the kernel.
+ */
+int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
+                    int B, int n, int npad, int dpad, double* invdiag, const double* y, double* z, double* logdet_half,
+                    double* zz, int* info, double* Lg, const double* a_g, const double* nrm_g, const double* hp_g,
+                    const double* diag_add_g, int ng, int npad_g, double* invdiag_g, const double* y_g, double* z_g,
+                    double* logdet_half_g, double* zz_g, int* info_g, void* work, void* stream);
+long long gpr_potrf_grbcm_work_bytes(int B, int npad, int npad_g);
+
+/*
  * alpha = L^-T z  (backward half of cholesky_solve, gpr.py:70-72).  HBM-bound: reads L once.
  *   z [B,npad] in, alpha [B,npad] out (may alias z only when work == NULL)
  *   work  >= gpr_trsv_work_bytes(B) or NULL.  With a workspace and fewer experts than SMs the solve runs as a

@@ -35,6 +35,9 @@ SIGNATURES = {
     "gpr_se_kernel_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpr_potrf_work_bytes": (c_longlong, [_I, _I]),
+    "gpr_potrf_grbcm": (c_int, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P,
+                                _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gpr_potrf_grbcm_work_bytes": (c_longlong, [_I, _I, _I]),
     "gpr_potrf_batched_shared": (c_int, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gpr_trsv_work_bytes": (c_longlong, [_I]),

@@ -287,8 +287,10 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
                                             const double* __restrict__ nrm, const double* __restrict__ hp, int hp_stride,
                                             const double* __restrict__ diag_add, int dpad, double* invdiag, const double* y,
                                             double* zb, double* logdet_half, double* zz, int* info, const double* dpart,
-                                            bool first = false, bool use_first = false) {
+                                            bool first = false, bool use_first = false, const double* base_ld = nullptr,
+                                            const double* base_zz = nullptr, const int* base_info = nullptr) {
     // first: this is the expert's first diagonal task (logdet / z.z / info start here).  Default (use_first == false): j == 0.
+    // base_*: values the sums start from (the communication expert's, when it is factorised in the same launch).
     const int tid = threadIdx.x;
     const int nt = npad / TILE;
     const bool start = use_first ? first : (j == 0);
@@ -345,10 +347,10 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
         for (int k = tid; k < TILE; k += 32) s += log(T[k * XLD + k]);
         s = warp_sum(s);
         if (tid == 0) {
-            if (logdet_half) __stcg(logdet_half + b, (start ? 0.0 : __ldcg(logdet_half + b)) + s);
+            if (logdet_half) __stcg(logdet_half + b, (start ? (base_ld ? __ldcg(base_ld) : 0.0) : __ldcg(logdet_half + b)) + s);
             if (info) {
-                if (start && *s_fail > TILE) __stcg(info + b, 0);
-                if (*s_fail <= TILE && (start || __ldcg(info + b) == 0)) __stcg(info + b, j * TILE + *s_fail);
+                const int prev = start ? (base_info ? __ldcg(base_info) : 0) : __ldcg(info + b);
+                if (start || (prev == 0 && *s_fail <= TILE)) __stcg(info + b, prev != 0 ? prev : (*s_fail <= TILE ? j * TILE + *s_fail : 0));
             }
         }
     }
@@ -373,7 +375,7 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
         if (tid < 32 && zz) {
             double s = svec[tid] + svec[tid + 32] + svec[tid + 64] + svec[tid + 96];
             s = warp_sum(s);
-            if (tid == 0) __stcg(zz + b, (start ? 0.0 : __ldcg(zz + b)) + s);
+            if (tid == 0) __stcg(zz + b, (start ? (base_zz ? __ldcg(base_zz) : 0.0) : __ldcg(zz + b)) + s);
         }
     }
 }
@@ -596,6 +598,14 @@ struct PotrfArgs {
     const double* Lg;
     int npad_g;
     const double* invdiag_g;
+    // Communication expert factorised IN THE SAME LAUNCH (gpr_potrf_grbcm): its tasks come first in every shared block column,
+    // local tiles of those columns wait on its progress counters (gprog), its z blocks are broadcast into every expert's z
+    // (zbcast: [zbcast_B, zbcast_stride]) and the experts' logdet / z.z / info start from its totals (base_*).
+    const int* gprog;
+    double* zbcast;
+    int zbcast_B, zbcast_stride;
+    const double *base_ld, *base_zz;
+    const int* base_info;
 };
 
 // The two task bodies are separate NON-inlined functions so that each gets the register allocation of a stand-alone
@@ -633,8 +643,18 @@ __device__ __forceinline__ int df_diag_task(const PotrfArgs& A, int b, int j, un
     }
     hook.reduce_to(svec, nullptr);
     // with a shared leading block the host pre-loads logdet_half / zz with the communication expert's sums: never "start"
+    // start of the expert's sums: block column 0, or — with the communication expert in the same launch — block column gt
+    // continuing from its totals; with a precomputed shared block the host pre-loaded them and there is no start
     diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, A.n, npad, A.a, A.nrm, A.hp, A.hp_stride, A.diag_add, A.dpad, A.invdiag,
-                     A.y, zb, A.logdet_half, A.zz, A.info, nullptr, A.gt == 0 && j == 0, true);
+                     A.y, zb, A.logdet_half, A.zz, A.info, nullptr, (A.gt == 0 && j == 0) || (A.base_ld != nullptr && j == A.gt), true,
+                     A.base_ld, A.base_zz, A.base_info);
+    if (A.zbcast && zb) {  // communication expert: hand z_j to every local expert before publishing the task
+        __syncthreads();
+        if (threadIdx.x < TILE) {
+            const double v = zb[j * TILE + threadIdx.x];
+            for (int e = 0; e < A.zbcast_B; ++e) __stcg(A.zbcast + (long long)e * A.zbcast_stride + j * TILE + threadIdx.x, v);
+        }
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_gpu(prog + j, j + 1);
@@ -660,6 +680,7 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
     if (j > 0) {
         if (!df_wait(prog + i, j, abort_flag, A.info, &s_ok)) return -1;  // L[i, 0:j]
         if (!shared_col && !df_wait(prog + j, j, abort_flag, A.info, &s_ok)) return -1;  // L[j, 0:j]
+        if (shared_col && A.gprog && !df_wait(A.gprog + j, j, abort_flag, A.info, &s_ok)) return -1;  // L_g[j, 0:j], same launch
         const double* Brow = shared_col ? A.Lg + ((long long)j * TILE) * A.npad_g : Lb + ((long long)j * TILE) * npad;
         Seg s0{Lb + ((long long)i * TILE) * npad, npad, Brow, shared_col ? (long long)A.npad_g : (long long)npad, j * (TILE / KC)};
         mainloop<false, XPF_POTRF>(acc, s0, none, smem, nh, pipe);
@@ -699,8 +720,8 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
             }
     }
     __threadfence_block();
-    if (shared_col) __syncthreads();  // publishes X to the CTA (df_wait's barrier does it otherwise)
-    else if (!df_wait(prog + j, j + 1, abort_flag, A.info, &s_ok)) return -1;  // inv(L_jj)
+    if (shared_col && !A.gprog) __syncthreads();  // publishes X to the CTA (df_wait's barrier does it otherwise)
+    else if (!df_wait(shared_col ? A.gprog + j : prog + j, j + 1, abort_flag, A.info, &s_ok)) return -1;  // inv(L_jj)
     zero_acc(acc);
     const double* invj = shared_col ? A.invdiag_g + (long long)j * TILE * TILE : A.invdiag + ((long long)b * nt + j) * TILE * TILE;
     Seg s1{Lij, npad, invj, TILE, TILE / KC};
@@ -721,17 +742,19 @@ __device__ __forceinline__ int df_panel_task(const PotrfArgs& A, int b, int i, i
 // running CTAs" holds whatever order the hardware dispatches blocks in), and the body is straight-line code like the
 // per-column kernels (inside a persistent loop ptxas spilled into all four mainloop copies, +100 instructions per chunk).
 template <bool GEN>
-__global__ void __launch_bounds__(NTHREADS, 1) potrf_dataflow_kernel(const __grid_constant__ PotrfArgs A) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+potrf_dataflow_kernel(const __grid_constant__ PotrfArgs A, const __grid_constant__ PotrfArgs G) {
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     __shared__ int s_col, s_local;
     Pipe pipe;
+    const int gc = A.gprog ? 1 : 0;  // communication expert in this launch (G): gt - col extra tasks lead every shared column
     if (threadIdx.x == 0) {
         const int B = A.B, nt = A.npad / TILE, gt = A.gt;
         const int task = atomicAdd(A.ctl, 1);
         // tasks of block column `col`: B diagonal tasks (col >= gt only) then B * (number of rows below max(col, gt-1)) panel tiles
         int col = 0, col_start = 0;
         for (;;) {
-            const int ntask = col < gt ? B * (nt - gt) : B * (nt - col);
+            const int ntask = col < gt ? gc * (gt - col) + B * (nt - gt) : B * (nt - col);
             if (task < col_start + ntask) break;
             col_start += ntask;
             ++col;
@@ -740,7 +763,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf_dataflow_kernel(const __gri
         s_local = task - col_start;
     }
     pipe_init(pipe, pipe_bars);  // ends with a CTA barrier
-    const int col = s_col, local = s_local, nt = A.npad / TILE;
+    const int col = s_col, nt = A.npad / TILE;
+    int local = s_local;
+    if (col < A.gt && gc) {  // the communication expert's own tasks of this column: its diagonal tile, then its panel tiles
+        if (local == 0) {
+            df_diag_task<GEN>(G, 0, col, 0u, pipe.bars);
+            return;
+        }
+        if (local < A.gt - col) {
+            df_panel_task<GEN>(G, 0, col + local, col, 0u, pipe.bars);
+            return;
+        }
+        local -= A.gt - col;
+    }
     if (col < A.gt) {  // shared block column: panel tiles of the rows below the shared block only
         const int per = nt - A.gt;
         df_panel_task<GEN>(A, local / per, A.gt + local % per, col, 0u, pipe.bars);
@@ -829,15 +864,15 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
             }
             int* ctl = reinterpret_cast<int*>(work);
             PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, ctl + 64,
-                        gt, Lg, npad_g, invdiag_g};
+                        gt, Lg, npad_g, invdiag_g, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr};
             CUDA_TRY(cudaMemsetAsync(work, 0, 256 + (size_t)B * nt * 4, st));
             const int grid = (int)total;  // one CTA per tile task
             if (gen) {
                 CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<true>, smem_df));
-                potrf_dataflow_kernel<true><<<grid, NTHREADS, smem_df, st>>>(A);
+                potrf_dataflow_kernel<true><<<grid, NTHREADS, smem_df, st>>>(A, A);
             } else {
                 CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<false>, smem_df));
-                potrf_dataflow_kernel<false><<<grid, NTHREADS, smem_df, st>>>(A);
+                potrf_dataflow_kernel<false><<<grid, NTHREADS, smem_df, st>>>(A, A);
             }
             CUDA_TRY(cudaGetLastError());
             return GPR_OK;
@@ -895,6 +930,45 @@ extern "C" int gpr_potrf_batched_shared(double* L, const double* a, const double
     ARG_CHECK(y && z && logdet_half && zz && info);
     return potrf_impl(L, 1, a, nrm, hp, hp_stride, diag_add, B, n, npad, dpad, invdiag, y, z, logdet_half, zz, info, work, stream,
                       ng / TILE, Lg, npad_g, invdiag_g);
+}
+
+// Whole GRBCM fit in one launch: the communication expert (xg, yg) and B local experts that start with its ng rows under its
+// hyper-parameters (see gpr_potrf_batched_shared; here the shared factor is produced by the same launch, so its serial chain
+// of ng/128 block columns overlaps the local experts' tiles instead of preceding them).
+extern "C" long long gpr_potrf_grbcm_work_bytes(int B, int npad, int npad_g) {
+    return 256 + align256((long long)B * (npad / TILE) * 4) + align256((long long)(npad_g / TILE) * 4);
+}
+
+extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
+                               int B, int n, int npad, int dpad, double* invdiag, const double* y, double* z, double* logdet_half,
+                               double* zz, int* info, double* Lg, const double* a_g, const double* nrm_g, const double* hp_g,
+                               const double* diag_add_g, int ng, int npad_g, double* invdiag_g, const double* y_g, double* z_g,
+                               double* logdet_half_g, double* zz_g, int* info_g, void* work, void* stream) {
+    ARG_CHECK(L && a && nrm && hp && invdiag && y && z && logdet_half && zz && info && work);
+    ARG_CHECK(Lg && a_g && nrm_g && hp_g && invdiag_g && y_g && z_g && logdet_half_g && zz_g && info_g);
+    ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n && dpad > 0 && dpad % 4 == 0);
+    ARG_CHECK(ng > 0 && ng % TILE == 0 && ng < n && npad_g == ng);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE, gt = ng / TILE;
+    const long long total = (long long)gt * (gt + 1) / 2 + (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
+    if (total >= (1LL << 30)) return fail(GPR_ERR_UNSUPPORTED, "too many tile tasks for one launch%s (%lld)", "", total);
+    const int fb = feat_smem_bytes(dpad);
+    if (TILE * XLD * 8 + fb > 227 * 1024)
+        return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
+    int smem_df = MAIN_SMEM_BYTES;
+    if (TILE * XLD * 8 + fb > smem_df) smem_df = TILE * XLD * 8 + fb;
+    int* ctl = reinterpret_cast<int*>(work);
+    int* progress = ctl + 64;
+    int* gprog = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + 256 + align256((long long)B * nt * 4));
+    CUDA_TRY(cudaMemsetAsync(work, 0, (size_t)gpr_potrf_grbcm_work_bytes(B, npad, npad_g), st));
+    PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, progress,
+                gt, Lg, npad_g, invdiag_g, gprog, nullptr, 0, 0, logdet_half_g, zz_g, info_g};
+    PotrfArgs G{Lg, 1, npad_g, ng, a_g, nrm_g, hp_g, 0, diag_add_g, dpad, invdiag_g, y_g, z_g, logdet_half_g, zz_g, info_g, ctl, gprog,
+                0, nullptr, 0, nullptr, nullptr, z, B, npad, nullptr, nullptr, nullptr};
+    CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<true>, smem_df));
+    potrf_dataflow_kernel<true><<<(int)total, NTHREADS, smem_df, st>>>(A, G);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -226,6 +226,56 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     return st
 
 
+def fit_grbcm(xg: torch.Tensor, yg: torch.Tensor, hp_g: torch.Tensor, x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor,
+              has_noise: bool, jitter: float = JITTER, L_out: Optional[torch.Tensor] = None) -> Tuple[FitState, FitState]:
+    """GRBCM's two factorisations (gr_bcm.py:28-29 -> gpr.py:65-74) in ONE launch, for the shared-hyper-parameter case:
+    the communication expert on (xg [1,ng,d], yg [1,ng], hp_g [1,P]) and the B local experts x [B,n,d] whose first ng rows
+    are xg and whose hp rows all equal hp_g (the caller vouches for both; ng % 128 == 0).  Equivalent to
+    ``st_g = fit(xg, yg, hp_g); st_l = fit(x, y, hp, shared=st_g)`` but the communication expert's serial chain of block
+    columns runs under the local experts' tiles (gpr_potrf_grbcm).  Returns (st_g, st_l)."""
+    B, n, d = x.shape
+    ng = xg.shape[1]
+    assert xg.shape[0] == 1 and ng % TILE == 0 and ng < n and hp.shape == (B, d + 1 + int(has_noise)) and hp_g.shape[0] == 1
+    dev = x.device
+    npad, gt = round_up(n, TILE), ng // TILE
+    nt = npad // TILE
+    lib = _lib.load()
+
+    def buffers(Bk, nk, npk):
+        return (torch.empty(Bk, npk // TILE, TILE, TILE, dtype=F64, device=dev), torch.zeros(Bk, npk, dtype=F64, device=dev),
+                torch.empty(Bk, npk, dtype=F64, device=dev), torch.empty(Bk, dtype=F64, device=dev),
+                torch.empty(Bk, dtype=F64, device=dev), torch.empty(Bk, dtype=torch.int32, device=dev))
+
+    a_g, nrm_g = scale_inputs(xg, hp_g, 1, ng)
+    a, nrm = scale_inputs(x, hp, B, npad)
+    dpad = a.shape[2]
+    dadd_g, prior_g = split_hp(hp_g, d, has_noise, jitter)
+    dadd, prior = split_hp(hp, d, has_noise, jitter)
+    Lg = torch.empty(1, ng, ng, dtype=F64, device=dev)
+    L = torch.empty(B, npad, npad, dtype=F64, device=dev) if L_out is None else L_out
+    inv_g, yp_g, z_g, ld_g, zz_g, info_g = buffers(1, ng, ng)
+    inv, yp, z, ld, zz, info = buffers(B, n, npad)
+    yp_g[:, :ng] = yg
+    yp[:, :n] = y
+    work = _work("potrf_grbcm", int(lib.gpr_potrf_grbcm_work_bytes(B, npad, ng)), dev)
+    _lib.call("gpr_potrf_grbcm", _p(L), _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(dadd), B, n, npad, dpad, _p(inv), _p(yp), _p(z),
+              _p(ld), _p(zz), _p(info), _p(Lg), _p(a_g), _p(nrm_g), _p(hp_g), _p(dadd_g), ng, ng, _p(inv_g), _p(yp_g), _p(z_g),
+              _p(ld_g), _p(zz_g), _p(info_g), _p(work), _stream())
+    # the leading block itself, for the kernels that walk a whole factor (backward solve, gradient, full covariance)
+    L[:, :ng, :ng] = Lg[0]
+    inv[:, :gt] = inv_g[0]
+    _count(1)
+    alpha_g = torch.empty(1, ng, dtype=F64, device=dev)
+    alpha = torch.empty(B, npad, dtype=F64, device=dev)
+    for (Lk, ik, Bk, npk, zk, ak, tag) in ((Lg, inv_g, 1, ng, z_g, alpha_g, "_g"), (L, inv, B, npad, z, alpha, "")):
+        twork = _work("trsv" + tag, int(lib.gpr_trsv_work_bytes(Bk)), dev)
+        _lib.call("gpr_trsv_backward", _p(Lk), _p(ik), Bk, npk, _p(zk), _p(ak), _p(twork), _stream())
+        _count(1)
+    st_g = FitState(1, ng, ng, d, dpad, has_noise, hp_g, a_g, nrm_g, Lg, inv_g, z_g, alpha_g, ld_g, zz_g, info_g, prior_g)
+    st_l = FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, inv, z, alpha, ld, zz, info, prior, st_g)
+    return st_g, st_l
+
+
 def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
     """In-place batched Cholesky of a padded [B, npad, npad] buffer holding the lower triangle of K
     (identity on the padding).  Returns (invdiag, z, logdet_half, zz, info).  tc.cholesky, gpr.py:69."""

@@ -88,14 +88,17 @@ class GRBCM(GPR):
         if self._shares_hyperparameters():
             # one hyper-parameter vector for the whole committee: the local experts' factors start with the communication
             # expert's (gr_bcm.py:19-26 puts its training set first in every expert), so it is fitted first and reused
-            if g.need_upd:
-                g.update()
-                l.need_upd = True
-            if l.need_upd:
-                l._launch_update(shared=g._state)
-                l._finish_update()
-                if l._state.shared_from is g._state:
-                    engine.tril_inverse(g._state)            # once per fit: the communication expert predicts in GEMM form
+            if g.need_upd and os.environ.get("PYGPR_GRBCM_FUSED_FIT", "1") != "0":
+                self._fused_update()                         # both factorisations in one launch
+            else:
+                if g.need_upd:
+                    g.update()
+                    l.need_upd = True
+                if l.need_upd:
+                    l._launch_update(shared=g._state)
+                    l._finish_update()
+            if l._state.shared_from is g._state:
+                engine.tril_inverse(g._state)                # once per fit: the communication expert predicts in GEMM form
             return None
         if l._state is not None and l._state.shared_from is not None and not l.need_upd and g.need_upd:
             l.need_upd = True                                 # the local factors were built on a communication factor that is stale
@@ -115,6 +118,20 @@ class GRBCM(GPR):
         g._finish_update()
         l._finish_update()
         return None
+
+    def _fused_update(self) -> None:
+        """gpg.update() + gpl.update() (gr_bcm.py:152-153 -> gpr.py:65-74) as one launch (engine.fit_grbcm)."""
+        g, l = self.gpg, self.gpl
+        spec = fused_spec(g.cov)
+        xg, yg, hp_g = g._device_inputs()
+        x, y, hp = l._device_inputs()
+        old, l._state, g._state = l._state, None, None
+        npad = engine.round_up(x.shape[1], engine.TILE)
+        L_buf = old.L if old is not None and tuple(old.L.shape) == (x.shape[0], npad, npad) and old.L.device == x.device else None
+        del old
+        g._state, l._state = engine.fit_grbcm(xg, yg, hp_g, x, y, hp, spec[0], L_out=L_buf)
+        g._finish_update()
+        l._finish_update()
 
     def _shares_hyperparameters(self) -> bool:
         """True when every local expert's hyper-parameter row equals the communication expert's vector (the GRBCM paper's
