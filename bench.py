@@ -318,9 +318,10 @@ def main():
                                          "from vt_gemm_kernel inside the same bracket)") if shared else
             "predict_kernel (local experts; the communication expert's launch overlaps it on a side stream)", "achieved": pred_flops_kernel / kern_ms * 1e-9, "peak": peak_tf,
             "unit": "TFLOP/s", "frac": pred_flops_kernel / kern_ms * 1e-9 / peak_tf,
-            # dram__bytes_read + dram__bytes_write of this launch (2.533 TB + 68.7 GB) from the ncu --set full capture in
-            # profiles/r01_s2_ncu_predict_kernel_bench_scale.json (valid for the default 1-GPU config only)
-            "traffic": 2.602e12 if (world == 1 and not args.small and m == 4096 and not shared) else None,
+            # dram__bytes_read + dram__bytes_write of this launch from the ncu --set full captures of the default 1-GPU config:
+            # shared block 1.811 TB + 73.1 GB (profiles/r01_s3_ncu_predict_shared_bench_scale.json), general path 2.533 TB +
+            # 68.7 GB (profiles/r01_s2_ncu_predict_kernel_bench_scale.json); other configurations were not captured
+            "traffic": (1.884e12 if shared else 2.602e12) if (world == 1 and not args.small and m == 4096) else None,
             "shared_leading_block": shared, "unshared_count_tflops": pred_flops_unshared / kern_ms * 1e-9,
             "peak_source": "cuBLAS dgemm 8192^3 (A B^T) measured in this run on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
             "kernel_ms": kern_ms, "flops_per_launch": pred_flops_kernel}

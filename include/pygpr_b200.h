@@ -137,6 +137,10 @@ int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, const double*
                     double* logdet_half_g, double* zz_g, int* info_g, void* work, void* stream);
 long long gpr_potrf_grbcm_work_bytes(int B, int npad, int npad_g);
 
+/* L[b, 0:ng, 0:ng] = Lg[0:ng, 0:ng] for every expert b (tile granular; lower_only != 0 leaves the tiles above the block diagonal
+ * alone) — the copy gpr_potrf_batched_shared / gpr_potrf_grbcm ask the caller for. */
+int gpr_copy_leading_block(double* L, int B, int npad, const double* Lg, int npad_g, int ng, int lower_only, void* stream);
+
 /*
  * alpha = L^-T z  (backward half of cholesky_solve, gpr.py:70-72).  HBM-bound: reads L once.
  *   z [B,npad] in, alpha [B,npad] out (may alias z only when work == NULL)

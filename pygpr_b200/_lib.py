@@ -38,6 +38,7 @@ SIGNATURES = {
     "gpr_potrf_grbcm": (c_int, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P,
                                 _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gpr_potrf_grbcm_work_bytes": (c_longlong, [_I, _I, _I]),
+    "gpr_copy_leading_block": (c_int, [_P, _I, _I, _P, _I, _I, _I, _P]),
     "gpr_potrf_batched_shared": (c_int, [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "gpr_trsv_backward": (c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gpr_trsv_work_bytes": (c_longlong, [_I]),

@@ -971,6 +971,28 @@ extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, co
     return GPR_OK;
 }
 
+// Replicate the communication expert's leading factor block into every expert's buffer (128 x 128 tiles; lower_only skips the
+// tiles above the block diagonal, which are only needed when they carry L_g^-T for gpr_lml_grad_shared).
+__global__ void __launch_bounds__(NTHREADS) copy_blocks_kernel(const double* __restrict__ src, long long src_ld, double* __restrict__ dst,
+                                                               long long dst_ld, long long dst_bstride, int lower_only) {
+    const int tc = blockIdx.x, tr = blockIdx.y;
+    if (lower_only && tc > tr) return;
+    const double* s = src + (long long)tr * TILE * src_ld + (long long)tc * TILE;
+    double* d = dst + (long long)blockIdx.z * dst_bstride + (long long)tr * TILE * dst_ld + (long long)tc * TILE;
+    for (int id = threadIdx.x; id < TILE * (TILE / 2); id += NTHREADS) {
+        const int r = id / (TILE / 2), c2 = (id % (TILE / 2)) * 2;
+        __stcs(reinterpret_cast<double2*>(d + (long long)r * dst_ld + c2), __ldg(reinterpret_cast<const double2*>(s + (long long)r * src_ld + c2)));
+    }
+}
+
+extern "C" int gpr_copy_leading_block(double* L, int B, int npad, const double* Lg, int npad_g, int ng, int lower_only, void* stream) {
+    ARG_CHECK(L && Lg && B > 0 && ng > 0 && ng % TILE == 0 && ng <= npad && ng <= npad_g && npad % 2 == 0 && npad_g % 2 == 0);
+    copy_blocks_kernel<<<dim3(ng / TILE, ng / TILE, B), NTHREADS, 0, (cudaStream_t)stream>>>(Lg, npad_g, L, npad, (long long)npad * npad,
+                                                                                            lower_only);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4: alpha = L^-T z.  HBM-bound (reads the lower triangle of L once); one CTA per expert walks the block
 // columns from last to first:  alpha_j = inv(L_jj)^T (z_j - sum_{i>j} L_ij^T alpha_i).

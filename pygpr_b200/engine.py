@@ -208,9 +208,9 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
         # the leading block itself, for the kernels that walk the whole factor (backward solve, gradient, full covariance);
         # if L_g^-T was already formed in the communication factor's block-upper part (kinv / tril_inverse) it comes along
         shared_upper = shared.Kinv is not None or shared.Linv is not None
-        L[:, :ng, :ng] = shared.L[0, :ng, :ng]
+        _lib.call("gpr_copy_leading_block", _p(L), B, npad, _p(shared.L), shared.npad, ng, int(not shared_upper), _stream())
         invdiag[:, :gt] = shared.invdiag[0, :gt]
-        _count(1)
+        _count(2)
     else:
         _lib.call("gpr_potrf_batched", _p(L), 1, _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
                   _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream())
@@ -262,9 +262,9 @@ def fit_grbcm(xg: torch.Tensor, yg: torch.Tensor, hp_g: torch.Tensor, x: torch.T
               _p(ld), _p(zz), _p(info), _p(Lg), _p(a_g), _p(nrm_g), _p(hp_g), _p(dadd_g), ng, ng, _p(inv_g), _p(yp_g), _p(z_g),
               _p(ld_g), _p(zz_g), _p(info_g), _p(work), _stream())
     # the leading block itself, for the kernels that walk a whole factor (backward solve, gradient, full covariance)
-    L[:, :ng, :ng] = Lg[0]
+    _lib.call("gpr_copy_leading_block", _p(L), B, npad, _p(Lg), ng, ng, 1, _stream())
     inv[:, :gt] = inv_g[0]
-    _count(1)
+    _count(2)
     alpha_g = torch.empty(1, ng, dtype=F64, device=dev)
     alpha = torch.empty(B, npad, dtype=F64, device=dev)
     for (Lk, ik, Bk, npk, zk, ak, tag) in ((Lg, inv_g, 1, ng, z_g, alpha_g, "_g"), (L, inv, B, npad, z, alpha, "")):
