@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/pygpr_b200.h"
 #include "gpr_core.cuh"
 
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
                    const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag, int lookahead,
                    double* __restrict__ z, int S, double* __restrict__ sk_slots, double* __restrict__ sk_gemv,
-                   int* __restrict__ sk_counters) {
+                   int* __restrict__ sk_counters, int row0) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     __shared__ int s_flag;
@@ -430,7 +432,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
     pipe_init(pipe, pipe_bars);
     const int b = blockIdx.y;
     const int nt = npad / TILE;
-    const int ntile_x = gridDim.x / S;                 // row tiles (+ the look-ahead tile) in this launch
+    const int ntile_x = gridDim.x / S;                 // row tiles (+ the look-ahead tile) in this launch; first row tile j+1+row0
     const int tx = blockIdx.x / S, part = blockIdx.x % S;
     // this CTA's slice of the j k-blocks
     const int kb0 = (int)((long long)part * j / S), kb1 = (int)((long long)(part + 1) * j / S);
@@ -470,7 +472,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
         return;
     }
 
-    const int i = j + 1 + tx;
+    const int i = j + 1 + row0 + tx;
     double* Lij = Lb + ((long long)i * TILE) * npad + j * TILE;
     NoHook nh;
     Seg s0{Lb + ((long long)i * TILE) * npad + (long long)kb0 * TILE, npad, Lb + ((long long)j * TILE) * npad + (long long)kb0 * TILE, npad,
@@ -811,12 +813,41 @@ static int choose_split(long long tiles, int depth, int sms, long long slot_cap)
 static inline long long align256(long long v) { return (v + 255) / 256 * 256; }
 // workspace layout: [counters: B*nt ints][gemv slots: B*32*128 doubles][tile slots: 12*sms + B*nt tiles of 128x128 doubles]
 static long long potrf_slot_tiles(int B, int nt, int sms) { return 12LL * sms + (long long)B * nt; }
+static long long potrf_chain_slot_tiles(int sms) { return 6LL * sms; }
 
 extern "C" long long gpr_potrf_work_bytes(int B, int npad) {
     int sms = gpr_device_sm_count();
     if (sms <= 0) sms = 148;
     const int nt = npad / TILE;
-    return 256 + align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
+    return 256 + align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8 +
+           align256((long long)B * nt * 4) + potrf_chain_slot_tiles(sms) * TILE * TILE * 8;   // + the chain launches' own counters / slots
+}
+
+// Internal streams / events of the two-stream per-column schedule (created once per device; no device memory)
+struct PotrfAux {
+    cudaStream_t chain = nullptr, bulk = nullptr;
+    cudaEvent_t fork = nullptr, join_chain = nullptr, join_bulk = nullptr, diag[4] = {}, bulk_done[4] = {};
+    bool ready = false;
+};
+static PotrfAux g_potrf_aux[64];
+static std::mutex g_potrf_aux_mutex, g_potrf_enqueue_mutex;
+static PotrfAux* potrf_aux() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_potrf_aux_mutex);
+    PotrfAux& x = g_potrf_aux[dev];
+    if (!x.ready) {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&x.chain, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;   // hi = highest priority
+        if (cudaStreamCreateWithPriority(&x.bulk, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+        cudaEvent_t* evs[] = {&x.fork, &x.join_chain, &x.join_bulk, &x.diag[0], &x.diag[1], &x.diag[2], &x.diag[3],
+                              &x.bulk_done[0], &x.bulk_done[1], &x.bulk_done[2], &x.bulk_done[3]};
+        for (cudaEvent_t* e : evs)
+            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        x.ready = true;
+    }
+    return &x;
 }
 
 static int potrf_impl(double* L, int gen, const double* a, const double* nrm, const double* hp, int hp_stride,
@@ -847,8 +878,10 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         const char* mode = getenv("PYGPR_POTRF_MODE");
         const long long total = (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
         // measured on B200 (tools/potrf_modes.py): dataflow wins from ~8 experts up (+8 % at B=32..63), ties at 4, loses below
-        bool dataflow = work && nt >= 2 && B >= 6 && total < (1LL << 30);
-        if (mode && !strcmp(mode, "columns")) dataflow = false;
+        // (two-stream per-column form: B=1 n=16384 61 ms vs 146 ms dataflow); up to 16 block columns the single launch also wins
+        // for few experts (B=1 n=1024: 1.58 vs 1.83 ms, B=3 n=2048: 3.39 vs 3.90 ms) because launch latencies dominate there
+        bool dataflow = work && nt >= 2 && (B >= 6 || nt <= 16) && total < (1LL << 30);
+        if (mode && !strncmp(mode, "columns", 7)) dataflow = false;
         if (mode && !strcmp(mode, "dataflow") && work && total < (1LL << 30)) dataflow = true;
         if (gt > 0) {  // the shared leading block exists in the dataflow form only
             if (!work || total >= (1LL << 30)) return fail(GPR_ERR_BAD_ARG, "shared leading block needs a workspace%s", "");
@@ -891,25 +924,73 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         CUDA_TRY(opt_in_smem(potrf_diag_kernel<false>, smem_diag));
         CUDA_TRY(opt_in_smem(potrf_panel_kernel<false>, smem_panel));
     }
+    // Per-column schedule.  With a workspace it runs on two internal streams: the CHAIN  diag(j) -> [tile (j+1, j) + look-ahead
+    // product] -> diag(j+1) -> ...  (few CTAs, latency bound: the register-resident potf2/trti2 is ~0.1 ms per column) on a
+    // high-priority stream, and the BULK of each panel (row tiles j+2 ...) on a low-priority one that only needs diag(j); the
+    // chain of column j+1 needs the bulk of column j-1... so a column costs max(bulk, chain) instead of their sum
+    // (n = 16384, one matrix: 79 -> 61 ms; 4 x 8192: 40 -> 32 ms).  PYGPR_POTRF_MODE=columns1 keeps everything on the caller's stream.
+    const char* mode1 = getenv("PYGPR_POTRF_MODE");
+    PotrfAux* aux = (work && nt >= 3 && !(mode1 && !strcmp(mode1, "columns1"))) ? potrf_aux() : nullptr;
+    int* counters_c = nullptr;
+    double* slots_c = nullptr;
+    // the internal streams and events are per device: one factorisation at a time may be ENQUEUED through them
+    std::unique_lock<std::mutex> enqueue_lock(g_potrf_enqueue_mutex, std::defer_lock);
+    if (aux) enqueue_lock.lock();
+    if (aux) {
+        char* p = reinterpret_cast<char*>(slots) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
+        counters_c = reinterpret_cast<int*>(p);
+        slots_c = reinterpret_cast<double*>(p + align256((long long)B * nt * 4));
+        CUDA_TRY(cudaMemsetAsync(counters_c, 0, (size_t)B * nt * 4, st));
+        CUDA_TRY(cudaEventRecord(aux->fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(aux->chain, aux->fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(aux->bulk, aux->fork, 0));
+    }
+    cudaStream_t sc = aux ? aux->chain : st, sb = aux ? aux->bulk : st;
+    auto launch_panel = [&](cudaStream_t s_, int j, int row0, int ntile_rows, int lookahead, int S, double* sl, int* cnt) {
+        dim3 grid((ntile_rows + lookahead) * S, B);
+        if (gen)
+            potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, s_>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag, lookahead,
+                                                                         y ? z : nullptr, S, sl, gemv, cnt, row0);
+        else
+            potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, s_>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag, lookahead,
+                                                                          y ? z : nullptr, S, sl, gemv, cnt, row0);
+    };
+    bool bulk_prev = false;  // column j-1 had a bulk launch
     for (int j = 0; j < nt; ++j) {
         if (gen)
-            potrf_diag_kernel<true><<<B, NTHREADS, smem_diag, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad, invdiag,
+            potrf_diag_kernel<true><<<B, NTHREADS, smem_diag, sc>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad, invdiag,
                                                                      y, z, logdet_half, zz, info);
         else
-            potrf_diag_kernel<false><<<B, NTHREADS, smem_diag, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad,
+            potrf_diag_kernel<false><<<B, NTHREADS, smem_diag, sc>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad,
                                                                       invdiag, y, z, logdet_half, zz, info);
-        if (j + 1 < nt) {
-            const int lookahead = (j >= 1) ? 1 : 0;
+        if (j + 1 >= nt) break;
+        const int lookahead = (j >= 1) ? 1 : 0;
+        if (!aux) {
             const int ntile_x = nt - 1 - j + lookahead;
             const int S = work ? choose_split((long long)B * ntile_x, j, sms, potrf_slot_tiles(B, nt, sms)) : 1;
-            dim3 grid(ntile_x * S, B);
-            if (gen)
-                potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag,
-                                                                             lookahead, y ? z : nullptr, S, slots, gemv, counters);
-            else
-                potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, st>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag,
-                                                                              lookahead, y ? z : nullptr, S, slots, gemv, counters);
+            launch_panel(st, j, 0, nt - 1 - j, lookahead, S, slots, counters);
+            continue;
         }
+        const int rows_bulk = nt - 2 - j;
+        CUDA_TRY(cudaEventRecord(aux->diag[j & 3], sc));
+        if (rows_bulk > 0) {
+            CUDA_TRY(cudaStreamWaitEvent(sb, aux->diag[j & 3], 0));
+            const int S = choose_split((long long)B * rows_bulk, j, sms, potrf_slot_tiles(B, nt, sms));
+            launch_panel(sb, j, 1, rows_bulk, 0, S, slots, counters);
+            CUDA_TRY(cudaEventRecord(aux->bulk_done[j & 3], sb));
+        }
+        if (bulk_prev) CUDA_TRY(cudaStreamWaitEvent(sc, aux->bulk_done[(j - 1) & 3], 0));   // row j+1 of column j-1
+        {
+            const int S = choose_split((long long)B * (1 + lookahead), j, sms, potrf_chain_slot_tiles(sms));
+            launch_panel(sc, j, 0, 1, lookahead, S, slots_c, counters_c);
+        }
+        bulk_prev = rows_bulk > 0;
+    }
+    if (aux) {
+        CUDA_TRY(cudaEventRecord(aux->join_chain, sc));
+        CUDA_TRY(cudaEventRecord(aux->join_bulk, sb));
+        CUDA_TRY(cudaStreamWaitEvent(st, aux->join_chain, 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, aux->join_bulk, 0));
     }
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;

@@ -47,7 +47,7 @@ def bench(B, n, d, reps=3):
     npad = eng.round_up(n, 128)
     L = torch.empty(B, npad, npad, dtype=torch.float64, device="cuda")
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    for mode in ("columns", "dataflow"):
+    for mode in ("columns1", "columns", "dataflow"):
         fit(mode, x, y, hp, L); torch.cuda.synchronize()
         best = 1e9
         for _ in range(reps):
@@ -61,6 +61,9 @@ if __name__ == "__main__":
     if what in ("all", "check"):
         for c in [(3, 300, 4), (5, 1500, 8), (1, 128, 3), (2, 129, 16), (40, 1024, 16)]:
             check(*c)
+    if what == "small":
+        for c in [(1, 16384, 8), (1, 4096, 16), (1, 8192, 16), (2, 8192, 8), (4, 8192, 16), (1, 1024, 4), (3, 2048, 8)]:
+            bench(*c)
     if what == "border":
         for c in [(2, 16384, 8), (4, 8192, 16), (4, 16384, 8), (16, 2048, 8), (8, 4096, 8), (16, 4096, 8), (148, 1024, 8), (2, 8192, 8)]:
             bench(*c)
