@@ -337,7 +337,8 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
     __syncthreads();
     DiagBlock blk;
     diag_block_coords(blk);
-    potf2_reg(T, pub, s_fail, blk);
+    __shared__ double invblk[(TILE / 8) * 64];
+    potf2_blk(T, invblk, s_fail, blk);
 
     // write L_jj (strict upper zeroed) and accumulate sum log L_ii
     for (int id = tid; id < TILE * TILE; id += NTHREADS) {
@@ -356,7 +357,7 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             }
         }
     }
-    trtri_reg(T, pub, blk);
+    trtri_blk(T, invblk, blk);
     double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
     for (int id = tid; id < TILE * TILE; id += NTHREADS) inv[id] = T[(id >> 7) * XLD + (id & 127)];
     if (y) {
