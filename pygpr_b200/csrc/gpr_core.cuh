@@ -378,13 +378,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---------------------------------------------------------------------------------------------
 // Register-resident factorisation of one 128x128 diagonal tile.
-// The lower triangle is cut into 136 blocks of 8x8; thread q < 136 owns block (bi, bj) in 64 registers.  A
-// right-looking step is: owners of the pivot column (row) publish 8 values, ONE barrier (the published vector is
-// double buffered), then every live block does 4 LDS.128 x2 + 64 unconditional DFMA.  Boundary blocks mask the
-// published vector instead of predicating the update, the kr loop stays rolled (register column/row selected by a
-// switch only in the 8-value publish), and no sqrt/divide sits on the step-to-step dependency chain: the Cholesky
-// update uses u_i u_j / p with the columns kept unscaled until the end.  (r01: the smem version took ~0.5 ms per
-// tile, a fully unrolled/predicated register version 0.36 ms (240 KB of code, 53 % barrier stalls).)
+// The lower triangle is cut into 136 blocks of 8x8; thread q < 136 owns block (bi, bj) in 64 registers (potf2_blk /
+// trtri_blk below).  History (r01): an smem version took ~0.5 ms per tile, a fully unrolled/predicated register version
+// 0.36 ms (240 KB of code, 53 % barrier stalls), 128 rolled rank-1 steps with one barrier each ~0.1 ms, the blocked form
+// below ~0.07 ms; what is left is phase latency (in-thread 8x8 Cholesky with its sqrt/divide chain) and idle lanes as the
+// trailing matrix shrinks.
 // ---------------------------------------------------------------------------------------------
 struct DiagBlock {
     int bi, bj;       // block row / column (bi >= bj); bi = -1 for idle threads
@@ -403,163 +401,9 @@ __device__ __forceinline__ void diag_block_coords(DiagBlock& d) {
     }
 }
 
-template <int KR>
-__device__ __forceinline__ void publish_col(const DiagBlock& d, double* dst) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) dst[r] = d.R[r][KR];
-}
-__device__ __forceinline__ void publish_col(const DiagBlock& d, int kr, double* dst) {
-    switch (kr) {
-        case 0: publish_col<0>(d, dst); break;
-        case 1: publish_col<1>(d, dst); break;
-        case 2: publish_col<2>(d, dst); break;
-        case 3: publish_col<3>(d, dst); break;
-        case 4: publish_col<4>(d, dst); break;
-        case 5: publish_col<5>(d, dst); break;
-        case 6: publish_col<6>(d, dst); break;
-        default: publish_col<7>(d, dst); break;
-    }
-}
-template <int KR>
-__device__ __forceinline__ void scale_publish_row(DiagBlock& d, double f, double* dst) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const double v = d.R[KR][c] * f;
-        d.R[KR][c] = v;
-        dst[c] = v;
-    }
-}
-__device__ __forceinline__ void scale_publish_row(DiagBlock& d, int kr, double f, double* dst) {
-    switch (kr) {
-        case 0: scale_publish_row<0>(d, f, dst); break;
-        case 1: scale_publish_row<1>(d, f, dst); break;
-        case 2: scale_publish_row<2>(d, f, dst); break;
-        case 3: scale_publish_row<3>(d, f, dst); break;
-        case 4: scale_publish_row<4>(d, f, dst); break;
-        case 5: scale_publish_row<5>(d, f, dst); break;
-        case 6: scale_publish_row<6>(d, f, dst); break;
-        default: scale_publish_row<7>(d, f, dst); break;
-    }
-}
-
-// T (row stride XLD) holds the symmetric tile (lower part used).  On return T holds L in the lower triangle AND its
-// transpose in the upper triangle (T[k][i] = L[i][k]) so a column of L is a contiguous row for the inversion.
-// pub: 3 x 128 doubles scratch (two publish buffers + pivots).  *fail = first 1-based column with a non-positive
-// pivot (0 if none).
-__device__ __forceinline__ void potf2_reg(double* T, double* pub, int* fail, DiagBlock& d) {
-    const bool live = d.bi >= 0;
-    double* piv = pub + 2 * TILE;
-    if (live) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) d.R[r][c] = T[(d.bi * 8 + r) * XLD + d.bj * 8 + c];
-    }
-#pragma unroll 1
-    for (int k = 0; k < TILE; ++k) {
-        const int kb = k >> 3, kr = k & 7;
-        double* u = pub + (k & 1) * TILE;
-        if (live && d.bj == kb) publish_col(d, kr, u + d.bi * 8);   // unscaled column k (rows of this block)
-        __syncthreads();
-        if (live && d.bj >= kb) {
-            const double p = u[k];
-            if (d.bi == kb && d.bj == kb) {
-                piv[k] = p;
-                if (!(p > 0.0)) atomicMin(fail, k + 1);
-            }
-            const double pinv = __drcp_rn(p);
-            double li[8], lj[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) li[r] = u[d.bi * 8 + r] * pinv;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) lj[c] = u[d.bj * 8 + c];
-            if (d.bj == kb) {  // columns <= k of the pivot block column are final (kept unscaled): mask them out
-#pragma unroll
-                for (int c = 0; c < 8; ++c) lj[c] = (c > kr) ? lj[c] : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) d.R[r][c] -= li[r] * lj[c];
-        }
-    }
-    __syncthreads();
-    // L[i][k] = u_ik / sqrt(p_k),  L[k][k] = sqrt(p_k); write both triangles of T
-    if (threadIdx.x < TILE) {
-        const double sq = sqrt(piv[threadIdx.x]);
-        pub[threadIdx.x] = sq;
-        pub[TILE + threadIdx.x] = 1.0 / sq;
-    }
-    __syncthreads();
-    if (live) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int gr = d.bi * 8 + r, gc = d.bj * 8 + c;
-                if (gr >= gc) {
-                    const double v = (gr == gc) ? pub[gc] : d.R[r][c] * pub[TILE + gc];
-                    T[gr * XLD + gc] = v;
-                    T[gc * XLD + gr] = v;
-                }
-            }
-    }
-    __syncthreads();
-}
-
-// X = L^-1 by right-looking forward substitution on the identity, blocks in registers.  T as left by potf2_reg
-// (column k of L readable as row k).  On return T holds X in the lower triangle and zeros above it.
-__device__ __forceinline__ void trtri_reg(double* T, double* pub, DiagBlock& d) {
-    const bool live = d.bi >= 0;
-    double* dinv = pub + 2 * TILE;
-    if (threadIdx.x < TILE) dinv[threadIdx.x] = 1.0 / T[threadIdx.x * XLD + threadIdx.x];
-    if (live) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) d.R[r][c] = (d.bi == d.bj && r == c) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int k = 0; k < TILE; ++k) {
-        const int kb = k >> 3, kr = k & 7;
-        double* xr = pub + (k & 1) * TILE;
-        if (live && d.bi == kb) scale_publish_row(d, kr, dinv[k], xr + d.bj * 8);  // row k of X is final
-        __syncthreads();
-        if (live && d.bi >= kb && d.bj <= kb) {
-            double lc[8], xv[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) lc[r] = T[k * XLD + d.bi * 8 + r];
-            if (d.bi == kb) {  // rows <= k of the pivot block row are final
-#pragma unroll
-                for (int r = 0; r < 8; ++r) lc[r] = (r > kr) ? lc[r] : 0.0;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) xv[c] = xr[d.bj * 8 + c];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) d.R[r][c] -= lc[r] * xv[c];
-        }
-    }
-    __syncthreads();
-    if (live) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int gr = d.bi * 8 + r, gc = d.bj * 8 + c;
-                if (gr >= gc) T[gr * XLD + gc] = d.R[r][c];
-                else T[gr * XLD + gc] = 0.0;
-                if (gr > gc) T[gc * XLD + gr] = 0.0;
-            }
-    }
-    __syncthreads();
-}
-
 // ---------------------------------------------------------------------------------------------
-// Blocked form of the two routines above (v2).  The 128 rank-1 steps (one CTA barrier and 64 DFMA per thread each, ~780
-// clocks per step) become 16 block steps over the 8x8 register blocks: the owner of the diagonal block factorises and
+// Blocked factorisation / inversion (v2).  v1 ran 128 rank-1 steps (one CTA barrier and 64 DFMA per thread each, ~780 clocks
+// per step); here 16 block steps over the 8x8 register blocks: the owner of the diagonal block factorises and
 // inverts it in registers, the panel blocks multiply by that inverse, the trailing blocks take one 8x8x8 product
 // (512 DFMA behind 32 LDS.128) — 2 barriers per block step instead of 8, and 8x more independent work between them.
 // T is the exchange medium: every block is written at its final position.  invblk[kb] = inv(L_kk) (8x8, row major).
