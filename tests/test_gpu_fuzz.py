@@ -1,0 +1,18 @@
+"""Randomised parity sweep (tools/fuzz_parity.py): ragged sizes, 2..9 experts, aligned / unaligned communication sets, shared /
+per-expert hyper-parameters, every quantity of the path against the CPU oracle at relative 1e-8."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_shapes_against_oracle(seed):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), str(seed), "16"], capture_output=True,
+                         text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "fuzz_parity: ok" in res.stdout
