@@ -308,7 +308,25 @@ def _work(kind: str, nbytes: int, dev: torch.device) -> torch.Tensor:
     return buf
 
 
-def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind: str = "predict"
+_sm_count = {}
+
+
+def _use_gemm_form(st: FitState, m: int) -> bool:
+    """Prediction form: blocked substitution (one serial task per expert and 128 test points — the bench path) or the
+    triangular GEMM with L^-1 (independent tiles; needs the inverse once per fit).  PYGPR_PREDICT_FORM=subst|gemm forces."""
+    import os
+    form = os.environ.get("PYGPR_PREDICT_FORM", "auto")
+    if form in ("subst", "gemm"):
+        return form == "gemm"
+    dev = st.L.device.index
+    if dev not in _sm_count:
+        _sm_count[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    tasks = st.B * ((m + TILE - 1) // TILE)
+    vt_bytes = tasks * TILE * st.npad * 8
+    return st.npad >= 2 * TILE and 2 * tasks < _sm_count[dev] and vt_bytes + st.B * st.npad * st.npad * 8 < (8 << 30)
+
+
+def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind: str = "predict", allow_gemm: bool = True
             ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """mean [B, m] and variance [B, m] of every expert at xs [m, d]  (gpr.py:76-106)."""
     assert st.alpha is not None
@@ -316,6 +334,18 @@ def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind:
     dev = xs.device
     mean = torch.empty(st.B, m, dtype=F64, device=dev)
     var = torch.empty(st.B, m, dtype=F64, device=dev) if want_var else None
+    if want_var and allow_gemm and _use_gemm_form(st, m):
+        # few (expert, 128-test-point) tasks — a single large GP, a handful of experts, few test points: the serial
+        # substitutions would leave most SMs idle, the triangular GEMM with the cached L^-1 has (m/128)(n/128) tiles per expert
+        lib = _lib.load()
+        mt = (m + TILE - 1) // TILE
+        Linv = tril_inverse(st)
+        vt = _work(scratch_kind + "_vt", st.B * mt * TILE * st.npad * 8, dev)
+        scratch = _work(scratch_kind + "_gemm", int(lib.gpr_predict_gemm_scratch_bytes(st.B, st.npad, st.dpad, m)), dev)
+        _lib.call("gpr_predict_gemm", _p(Linv), _p(st.a), _p(st.nrm), _p(st.z), _p(st.hp), st.hp.shape[-1], _p(st.prior), _p(xs),
+                  st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), _p(vt), _p(scratch), _stream())
+        _count(4)
+        return mean, var
     scratch = _work(scratch_kind, int(_lib.load().gpr_predict_scratch_bytes(st.npad)), dev)
     _lib.call("gpr_predict", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
               _p(st.prior), _p(xs), st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), int(want_var),
@@ -353,7 +383,7 @@ def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     side.wait_stream(main)                    # inputs are ready; taken BEFORE the big launch so the side stream does not wait for it
     ml, vl = predict(st_l, xs, True)
     with torch.cuda.stream(side):
-        mg, vg = predict(st_g, xs, True, scratch_kind="predict_side")
+        mg, vg = predict(st_g, xs, True, scratch_kind="predict_side", allow_gemm=False)   # substitution tasks: tail fillers
     main.wait_stream(side)
     mg.record_stream(main)
     vg.record_stream(main)

@@ -54,7 +54,10 @@ def test_se_kernels(eng, orc, B, n, d, m):
 @pytest.mark.parametrize("B,n,d,m,per", [(1, 37, 3, 11, False), (1, 128, 2, 128, False), (4, 130, 5, 29, True),
                                          (2, 256, 16, 300, False), (3, 300, 7, 129, True), (2, 1000, 1, 200, False),
                                          (1, 1500, 8, 64, False)])
-def test_fit_predict(eng, orc, B, n, d, m, per):
+@pytest.mark.parametrize("form", ["subst", "gemm"])
+def test_fit_predict(eng, orc, monkeypatch, B, n, d, m, per, form):
+    """form: blocked substitution (the bench kernel) / triangular GEMM with L^-1 (what few-task predictions use)."""
+    monkeypatch.setenv("PYGPR_PREDICT_FORM", form)
     x, y, xs, hp = _data(2, B, n, d, m, per_expert=per)
     st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True)
     torch.cuda.synchronize()

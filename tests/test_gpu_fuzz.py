@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("seed", [11, 12])
-def test_random_shapes_against_oracle(seed):
+@pytest.mark.parametrize("seed,form", [(11, "subst"), (12, "auto")])
+def test_random_shapes_against_oracle(seed, form):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), str(seed), "16"], capture_output=True,
-                         text=True, timeout=600, cwd=ROOT)
+                         text=True, timeout=600, cwd=ROOT, env=dict(os.environ, PYGPR_PREDICT_FORM=form))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "fuzz_parity: ok" in res.stdout

@@ -47,11 +47,13 @@ def _dense_reference(x, y, xs, hp):
     return mean, var, nlml, alpha[..., 0]
 
 
+@pytest.mark.parametrize("form", ["subst", "gemm"])   # blocked substitution (bench kernel) / triangular GEMM with L^-1
 @pytest.mark.parametrize("B,n,d,m", [(6, 8192, 16, 384), (2, 4096, 16, 256), (1, 16384, 8, 128)])
-def test_fit_predict_at_baseline_sizes(B, n, d, m):
+def test_fit_predict_at_baseline_sizes(monkeypatch, B, n, d, m, form):
     """Expert orders of configs 4 (8192, and the 4096 communication expert) and 2 (16384): both schedules of the
     factorisation are exercised (B=6 -> dataflow, B<6 -> per-column with split-K)."""
     from pygpr_b200 import engine as eng
+    monkeypatch.setenv("PYGPR_PREDICT_FORM", form)
     x, y, xs, hp = _data(11, B, n, d, m)
     st = eng.fit(x, y, hp, True)
     mean, var = eng.predict(st, xs, True)

@@ -39,7 +39,10 @@ def main():
         mle = P.MLE(gp); hp = gp.params.numpy()
         tl, nl = timed(lambda: mle.loss(hp), 2); tg, lg = timed(lambda: mle.loss_and_grad(hp), 2)
         tr, gamma = timed(lambda: P.get_learn_rate(gp.params, mle, 1e-4), 1)
-        print(json.dumps({"config": "2: exact GPR n=16384 d=8 LML+grad", "loss_ms": tl * 1e3, "loss_tflops": n ** 3 / 3 / tl * 1e-12,
+        xs = torch.rand(1024, d)
+        gp.update()
+        tp, _ = timed(lambda: gp.predict(xs, var="diag"), 2)
+        print(json.dumps({"config": "2: exact GPR n=16384 d=8 LML+grad", "predict_1024_ms": tp * 1e3, "loss_ms": tl * 1e3, "loss_tflops": n ** 3 / 3 / tl * 1e-12,
                           "loss_and_grad_ms": tg * 1e3, "loss_and_grad_tflops": float(n) ** 3 / tg * 1e-12, "nlml": float(nl),
                           "grad_norm": float(np.linalg.norm(lg[1])), "get_learn_rate_ms": tr * 1e3, "gamma": float(gamma)}), flush=True)
     if "3" in which:  # GRBCM 64 x 2048 + comm, d=8
