@@ -153,7 +153,16 @@ class GRBCM(GPR):
             # gr_bcm.py:152-153 with the two predictions overlapped on the device (engine.predict_pair)
             self.update()
             xd = engine._dev(xs).reshape(-1, xs.shape[-1])
-            (mg, vg), (ml, vl) = engine.predict_pair(self.gpg._state, self.gpl._state, xd)
+            # test points go through in chunks: the per-chunk scratch (the communication expert's V_g^T is
+            # [chunk, ng]) stays bounded however many points are asked for; the kernels see chunks as independent batches
+            step = max(int(os.environ.get("PYGPR_PREDICT_CHUNK", "16384")), 1)
+            if xd.shape[0] <= step:
+                (mg, vg), (ml, vl) = engine.predict_pair(self.gpg._state, self.gpl._state, xd)
+            else:
+                parts = [engine.predict_pair(self.gpg._state, self.gpl._state, xd[s:s + step].contiguous())
+                         for s in range(0, xd.shape[0], step)]
+                mg, vg = (torch.cat([p[0][k] for p in parts], dim=1) for k in (0, 1))
+                ml, vl = (torch.cat([p[1][k] for p in parts], dim=1) for k in (0, 1))
             ys_g, covars_g = _back(mg.squeeze(), self.gpg.x), self.gpg._shape_out(vg)
             ys_l, covars_l = _back(ml.squeeze(), self.gpl.x), self.gpl._shape_out(vl)
         else:
