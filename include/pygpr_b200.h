@@ -129,6 +129,7 @@ int gpr_potrf_batched_shared(double* L, const double* a, const double* nrm, cons
  * communication expert's tile tasks lead every shared block column and the local tiles wait on its progress counters, so
  * its serial chain of ng/128 block columns runs under the local experts' work.  *_g arguments as for gpr_potrf_batched with
  * B = 1 (hp_g: one row); outputs of both models as in the two separate calls; z[b, 0:ng] is filled by the kernel.
+ * ng need not be a multiple of 128: the floor(ng/128) whole blocks are shared, the ragged rest is each model's own.
  */
 int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
                     int B, int n, int npad, int dpad, double* invdiag, const double* y, double* z, double* logdet_half,
@@ -136,6 +137,10 @@ int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, const double*
                     const double* diag_add_g, int ng, int npad_g, double* invdiag_g, const double* y_g, double* z_g,
                     double* logdet_half_g, double* zz_g, int* info_g, void* work, void* stream);
 long long gpr_potrf_grbcm_work_bytes(int B, int npad, int npad_g);
+
+/* out[0] = sum_{i<rows} log L_ii, out[1] = sum_{i<rows} z_i^2 of a finished B = 1 factorisation: the values gpr_potrf_batched_shared's
+ * logdet_half / zz are pre-loaded with when only the first `rows` rows are shared. */
+int gpr_factor_partials(const double* L, int npad, const double* z, int rows, double* out, void* stream);
 
 /* L[b, 0:ng, 0:ng] = Lg[0:ng, 0:ng] for every expert b (tile granular; lower_only != 0 leaves the tiles above the block diagonal
  * alone) — the copy gpr_potrf_batched_shared / gpr_potrf_grbcm ask the caller for. */
@@ -194,10 +199,12 @@ int gpr_tril_inverse(double* L, const double* invdiag, int B, int npad, double* 
  * instead of ceil(m/128) serial substitutions, for the single communication expert whose V^T every local expert waits for.
  *   mean = V^T z (= K* alpha, gpr.py:79-85),  var = prior - |V|^2 (gpr.py:96-106),  vt [B, ceil(m/128), 128, npad]
  *   z = L^-1 y [B, npad];  scratch >= gpr_predict_gemm_scratch_bytes(B, npad, dpad, m)
+ *   mean_part / var_part (or NULL): the same sums restricted to the first rows_part training rows (a multiple of 128) — what
+ *   gpr_predict_shared continues from when only those rows are shared with the local experts
  */
 int gpr_predict_gemm(const double* X, const double* a, const double* nrm, const double* z, const double* hp, int hp_stride,
                      const double* prior, const double* xs, int B, int n, int npad, int d, int dpad, int m, double* mean,
-                     double* var, double* vt, void* scratch, void* stream);
+                     double* var, double* vt, void* scratch, void* stream, int rows_part, double* mean_part, double* var_part);
 long long gpr_predict_gemm_scratch_bytes(int B, int npad, int dpad, int m);
 
 /*

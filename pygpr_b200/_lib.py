@@ -23,7 +23,8 @@ SIGNATURES = {
     "gpr_device_sm_count": (c_int, []),
     "gpr_predict_scratch_bytes": (c_longlong, [_I]),
     "gpr_tril_inverse": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
-    "gpr_predict_gemm": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gpr_predict_gemm": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "gpr_factor_partials": (c_int, [_P, _I, _P, _I, _P, _P]),
     "gpr_predict_gemm_scratch_bytes": (c_longlong, [_I, _I, _I, _I]),
     "gpr_predict_keep": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpr_predict_shared": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P]),

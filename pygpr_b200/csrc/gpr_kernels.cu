@@ -290,7 +290,11 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
                                             const double* __restrict__ diag_add, int dpad, double* invdiag, const double* y,
                                             double* zb, double* logdet_half, double* zz, int* info, const double* dpart,
                                             bool first = false, bool use_first = false, const double* base_ld = nullptr,
-                                            const double* base_zz = nullptr, const int* base_info = nullptr) {
+                                            const double* base_zz = nullptr, const int* base_info = nullptr, int base_n = 0,
+                                            double* ld_blk = nullptr, double* zz_blk = nullptr) {
+    // base_ld / base_zz: per-block-column partial sums of ANOTHER factorisation (the communication expert's, same launch);
+    // at `start` the first base_n of them are the value the sums continue from.  ld_blk / zz_blk: where THIS expert records
+    // its own per-block-column partials (row b*nt + j), for exactly that use.
     // first: this is the expert's first diagonal task (logdet / z.z / info start here).  Default (use_first == false): j == 0.
     // base_*: values the sums start from (the communication expert's, when it is factorised in the same launch).
     const int tid = threadIdx.x;
@@ -350,9 +354,14 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
         for (int k = tid; k < TILE; k += 32) s += log(T[k * XLD + k]);
         s = warp_sum(s);
         if (tid == 0) {
-            if (logdet_half) __stcg(logdet_half + b, (start ? (base_ld ? __ldcg(base_ld) : 0.0) : __ldcg(logdet_half + b)) + s);
+            double prev_ld = start ? 0.0 : __ldcg(logdet_half + b);
+            if (start && base_ld)
+                for (int q = 0; q < base_n; ++q) prev_ld += __ldcg(base_ld + q);
+            if (logdet_half) __stcg(logdet_half + b, prev_ld + s);
+            if (ld_blk) __stcg(ld_blk + (long long)b * nt + j, s);
             if (info) {
-                const int prev = start ? (base_info ? __ldcg(base_info) : 0) : __ldcg(info + b);
+                int prev = start ? (base_info ? __ldcg(base_info) : 0) : __ldcg(info + b);
+                if (start && base_info && prev > base_n * TILE) prev = 0;  // the other factorisation failed outside the shared block
                 if (start || (prev == 0 && *s_fail <= TILE)) __stcg(info + b, prev != 0 ? prev : (*s_fail <= TILE ? j * TILE + *s_fail : 0));
             }
         }
@@ -378,7 +387,13 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
         if (tid < 32 && zz) {
             double s = svec[tid] + svec[tid + 32] + svec[tid + 64] + svec[tid + 96];
             s = warp_sum(s);
-            if (tid == 0) __stcg(zz + b, (start ? (base_zz ? __ldcg(base_zz) : 0.0) : __ldcg(zz + b)) + s);
+            if (tid == 0) {
+                double prev_zz = start ? 0.0 : __ldcg(zz + b);
+                if (start && base_zz)
+                    for (int q = 0; q < base_n; ++q) prev_zz += __ldcg(base_zz + q);
+                __stcg(zz + b, prev_zz + s);
+                if (zz_blk) __stcg(zz_blk + (long long)b * nt + j, s);
+            }
         }
     }
 }
@@ -606,9 +621,10 @@ struct PotrfArgs {
     // (zbcast: [zbcast_B, zbcast_stride]) and the experts' logdet / z.z / info start from its totals (base_*).
     const int* gprog;
     double* zbcast;
-    int zbcast_B, zbcast_stride;
-    const double *base_ld, *base_zz;
+    int zbcast_B, zbcast_stride, zbcast_gt;   // only the first zbcast_gt blocks of z are shared
+    const double *base_ld, *base_zz;          // the communication expert's per-block-column partials (first gt are the base)
     const int* base_info;
+    double *ld_blk, *zz_blk;                  // where this factorisation records its own per-block-column partials
 };
 
 // The two task bodies are separate NON-inlined functions so that each gets the register allocation of a stand-alone
@@ -650,8 +666,8 @@ __device__ __forceinline__ int df_diag_task(const PotrfArgs& A, int b, int j, un
     // continuing from its totals; with a precomputed shared block the host pre-loaded them and there is no start
     diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, A.n, npad, A.a, A.nrm, A.hp, A.hp_stride, A.diag_add, A.dpad, A.invdiag,
                      A.y, zb, A.logdet_half, A.zz, A.info, nullptr, (A.gt == 0 && j == 0) || (A.base_ld != nullptr && j == A.gt), true,
-                     A.base_ld, A.base_zz, A.base_info);
-    if (A.zbcast && zb) {  // communication expert: hand z_j to every local expert before publishing the task
+                     A.base_ld, A.base_zz, A.base_info, A.gt, A.ld_blk, A.zz_blk);
+    if (A.zbcast && zb && j < A.zbcast_gt) {  // communication expert: hand z_j to every local expert before publishing the task
         __syncthreads();
         if (threadIdx.x < TILE) {
             const double v = zb[j * TILE + threadIdx.x];
@@ -750,14 +766,16 @@ potrf_dataflow_kernel(const __grid_constant__ PotrfArgs A, const __grid_constant
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     __shared__ int s_col, s_local;
     Pipe pipe;
-    const int gc = A.gprog ? 1 : 0;  // communication expert in this launch (G): gt - col extra tasks lead every shared column
+    // communication expert in this launch (G): its own ntg - col tile tasks lead block column col (ntg >= gt block columns:
+    // one more than the shared gt when its size is not a multiple of 128)
+    const int ntg = A.gprog ? G.npad / TILE : 0;
     if (threadIdx.x == 0) {
         const int B = A.B, nt = A.npad / TILE, gt = A.gt;
         const int task = atomicAdd(A.ctl, 1);
         // tasks of block column `col`: B diagonal tasks (col >= gt only) then B * (number of rows below max(col, gt-1)) panel tiles
         int col = 0, col_start = 0;
         for (;;) {
-            const int ntask = col < gt ? gc * (gt - col) + B * (nt - gt) : B * (nt - col);
+            const int ntask = (col < ntg ? ntg - col : 0) + (col < gt ? B * (nt - gt) : B * (nt - col));
             if (task < col_start + ntask) break;
             col_start += ntask;
             ++col;
@@ -768,16 +786,16 @@ potrf_dataflow_kernel(const __grid_constant__ PotrfArgs A, const __grid_constant
     pipe_init(pipe, pipe_bars);  // ends with a CTA barrier
     const int col = s_col, nt = A.npad / TILE;
     int local = s_local;
-    if (col < A.gt && gc) {  // the communication expert's own tasks of this column: its diagonal tile, then its panel tiles
+    if (col < ntg) {  // the communication expert's own tasks of this column: its diagonal tile, then its panel tiles
         if (local == 0) {
             df_diag_task<GEN>(G, 0, col, 0u, pipe.bars);
             return;
         }
-        if (local < A.gt - col) {
+        if (local < ntg - col) {
             df_panel_task<GEN>(G, 0, col + local, col, 0u, pipe.bars);
             return;
         }
-        local -= A.gt - col;
+        local -= ntg - col;
     }
     if (col < A.gt) {  // shared block column: panel tiles of the rows below the shared block only
         const int per = nt - A.gt;
@@ -898,7 +916,7 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
             }
             int* ctl = reinterpret_cast<int*>(work);
             PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, ctl + 64,
-                        gt, Lg, npad_g, invdiag_g, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr};
+                        gt, Lg, npad_g, invdiag_g, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
             CUDA_TRY(cudaMemsetAsync(work, 0, 256 + (size_t)B * nt * 4, st));
             const int grid = (int)total;  // one CTA per tile task
             if (gen) {
@@ -1018,7 +1036,8 @@ extern "C" int gpr_potrf_batched_shared(double* L, const double* a, const double
 // hyper-parameters (see gpr_potrf_batched_shared; here the shared factor is produced by the same launch, so its serial chain
 // of ng/128 block columns overlaps the local experts' tiles instead of preceding them).
 extern "C" long long gpr_potrf_grbcm_work_bytes(int B, int npad, int npad_g) {
-    return 256 + align256((long long)B * (npad / TILE) * 4) + align256((long long)(npad_g / TILE) * 4);
+    return 256 + align256((long long)B * (npad / TILE) * 4) + align256((long long)(npad_g / TILE) * 4) +
+           2 * align256((long long)(npad_g / TILE) * 8);
 }
 
 extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
@@ -1029,10 +1048,12 @@ extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, co
     ARG_CHECK(L && a && nrm && hp && invdiag && y && z && logdet_half && zz && info && work);
     ARG_CHECK(Lg && a_g && nrm_g && hp_g && invdiag_g && y_g && z_g && logdet_half_g && zz_g && info_g);
     ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n && dpad > 0 && dpad % 4 == 0);
-    ARG_CHECK(ng > 0 && ng % TILE == 0 && ng < n && npad_g == ng);
+    ARG_CHECK(ng >= TILE && ng < n && npad_g % TILE == 0 && npad_g >= ng && npad_g - ng < TILE);
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt = npad / TILE, gt = ng / TILE;
-    const long long total = (long long)gt * (gt + 1) / 2 + (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
+    // gt whole 128-row blocks of the communication set are shared; a ragged last block of it is factorised by the communication
+    // expert for itself and, as part of their own rows, by every local expert
+    const int nt = npad / TILE, gt = ng / TILE, ntg = npad_g / TILE;
+    const long long total = (long long)ntg * (ntg + 1) / 2 + (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
     if (total >= (1LL << 30)) return fail(GPR_ERR_UNSUPPORTED, "too many tile tasks for one launch%s (%lld)", "", total);
     const int fb = feat_smem_bytes(dpad);
     if (TILE * XLD * 8 + fb > 227 * 1024)
@@ -1041,14 +1062,46 @@ extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, co
     if (TILE * XLD * 8 + fb > smem_df) smem_df = TILE * XLD * 8 + fb;
     int* ctl = reinterpret_cast<int*>(work);
     int* progress = ctl + 64;
-    int* gprog = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + 256 + align256((long long)B * nt * 4));
+    char* wp = reinterpret_cast<char*>(work) + 256 + align256((long long)B * nt * 4);
+    int* gprog = reinterpret_cast<int*>(wp);
+    double* ld_blk_g = reinterpret_cast<double*>(wp + align256((long long)ntg * 4));
+    double* zz_blk_g = ld_blk_g + align256((long long)ntg * 8) / 8;
     CUDA_TRY(cudaMemsetAsync(work, 0, (size_t)gpr_potrf_grbcm_work_bytes(B, npad, npad_g), st));
     PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, progress,
-                gt, Lg, npad_g, invdiag_g, gprog, nullptr, 0, 0, logdet_half_g, zz_g, info_g};
+                gt, Lg, npad_g, invdiag_g, gprog, nullptr, 0, 0, 0, ld_blk_g, zz_blk_g, info_g, nullptr, nullptr};
     PotrfArgs G{Lg, 1, npad_g, ng, a_g, nrm_g, hp_g, 0, diag_add_g, dpad, invdiag_g, y_g, z_g, logdet_half_g, zz_g, info_g, ctl, gprog,
-                0, nullptr, 0, nullptr, nullptr, z, B, npad, nullptr, nullptr, nullptr};
+                0, nullptr, 0, nullptr, nullptr, z, B, npad, gt, nullptr, nullptr, nullptr, ld_blk_g, zz_blk_g};
     CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<true>, smem_df));
     potrf_dataflow_kernel<true><<<(int)total, NTHREADS, smem_df, st>>>(A, G);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// sum_{i < rows} log L_ii and sum_{i < rows} z_i^2 of a finished factorisation: what gpr_potrf_batched_shared continues from when
+// only the first `rows` rows of the communication expert are shared (out[0], out[1]).
+__global__ void factor_partials_kernel(const double* __restrict__ L, int npad, const double* __restrict__ z, int rows, double* __restrict__ out) {
+    __shared__ double sl[NTHREADS / 32], sz[NTHREADS / 32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < rows; i += NTHREADS) {
+        a += log(L[(long long)i * npad + i]);
+        const double v = z[i];
+        b += v * v;
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = a; sz[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < NTHREADS / 32; ++w) { x += sl[w]; y += sz[w]; }
+        out[0] = x;
+        out[1] = y;
+    }
+}
+
+extern "C" int gpr_factor_partials(const double* L, int npad, const double* z, int rows, double* out, void* stream) {
+    ARG_CHECK(L && z && out && rows > 0 && rows <= npad);
+    factor_partials_kernel<<<1, NTHREADS, 0, (cudaStream_t)stream>>>(L, npad, z, rows, out);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }
@@ -2140,13 +2193,22 @@ vt_gemm_kernel(const double* __restrict__ Ks, const double* __restrict__ X, cons
 }
 
 __global__ void vt_finalize_kernel(const double* __restrict__ pv, const double* __restrict__ pm, const double* __restrict__ prior,
-                                   int nt, int mpad, int m, double* __restrict__ mean, double* __restrict__ var) {
+                                   int nt, int mpad, int m, double* __restrict__ mean, double* __restrict__ var, int gt_part,
+                                   double* __restrict__ mean_part, double* __restrict__ var_part) {
     const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     double sm = 0.0, sv = 0.0;
     for (int j = 0; j < nt; ++j) {
+        if (j == gt_part && mean_part) {  // the part of the sums that belongs to the first gt_part block rows (the shared ones)
+            mean_part[(long long)b * m + r] = sm;
+            var_part[(long long)b * m + r] = prior[b] - sv;
+        }
         sm += pm[((long long)b * nt + j) * mpad + r];
         sv += pv[((long long)b * nt + j) * mpad + r];
+    }
+    if (gt_part >= nt && mean_part) {
+        mean_part[(long long)b * m + r] = sm;
+        var_part[(long long)b * m + r] = prior[b] - sv;
     }
     mean[(long long)b * m + r] = sm;
     var[(long long)b * m + r] = prior[b] - sv;
@@ -2170,8 +2232,10 @@ extern "C" long long gpr_predict_gemm_scratch_bytes(int B, int npad, int dpad, i
 
 extern "C" int gpr_predict_gemm(const double* X, const double* a, const double* nrm, const double* z, const double* hp, int hp_stride,
                                 const double* prior, const double* xs, int B, int n, int npad, int d, int dpad, int m, double* mean,
-                                double* var, double* vt, void* scratch, void* stream) {
+                                double* var, double* vt, void* scratch, void* stream, int rows_part, double* mean_part,
+                                double* var_part) {
     ARG_CHECK(X && a && nrm && z && hp && prior && xs && mean && var && vt && scratch);
+    ARG_CHECK((!mean_part && !var_part) || (mean_part && var_part && rows_part > 0 && rows_part % TILE == 0 && rows_part <= npad));
     ARG_CHECK(B > 0 && n > 0 && m > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d);
     const int fsm = feat_smem_bytes(dpad);
     if (fsm > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused SE tile%s (dpad=%lld)", "", dpad);
@@ -2193,7 +2257,7 @@ extern "C" int gpr_predict_gemm(const double* X, const double* a, const double* 
                                                                     npad, (long long)mpad * npad, 1, 0, 0);
     CUDA_TRY(opt_in_smem(vt_gemm_kernel, MAIN_SMEM_BYTES));
     vt_gemm_kernel<<<dim3(nt, mpad / TILE, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(Ks, X, z, npad, mpad, vt, pv, pm);
-    vt_finalize_kernel<<<dim3((m + 127) / 128, B), 128, 0, st>>>(pv, pm, prior, nt, mpad, m, mean, var);
+    vt_finalize_kernel<<<dim3((m + 127) / 128, B), 128, 0, st>>>(pv, pm, prior, nt, mpad, m, mean, var, rows_part / TILE, mean_part, var_part);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }

@@ -162,8 +162,13 @@ def split_hp(hp: torch.Tensor, d: int, has_noise: bool, jitter: float = JITTER):
 def can_share(shared: Optional[FitState], n: int, d: int, has_noise: bool) -> bool:
     """Shape conditions for the shared leading block (the caller vouches that rows 0:ng of every expert are the
     communication set and that all hyper-parameter rows equal the communication expert's)."""
-    return (shared is not None and shared.B == 1 and shared.alpha is not None and shared.n % TILE == 0 and shared.n < n
+    return (shared is not None and shared.B == 1 and shared.alpha is not None and shared.n >= TILE and shared.n < n
             and shared.d == d and shared.has_noise == has_noise)
+
+
+def shared_rows(shared: FitState) -> int:
+    """Rows of the communication expert that are shared with the local experts: its whole 128-row blocks."""
+    return (shared.n // TILE) * TILE
 
 
 def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, want_alpha: bool = True,
@@ -197,11 +202,17 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     work = _work("potrf" + ws_tag, int(_lib.load().gpr_potrf_work_bytes(B, npad)), dev)   # ws_tag: a fit on another stream
     if shared is not None:
         assert can_share(shared, n, d, has_noise)
-        ng, gt = shared.n, shared.n // TILE
+        ng, gt = shared_rows(shared), shared.n // TILE
         z[:, :ng] = shared.z[0, :ng]                      # the forward solve, log-determinant and y^T K^-1 y continue
-        logdet_half[:] = shared.logdet_half[0]            # from the communication expert's values
-        zz[:] = shared.zz[0]
-        info[:] = shared.info[0]
+        if ng == shared.n:                                # from the communication expert's values (its first ng rows)
+            logdet_half[:] = shared.logdet_half[0]
+            zz[:] = shared.zz[0]
+        else:
+            part = torch.empty(2, dtype=F64, device=dev)
+            _lib.call("gpr_factor_partials", _p(shared.L), shared.npad, _p(shared.z), ng, _p(part), _stream())
+            logdet_half[:] = part[0]
+            zz[:] = part[1]
+        info[:] = torch.where((shared.info[0] > 0) & (shared.info[0] <= ng), shared.info[0], torch.zeros_like(shared.info[0]))
         _lib.call("gpr_potrf_batched_shared", _p(L), _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad,
                   _p(invdiag), _p(ypad), _p(z), _p(logdet_half), _p(zz), _p(info), _p(work), _stream(), ng,
                   _p(shared.L), shared.npad, _p(shared.invdiag))
@@ -235,9 +246,10 @@ def fit_grbcm(xg: torch.Tensor, yg: torch.Tensor, hp_g: torch.Tensor, x: torch.T
     columns runs under the local experts' tiles (gpr_potrf_grbcm).  Returns (st_g, st_l)."""
     B, n, d = x.shape
     ng = xg.shape[1]
-    assert xg.shape[0] == 1 and ng % TILE == 0 and ng < n and hp.shape == (B, d + 1 + int(has_noise)) and hp_g.shape[0] == 1
+    assert xg.shape[0] == 1 and ng >= TILE and ng < n and hp.shape == (B, d + 1 + int(has_noise)) and hp_g.shape[0] == 1
     dev = x.device
-    npad, gt = round_up(n, TILE), ng // TILE
+    npad, gt, ngp = round_up(n, TILE), ng // TILE, round_up(ng, TILE)
+    ngs = gt * TILE                                       # shared rows: the whole 128-row blocks of the communication set
     nt = npad // TILE
     lib = _lib.load()
 
@@ -246,32 +258,32 @@ def fit_grbcm(xg: torch.Tensor, yg: torch.Tensor, hp_g: torch.Tensor, x: torch.T
                 torch.empty(Bk, npk, dtype=F64, device=dev), torch.empty(Bk, dtype=F64, device=dev),
                 torch.empty(Bk, dtype=F64, device=dev), torch.empty(Bk, dtype=torch.int32, device=dev))
 
-    a_g, nrm_g = scale_inputs(xg, hp_g, 1, ng)
+    a_g, nrm_g = scale_inputs(xg, hp_g, 1, ngp)
     a, nrm = scale_inputs(x, hp, B, npad)
     dpad = a.shape[2]
     dadd_g, prior_g = split_hp(hp_g, d, has_noise, jitter)
     dadd, prior = split_hp(hp, d, has_noise, jitter)
-    Lg = torch.empty(1, ng, ng, dtype=F64, device=dev)
+    Lg = torch.empty(1, ngp, ngp, dtype=F64, device=dev)
     L = torch.empty(B, npad, npad, dtype=F64, device=dev) if L_out is None else L_out
-    inv_g, yp_g, z_g, ld_g, zz_g, info_g = buffers(1, ng, ng)
+    inv_g, yp_g, z_g, ld_g, zz_g, info_g = buffers(1, ng, ngp)
     inv, yp, z, ld, zz, info = buffers(B, n, npad)
     yp_g[:, :ng] = yg
     yp[:, :n] = y
-    work = _work("potrf_grbcm", int(lib.gpr_potrf_grbcm_work_bytes(B, npad, ng)), dev)
+    work = _work("potrf_grbcm", int(lib.gpr_potrf_grbcm_work_bytes(B, npad, ngp)), dev)
     _lib.call("gpr_potrf_grbcm", _p(L), _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(dadd), B, n, npad, dpad, _p(inv), _p(yp), _p(z),
-              _p(ld), _p(zz), _p(info), _p(Lg), _p(a_g), _p(nrm_g), _p(hp_g), _p(dadd_g), ng, ng, _p(inv_g), _p(yp_g), _p(z_g),
+              _p(ld), _p(zz), _p(info), _p(Lg), _p(a_g), _p(nrm_g), _p(hp_g), _p(dadd_g), ng, ngp, _p(inv_g), _p(yp_g), _p(z_g),
               _p(ld_g), _p(zz_g), _p(info_g), _p(work), _stream())
     # the leading block itself, for the kernels that walk a whole factor (backward solve, gradient, full covariance)
-    _lib.call("gpr_copy_leading_block", _p(L), B, npad, _p(Lg), ng, ng, 1, _stream())
-    inv[:, :gt] = inv_g[0]
+    _lib.call("gpr_copy_leading_block", _p(L), B, npad, _p(Lg), ngp, ngs, 1, _stream())
+    inv[:, :gt] = inv_g[0, :gt]
     _count(2)
-    alpha_g = torch.empty(1, ng, dtype=F64, device=dev)
+    alpha_g = torch.empty(1, ngp, dtype=F64, device=dev)
     alpha = torch.empty(B, npad, dtype=F64, device=dev)
-    for (Lk, ik, Bk, npk, zk, ak, tag) in ((Lg, inv_g, 1, ng, z_g, alpha_g, "_g"), (L, inv, B, npad, z, alpha, "")):
+    for (Lk, ik, Bk, npk, zk, ak, tag) in ((Lg, inv_g, 1, ngp, z_g, alpha_g, "_g"), (L, inv, B, npad, z, alpha, "")):
         twork = _work("trsv" + tag, int(lib.gpr_trsv_work_bytes(Bk)), dev)
         _lib.call("gpr_trsv_backward", _p(Lk), _p(ik), Bk, npk, _p(zk), _p(ak), _p(twork), _stream())
         _count(1)
-    st_g = FitState(1, ng, ng, d, dpad, has_noise, hp_g, a_g, nrm_g, Lg, inv_g, z_g, alpha_g, ld_g, zz_g, info_g, prior_g)
+    st_g = FitState(1, ng, ngp, d, dpad, has_noise, hp_g, a_g, nrm_g, Lg, inv_g, z_g, alpha_g, ld_g, zz_g, info_g, prior_g)
     st_l = FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, inv, z, alpha, ld, zz, info, prior, st_g)
     return st_g, st_l
 
@@ -343,7 +355,7 @@ def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind:
         vt = _work(scratch_kind + "_vt", st.B * mt * TILE * st.npad * 8, dev)
         scratch = _work(scratch_kind + "_gemm", int(lib.gpr_predict_gemm_scratch_bytes(st.B, st.npad, st.dpad, m)), dev)
         _lib.call("gpr_predict_gemm", _p(Linv), _p(st.a), _p(st.nrm), _p(st.z), _p(st.hp), st.hp.shape[-1], _p(st.prior), _p(xs),
-                  st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), _p(vt), _p(scratch), _stream())
+                  st.B, st.n, st.npad, st.d, st.dpad, m, _p(mean), _p(var), _p(vt), _p(scratch), _stream(), 0, None, None)
         _count(4)
         return mean, var
     scratch = _work(scratch_kind, int(_lib.load().gpr_predict_scratch_bytes(st.npad)), dev)
@@ -404,31 +416,32 @@ def tril_inverse(st: FitState) -> torch.Tensor:
 def predict_shared(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     """The two predictions of GRBCM.predict when the local experts were fitted on top of the communication expert's factor
     (fit(shared=st_g)): the communication expert's V_g^T = K*_g L_g^-T is kept and every local expert continues the
-    substitution from block row ng/128 (gpr_predict_keep + gpr_predict_shared).  Same return value as predict_pair."""
+    substitution from block row floor(ng/128) (gpr_predict_gemm + gpr_predict_shared).  Same return value as predict_pair."""
     assert st_l.shared_from is st_g and st_g.B == 1
     m = xs.shape[0]
     dev = xs.device
     lib = _lib.load()
     mt = (m + TILE - 1) // TILE
+    ngs = shared_rows(st_g)
     mg = torch.empty(1, m, dtype=F64, device=dev)
     vg = torch.empty(1, m, dtype=F64, device=dev)
+    # the same sums over the shared rows only (== mg, vg when the communication set is a whole number of blocks)
+    mg_s = mg if ngs == st_g.n else torch.empty(1, m, dtype=F64, device=dev)
+    vg_s = vg if ngs == st_g.n else torch.empty(1, m, dtype=F64, device=dev)
     vt = _work("predict_vt", mt * TILE * st_g.npad * 8, dev)
-    if st_g.Linv is not None:   # GEMM form: (m/128) x (ng/128) independent tiles instead of m/128 serial substitutions
-        scratch_g = _work("predict_gemm", int(lib.gpr_predict_gemm_scratch_bytes(1, st_g.npad, st_g.dpad, m)), dev)
-        _lib.call("gpr_predict_gemm", _p(st_g.Linv), _p(st_g.a), _p(st_g.nrm), _p(st_g.z), _p(st_g.hp), st_g.hp.shape[-1],
-                  _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt), _p(scratch_g), _stream())
-        _count(3)
-    else:
-        scratch_g = _work("predict_side", int(lib.gpr_predict_scratch_bytes(st_g.npad)), dev)
-        _lib.call("gpr_predict_keep", _p(st_g.L), _p(st_g.invdiag), _p(st_g.a), _p(st_g.nrm), _p(st_g.alpha), _p(st_g.hp),
-                  st_g.hp.shape[-1], _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt),
-                  _p(scratch_g), _stream())
+    # GEMM form: (m/128) x (ng/128) independent tiles instead of m/128 serial substitutions
+    Linv = tril_inverse(st_g)
+    scratch_g = _work("predict_gemm", int(lib.gpr_predict_gemm_scratch_bytes(1, st_g.npad, st_g.dpad, m)), dev)
+    _lib.call("gpr_predict_gemm", _p(Linv), _p(st_g.a), _p(st_g.nrm), _p(st_g.z), _p(st_g.hp), st_g.hp.shape[-1],
+              _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt), _p(scratch_g), _stream(),
+              ngs if ngs != st_g.n else 0, _p(mg_s) if ngs != st_g.n else None, _p(vg_s) if ngs != st_g.n else None)
+    _count(3)
     ml = torch.empty(st_l.B, m, dtype=F64, device=dev)
     vl = torch.empty(st_l.B, m, dtype=F64, device=dev)
     scratch = _work("predict", int(lib.gpr_predict_scratch_bytes(st_l.npad)), dev)
     _lib.call("gpr_predict_shared", _p(st_l.L), _p(st_l.invdiag), _p(st_l.a), _p(st_l.nrm), _p(st_l.z), _p(st_l.hp),
               st_l.hp.shape[-1], _p(xs), st_l.B, st_l.n, st_l.npad, st_l.d, st_l.dpad, m, _p(ml), _p(vl), _p(scratch), _stream(),
-              st_g.n, _p(vt), st_g.npad, _p(mg), _p(vg))
+              ngs, _p(vt), st_g.npad, _p(mg_s), _p(vg_s))
     _count(2)
     return (mg, vg), (ml, vl)
 
@@ -452,7 +465,7 @@ def lml_grad(st: FitState) -> torch.Tensor:
     nbytes = int(_lib.load().gpr_lml_grad_scratch_bytes(st.B, st.npad, st.d))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=st.L.device)
     sg = st.shared_from
-    if sg is not None and st.shared_upper and sg.Kinv is not None:
+    if sg is not None and st.shared_upper and sg.Kinv is not None and sg.n % TILE == 0:
         # shared leading block: neither L_g^-T nor K_g^-1 is recomputed per expert (gpr_lml_grad_shared)
         _lib.call("gpr_lml_grad_shared", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
                   int(st.has_noise), st.B, st.n, st.npad, st.d, st.dpad, _p(grad), _p(scratch), _stream(), sg.n, _p(sg.Kinv), sg.n)

@@ -135,12 +135,12 @@ class GRBCM(GPR):
 
     def _shares_hyperparameters(self) -> bool:
         """True when every local expert's hyper-parameter row equals the communication expert's vector (the GRBCM paper's
-        setting, and what GRBCM_MLE trains) and the communication set is tile aligned — the conditions of the shared
-        leading block (engine.fit(shared=...))."""
+        setting, and what GRBCM_MLE trains) and the communication set holds at least one 128-row block — the conditions of
+        the shared leading block (engine.fit(shared=...)); a ragged rest of the communication set is each expert's own."""
         g, l = self.gpg, self.gpl
         if os.environ.get("PYGPR_GRBCM_SHARE", "1") == "0":   # A/B knob: treat the experts as unrelated matrices
             return False
-        if fused_spec(g.cov) is None or self.ng % engine.TILE != 0 or self.nsc < 1:
+        if fused_spec(g.cov) is None or self.ng < engine.TILE or self.nsc < 1:
             return False
         pg = g.params.detach().reshape(-1)
         pl = l.params.detach().reshape(-1, l.params.shape[-1])
@@ -285,8 +285,8 @@ class GRBCM_MLE:
         # communication set) its factor is the leading block of every local expert's factor (engine.fit(shared=...))
         glob = MLE(g.gpg)
         st_g = glob._fit(theta, want_alpha=True)
-        share = st_g if (g.ng % engine.TILE == 0 and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
-        if share is not None and want_grad:
+        share = st_g if (g.ng >= engine.TILE and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
+        if share is not None and want_grad and g.ng % engine.TILE == 0:
             engine.kinv(st_g)      # K_g^-1 and L_g^-T once: the experts' gradients reuse both (gpr_lml_grad_shared)
         for s in range(0, g.nc, step):
             e = min(s + step, g.nc)
