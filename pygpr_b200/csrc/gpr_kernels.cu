@@ -559,7 +559,7 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
 // Waits are bounded (DF_SPIN_LIMIT polls): on a time-out the kernel raises the abort flag, every CTA drains, and
 // info[0] = -1 tells the host; the bound is a guard against a wedged GPU, not part of the protocol.
 // ---------------------------------------------------------------------------------------------
-constexpr long long DF_SPIN_LIMIT = 1LL << 22;
+constexpr long long DF_SPIN_LIMIT = 1LL << 25;   // ~30 s of polling: far beyond any legitimate wait, short of a wedged box
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -1879,7 +1879,10 @@ trtri_col_kernel(double* __restrict__ L, const double* __restrict__ invdiag, con
 static long long trtri_slot_tiles(int nt, int sms) { return 2LL * sms + nt; }
 static long long trtri_work_bytes(int B, int npad, int sms) {
     const int nt = npad / TILE;
-    return 256 + align256((long long)B * nt * 4) + (long long)B * trtri_slot_tiles(nt, sms) * TILE * TILE * 8;
+    // the split-K slots are only used by the column mode (few experts); the task mode needs the counter alone
+    // (255 experts of order 8192 would otherwise reserve 12 GB of slots beside 137 GB of factors)
+    const bool task_mode = (long long)B * (nt - 1) >= 2LL * sms;
+    return 256 + align256((long long)B * nt * 4) + (task_mode ? 0 : (long long)B * trtri_slot_tiles(nt, sms) * TILE * TILE * 8);
 }
 static int launch_trtri(double* L, const double* invdiag, const double* invdiagT, int B, int npad, void* work, cudaStream_t st,
                         int gt = 0) {
