@@ -340,9 +340,12 @@ def main():
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m * d * 8, "d2h_bytes_per_step": 2 * m * 8,
                     "ms_per_step": e2e_ms}}
     if grad_ms is not None:
-        gflops = nc_total * float(n_l) ** 3 * 2.0 / 3.0
+        gflops_unshared = nc_total * float(n_l) ** 3 * 2.0 / 3.0
+        gflops = nc_total * (float(n_l) ** 3 - float(n_g) ** 3) * 2.0 / 3.0 if shared else gflops_unshared
         line["lml_grad"] = {"ms": grad_ms, "tflops": gflops / grad_ms * 1e-9, "frac_of_peak": gflops / grad_ms * 1e-9 / (peak_tf * world),
-                            "what": "L^-T + fused K^-1/gradient reduction, 2N^3/3 per expert (Cholesky reported under fit)",
+                            "unshared_count_tflops": gflops_unshared / grad_ms * 1e-9,
+                            "what": "L^-T + fused K^-1/gradient reduction, 2N^3/3 per expert (Cholesky reported under fit), minus the "
+                                    "communication block's share (2 n_g^3/3 per expert) when one hyper-parameter vector is shared",
                             "cholesky_plus_grad_tflops": (gflops + fit_flops) / (grad_ms + fit_ms) * 1e-9}
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)

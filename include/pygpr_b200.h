@@ -142,8 +142,8 @@ long long gpr_potrf_grbcm_work_bytes(int B, int npad, int npad_g);
  * logdet_half / zz are pre-loaded with when only the first `rows` rows are shared. */
 int gpr_factor_partials(const double* L, int npad, const double* z, int rows, double* out, void* stream);
 
-/* L[b, 0:ng, 0:ng] = Lg[0:ng, 0:ng] for every expert b (tile granular; lower_only != 0 leaves the tiles above the block diagonal
- * alone) — the copy gpr_potrf_batched_shared / gpr_potrf_grbcm ask the caller for. */
+/* L[b, 0:ng, 0:ng] = Lg[0:ng, 0:ng] for every expert b (tile granular; lower_only: 0 all tiles, 1 tiles on / below the block
+ * diagonal, 2 tiles above it) — the copy gpr_potrf_batched_shared / gpr_potrf_grbcm ask the caller for. */
 int gpr_copy_leading_block(double* L, int B, int npad, const double* Lg, int npad_g, int ng, int lower_only, void* stream);
 
 /*

@@ -1111,7 +1111,8 @@ extern "C" int gpr_factor_partials(const double* L, int npad, const double* z, i
 __global__ void __launch_bounds__(NTHREADS) copy_blocks_kernel(const double* __restrict__ src, long long src_ld, double* __restrict__ dst,
                                                                long long dst_ld, long long dst_bstride, int lower_only) {
     const int tc = blockIdx.x, tr = blockIdx.y;
-    if (lower_only && tc > tr) return;
+    if (lower_only == 1 && tc > tr) return;   // 1: tiles on / below the block diagonal
+    if (lower_only == 2 && tc <= tr) return;  // 2: only the tiles above it (L_g^-T, fetched later for the shared-block gradient)
     const double* s = src + (long long)tr * TILE * src_ld + (long long)tc * TILE;
     double* d = dst + (long long)blockIdx.z * dst_bstride + (long long)tr * TILE * dst_ld + (long long)tc * TILE;
     for (int id = threadIdx.x; id < TILE * (TILE / 2); id += NTHREADS) {

@@ -465,6 +465,12 @@ def lml_grad(st: FitState) -> torch.Tensor:
     nbytes = int(_lib.load().gpr_lml_grad_scratch_bytes(st.B, st.npad, st.d))
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=st.L.device)
     sg = st.shared_from
+    if sg is not None and sg.n % TILE == 0 and not (st.shared_upper and sg.Kinv is not None):
+        # first gradient on a shared-block fit: form K_g^-1 / L_g^-T once and fetch L_g^-T into every expert's leading block
+        kinv(sg)
+        _lib.call("gpr_copy_leading_block", _p(st.L), st.B, st.npad, _p(sg.L), sg.npad, sg.n, 2, _stream())
+        _count(1)
+        st.shared_upper = True
     if sg is not None and st.shared_upper and sg.Kinv is not None and sg.n % TILE == 0:
         # shared leading block: neither L_g^-T nor K_g^-1 is recomputed per expert (gpr_lml_grad_shared)
         _lib.call("gpr_lml_grad_shared", _p(st.L), _p(st.invdiag), _p(st.a), _p(st.nrm), _p(st.alpha), _p(st.hp), st.hp.shape[-1],
