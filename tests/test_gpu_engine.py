@@ -203,3 +203,43 @@ def test_shared_block_fit_and_gradient(eng, orc, nc, nls, ng, d):
         loss_o, grad_o = orc.mle_loss_and_grad(SPEC, hp, x, y)
         assert_close(st.nlml().cpu().numpy(), loss_o.numpy(), TOL, "nlml vs reference")
         assert_close(g1.numpy(), grad_o.numpy(), TOL, "gradient vs reference")
+
+
+def test_vt_forms_agree(eng, orc):
+    """V^T = K* L^-T kept by the substitution (gpr_predict_keep) and produced by the triangular GEMM with L^-1
+    (gpr_predict_gemm) are the same matrix, and both give the reference's mean / variance; the GEMM form's partial sums over
+    the first whole blocks are the sums over those training rows."""
+    from pygpr_b200 import _lib
+    x, y, xs, hp = _data(17, 1, 500, 6, 150)
+    st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True)
+    m, mt = xs.shape[0], 2
+    xd = xs.cuda()
+    lib = _lib.load()
+    outs = []
+    for form in ("keep", "gemm"):
+        mean = torch.empty(1, m, dtype=torch.float64, device="cuda"); var = torch.empty_like(mean)
+        vt = torch.zeros(1, mt, 128, st.npad, dtype=torch.float64, device="cuda")
+        if form == "keep":
+            scratch = torch.empty(int(lib.gpr_predict_scratch_bytes(st.npad)), dtype=torch.uint8, device="cuda")
+            _lib.call("gpr_predict_keep", st.L.data_ptr(), st.invdiag.data_ptr(), st.a.data_ptr(), st.nrm.data_ptr(), st.alpha.data_ptr(),
+                      st.hp.data_ptr(), st.hp.shape[-1], st.prior.data_ptr(), xd.data_ptr(), 1, st.n, st.npad, st.d, st.dpad, m,
+                      mean.data_ptr(), var.data_ptr(), vt.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        else:
+            X = eng.tril_inverse(st)
+            mp = torch.empty_like(mean); vp = torch.empty_like(mean)
+            scratch = torch.empty(int(lib.gpr_predict_gemm_scratch_bytes(1, st.npad, st.dpad, m)), dtype=torch.uint8, device="cuda")
+            _lib.call("gpr_predict_gemm", X.data_ptr(), st.a.data_ptr(), st.nrm.data_ptr(), st.z.data_ptr(), st.hp.data_ptr(),
+                      st.hp.shape[-1], st.prior.data_ptr(), xd.data_ptr(), 1, st.n, st.npad, st.d, st.dpad, m, mean.data_ptr(),
+                      var.data_ptr(), vt.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream, 256,
+                      mp.data_ptr(), vp.data_ptr())
+        torch.cuda.synchronize()
+        outs.append((mean.cpu(), var.cpu(), vt.reshape(mt * 128, st.npad)[:m, :st.n].cpu()))
+    mean_ref, var_ref = orc.gp_predict(SPEC, hp, x, y, xs, "diag")
+    for mean, var, _ in outs:
+        assert_close(mean.numpy(), mean_ref.numpy(), TOL, "mean")
+        assert_close(var.numpy(), var_ref.numpy(), TOL, "var")
+    assert_close(outs[1][2].numpy(), outs[0][2].numpy(), 1e-10, "V^T (GEMM form) == V^T (substitution)")
+    V = outs[0][2]
+    z = st.z[0, :st.n].cpu()
+    assert_close(mp[0].cpu().numpy(), (V[:, :256] @ z[:256]).numpy(), 1e-10, "mean_part")
+    assert_close(vp[0].cpu().numpy(), (float(st.prior[0]) - (V[:, :256] ** 2).sum(-1)).numpy(), 1e-10, "var_part")
