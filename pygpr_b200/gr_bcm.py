@@ -56,8 +56,35 @@ class GRBCM(GPR):
         self.nsc = nls
         self.ng = ng
         self.dim = dim
-        self.beta = NotImplemented
-        self.prec = NotImplemented
+        self._weights = None
+        self._beta = NotImplemented
+        self._prec = NotImplemented
+
+    def _weight(self, k):
+        if self._weights is not None:
+            first, rows = self._weights[k]
+            return _back(torch.cat((first[None], rows)), self._weights[2])
+        return NotImplemented
+
+    @property
+    def beta(self):
+        if self._beta is None:
+            self._beta = self._weight(0)
+        return self._beta
+
+    @beta.setter
+    def beta(self, v):
+        self._beta = v
+
+    @property
+    def prec(self):
+        if self._prec is None:
+            self._prec = self._weight(1)
+        return self._prec
+
+    @prec.setter
+    def prec(self, v):
+        self._prec = v
 
     # ---------------------------------------------------------------------------------------------
     def aggregate(self, ys_g, covars_g, ys_l, covars_l, var="diag"):
@@ -73,8 +100,10 @@ class GRBCM(GPR):
         S, brow, prow = engine.grbcm_partial(mean_l, var_l, var_g, self.expert_offset, want_rows=True)
         gdist.all_reduce_sum_(S, self.group)                  # the only data-path collective: [3, m] doubles
         mu, v, b0, p0 = engine.grbcm_finalize(S, mean_g, var_g, want_rows=True)
-        self.beta = _back(torch.cat((b0[None], brow)), out_like)   # gr_bcm.py:135-136
-        self.prec = _back(torch.cat((p0[None], prow)), out_like)
+        # self.beta / self.prec (gr_bcm.py:135-136): kept on the device and moved to the callers' device on first read — a
+        # [nc+1, m] pair that most callers never look at should not cost a device->host copy per prediction
+        self._weights = ((b0, brow), (p0, prow), out_like)
+        self._beta = self._prec = None
         return _back(mu, out_like), _back(v, out_like)
 
     def _aggregate_full(self, ys_g, covars_g, ys_l, covars_l):
