@@ -311,6 +311,11 @@ def potrf_inplace(K: torch.Tensor, y: Optional[torch.Tensor] = None):
 _scratch_cache = {}
 
 
+def release_scratch() -> None:
+    """Drop the cached workspaces (they are grow-only; a long-lived process that once ran a huge case can hand them back)."""
+    _scratch_cache.clear()
+
+
 def _work(kind: str, nbytes: int, dev: torch.device) -> torch.Tensor:
     """Grow-only per-device workspace (the library never allocates; calls on one stream are ordered)."""
     key = (dev.index, kind)
