@@ -206,8 +206,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
+        # keep stdout to the one JSON line: NCCL writes its version banner (and anything NCCL_DEBUG asks for) to stdout
+        # unless it is given a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pygpr_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     import pygpr_b200 as P
