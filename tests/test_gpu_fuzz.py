@@ -16,3 +16,11 @@ def test_random_shapes_against_oracle(seed, form):
                          text=True, timeout=600, cwd=ROOT, env=dict(os.environ, PYGPR_PREDICT_FORM=form))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "fuzz_parity: ok" in res.stdout
+
+
+def test_repeated_runs_are_bit_identical():
+    """tools/determinism_check.py: fit + predict + gradient repeated (dataflow / two-stream Cholesky, column-owner solve, shared and
+    general paths) reproduce bit for bit — the library has no atomically-ordered sums, so any difference would be a race."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "determinism_check.py"), "6"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "determinism_check: ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
