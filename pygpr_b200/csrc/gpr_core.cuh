@@ -445,17 +445,35 @@ __device__ __forceinline__ void store_block8(const double (&R)[8][8], double* T,
         for (int c = 0; c < 8; c += 2)
             *reinterpret_cast<double2*>(T + (bi * 8 + r) * XLD + bj * 8 + c) = make_double2(R[r][c], R[r][c + 1]);
 }
-// R -= A * B^T (TRANS_B) or R -= A * B, A = T block (ai, aj), B = T block (bi, bj); two k at a time
+
+// Exchange buffer of the blocked routines: the 136 lower-triangular 8x8 blocks, block major, 66 doubles apart.  In the
+// row-major tile (stride 132 doubles) blocks that differ by a multiple of 8 rows sit on the same banks and the panel /
+// trailing phases ran 8- to 16-way conflicted (clock64 build: 2.8 k + 3.6 k clocks per block step for 288 + 512 DFMA); with
+// 528-byte block spacing consecutive block ids rotate through the eight 16-byte bank groups.
+constexpr int BLK_LD = 66;
+constexpr int BM_DOUBLES = 136 * BLK_LD;
+__device__ __forceinline__ int blk_id(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
+__device__ __forceinline__ void store_blk(const double (&R)[8][8], double* Bm, int bi, int bj) {
+    double* p = Bm + blk_id(bi, bj) * BLK_LD;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(p + r * 8 + c) = make_double2(R[r][c], R[r][c + 1]);
+}
+// R -= A * B^T (TRANS_B) or R -= A * B, A = block (ai, aj), B = block (bi, bj) of Bm; two k at a time
 template <bool TRANS_B>
-__device__ __forceinline__ void block8_mulsub(double (&R)[8][8], const double* T, int ai, int aj, int bi, int bj) {
+__device__ __forceinline__ void block8_mulsub(double (&R)[8][8], const double* Bm, int ai, int aj, int bi, int bj) {
+    const double* pa = Bm + blk_id(ai, aj) * BLK_LD;
+    const double* pb = Bm + blk_id(bi, bj) * BLK_LD;
 #pragma unroll
     for (int m = 0; m < 8; m += 2) {
-        double2 av[8], bv[8];
+        double2 av[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) av[r] = *reinterpret_cast<const double2*>(T + (ai * 8 + r) * XLD + aj * 8 + m);  // A[r][m..m+1]
+        for (int r = 0; r < 8; ++r) av[r] = *reinterpret_cast<const double2*>(pa + r * 8 + m);  // A[r][m..m+1]
         if (TRANS_B) {
+            double2 bv[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const double2*>(T + (bi * 8 + c) * XLD + bj * 8 + m);  // B[c][m..m+1]
+            for (int c = 0; c < 8; ++c) bv[c] = *reinterpret_cast<const double2*>(pb + c * 8 + m);  // B[c][m..m+1]
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -464,8 +482,8 @@ __device__ __forceinline__ void block8_mulsub(double (&R)[8][8], const double* T
             double2 b0[4], b1[4];  // B[m][0..7], B[m+1][0..7]
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                b0[c] = *reinterpret_cast<const double2*>(T + (bi * 8 + m) * XLD + bj * 8 + 2 * c);
-                b1[c] = *reinterpret_cast<const double2*>(T + (bi * 8 + m + 1) * XLD + bj * 8 + 2 * c);
+                b0[c] = *reinterpret_cast<const double2*>(pb + m * 8 + 2 * c);
+                b1[c] = *reinterpret_cast<const double2*>(pb + (m + 1) * 8 + 2 * c);
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -474,14 +492,14 @@ __device__ __forceinline__ void block8_mulsub(double (&R)[8][8], const double* T
                     R[r][2 * c] -= av[r].x * b0[c].x + av[r].y * b1[c].x;
                     R[r][2 * c + 1] -= av[r].x * b0[c].y + av[r].y * b1[c].y;
                 }
-            (void)bv;
         }
     }
 }
 
 // T: symmetric tile (lower part used) -> L in the lower triangle (strict upper of the diagonal 8x8 blocks zeroed; blocks above
-// the block diagonal untouched).  invblk: 16 x 64 doubles.  *fail as potf2_reg.
-__device__ __forceinline__ void potf2_blk(double* T, double* invblk, int* fail, DiagBlock& d) {
+// the block diagonal untouched).  Bm: BM_DOUBLES of scratch, left holding every strictly-lower block of L for trtri_blk.
+// invblk: 16 x 64 doubles.  *fail = first 1-based column with a non-positive pivot (unchanged if none).
+__device__ __forceinline__ void potf2_blk(double* T, double* Bm, double* invblk, int* fail, DiagBlock& d) {
     const bool live = d.bi >= 0;
     if (live) load_block8(d.R, T, d.bi, d.bj);
 #pragma unroll 1
@@ -494,7 +512,6 @@ __device__ __forceinline__ void potf2_blk(double* T, double* invblk, int* fail, 
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int c = r + 1; c < 8; ++c) d.R[r][c] = 0.0;
-            store_block8(d.R, T, kb, kb);
             // Y = inv(L_kk), column by column: Y[c][c] = 1/L[c][c], Y[r][c] = -(sum_{c<=m<r} L[r][m] Y[m][c]) / L[r][r]
             double* Y = invblk + kb * 64;
 #pragma unroll
@@ -532,17 +549,18 @@ __device__ __forceinline__ void potf2_blk(double* T, double* invblk, int* fail, 
                     d.R[r][c] = s;
                 }
             }
-            store_block8(d.R, T, d.bi, kb);
+            store_blk(d.R, Bm, d.bi, kb);
         }
         __syncthreads();
-        if (live && d.bj > kb) block8_mulsub<true>(d.R, T, d.bi, kb, d.bj, kb);  // trailing: R -= L[bi,kb] L[bj,kb]^T
+        if (live && d.bj > kb) block8_mulsub<true>(d.R, Bm, d.bi, kb, d.bj, kb);  // trailing: R -= L[bi,kb] L[bj,kb]^T
     }
+    if (live) store_block8(d.R, T, d.bi, d.bj);  // every thread holds its final block of L
     __syncthreads();
 }
 
-// X = L^-1 in place (T lower = L from potf2_blk, invblk = its diagonal-block inverses).  On return T holds X in the lower
-// triangle and zeros above it.
-__device__ __forceinline__ void trtri_blk(double* T, const double* invblk, DiagBlock& d) {
+// X = L^-1 (Bm = the strictly-lower blocks of L from potf2_blk, invblk = its diagonal-block inverses).  On return T holds X in
+// the lower triangle and zeros above it.
+__device__ __forceinline__ void trtri_blk(double* T, double* Bm, const double* invblk, DiagBlock& d) {
     const bool live = d.bi >= 0;
     for (int id = threadIdx.x; id < TILE * TILE; id += NTHREADS) {  // blocks above the block diagonal
         const int r = id >> 7, c = id & 127;
@@ -571,12 +589,14 @@ __device__ __forceinline__ void trtri_blk(double* T, const double* invblk, DiagB
                     d.R[r][c] = s;
                 }
             }
-            store_block8(d.R, T, kb, d.bj);
+            store_blk(d.R, Bm, kb, d.bj);  // over L[kb, bj], which was last read at block step bj < kb
         }
         __syncthreads();
-        if (live && d.bi > kb && d.bj <= kb) block8_mulsub<false>(d.R, T, d.bi, kb, kb, d.bj);  // R -= L[bi,kb] X[kb,bj]
+        if (live && d.bi > kb && d.bj <= kb) block8_mulsub<false>(d.R, Bm, d.bi, kb, kb, d.bj);  // R -= L[bi,kb] X[kb,bj]
         __syncthreads();  // row kb+1 is overwritten next; its L blocks were just read by the whole row
     }
+    if (live) store_block8(d.R, T, d.bi, d.bj);  // final X blocks (diagonal blocks carry their zeros above the diagonal)
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------

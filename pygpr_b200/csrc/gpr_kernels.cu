@@ -114,6 +114,13 @@ __device__ __forceinline__ FeatSmem carve_feat(double* base, int dpad) {
     return f;
 }
 static inline int feat_smem_bytes(int dpad) { return (2 * TILE * feat_sld(dpad) + 2 * TILE) * 8; }
+// dynamic shared memory of a kernel that factorises diagonal tiles: the pipeline stages, overlaid by the 128x128 tile, and
+// behind the tile the larger of the feature tiles (GEN) and the block-major exchange buffer of potf2_blk / trtri_blk
+static inline int diag_smem_bytes(int gen, int dpad) {
+    const int behind = (gen && feat_smem_bytes(dpad) > BM_DOUBLES * 8) ? feat_smem_bytes(dpad) : BM_DOUBLES * 8;
+    const int need = TILE * XLD * 8 + behind;
+    return need > MAIN_SMEM_BYTES ? need : MAIN_SMEM_BYTES;
+}
 
 // rows from (aR, nrmR) tile tr, cols from (aC, nrmC) tile tc; out[b][row][col] with leading dim ld.
 //   mode 0 (symmetric build): diag_add on row==col, identity padding up to `ldlim` when pad_identity
@@ -342,7 +349,8 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
     DiagBlock blk;
     diag_block_coords(blk);
     __shared__ double invblk[(TILE / 8) * 64];
-    potf2_blk(T, invblk, s_fail, blk);
+    double* Bm = smem + TILE * XLD;  // block-major exchange buffer, behind the tile (the GEN feature tiles there are spent)
+    potf2_blk(T, Bm, invblk, s_fail, blk);
 
     // write L_jj (strict upper zeroed) and accumulate sum log L_ii
     for (int id = tid; id < TILE * TILE; id += NTHREADS) {
@@ -366,7 +374,7 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             }
         }
     }
-    trtri_blk(T, invblk, blk);
+    trtri_blk(T, Bm, invblk, blk);
     double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
     for (int id = tid; id < TILE * TILE; id += NTHREADS) inv[id] = T[(id >> 7) * XLD + (id & 127)];
     if (y) {
@@ -907,13 +915,9 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
             dataflow = true;
         }
         if (dataflow) {
-            int smem_df = MAIN_SMEM_BYTES;
-            if (gen) {
-                const int fb = feat_smem_bytes(dpad);
-                if (TILE * XLD * 8 + fb > 227 * 1024)
-                    return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
-                if (TILE * XLD * 8 + fb > smem_df) smem_df = TILE * XLD * 8 + fb;
-            }
+            const int smem_df = diag_smem_bytes(gen, dpad);
+            if (smem_df > 226 * 1024)
+                return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
             int* ctl = reinterpret_cast<int*>(work);
             PotrfArgs A{L, B, npad, n, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, z, logdet_half, zz, info, ctl, ctl + 64,
                         gt, Lg, npad_g, invdiag_g, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -930,12 +934,11 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
             return GPR_OK;
         }
     }
-    int smem_diag = MAIN_SMEM_BYTES, smem_panel = MAIN_SMEM_BYTES;
+    int smem_diag = diag_smem_bytes(gen, dpad), smem_panel = MAIN_SMEM_BYTES;
+    if (smem_diag > 226 * 1024)
+        return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
     if (gen) {
         const int fb = feat_smem_bytes(dpad);
-        if (TILE * XLD * 8 + fb > 227 * 1024)
-            return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
-        if (TILE * XLD * 8 + fb > smem_diag) smem_diag = TILE * XLD * 8 + fb;
         if (fb > smem_panel) smem_panel = fb;
         CUDA_TRY(opt_in_smem(potrf_diag_kernel<true>, smem_diag));
         CUDA_TRY(opt_in_smem(potrf_panel_kernel<true>, smem_panel));
@@ -1055,11 +1058,9 @@ extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, co
     const int nt = npad / TILE, gt = ng / TILE, ntg = npad_g / TILE;
     const long long total = (long long)ntg * (ntg + 1) / 2 + (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
     if (total >= (1LL << 30)) return fail(GPR_ERR_UNSUPPORTED, "too many tile tasks for one launch%s (%lld)", "", total);
-    const int fb = feat_smem_bytes(dpad);
-    if (TILE * XLD * 8 + fb > 227 * 1024)
+    const int smem_df = diag_smem_bytes(1, dpad);
+    if (smem_df > 226 * 1024)
         return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused factorisation%s (dpad=%lld)", "", dpad);
-    int smem_df = MAIN_SMEM_BYTES;
-    if (TILE * XLD * 8 + fb > smem_df) smem_df = TILE * XLD * 8 + fb;
     int* ctl = reinterpret_cast<int*>(work);
     int* progress = ctl + 64;
     char* wp = reinterpret_cast<char*>(work) + 256 + align256((long long)B * nt * 4);
