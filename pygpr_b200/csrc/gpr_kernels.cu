@@ -254,6 +254,42 @@ extern "C" int gpr_se_kernel_grad(const double* Kse, const double* x, const doub
 // 128-deep block is computed one launch earlier by an extra CTA per expert inside the (wide) panel launch of column
 // j-1 and parked in the unused upper block (j-1, j) of L; the diagonal kernel then costs O(1) tiles, not O(j).
 // ---------------------------------------------------------------------------------------------
+// ---- inter-CTA progress flags (release / acquire at GPU scope; bounded polling as a hang guard) ----------------------------
+constexpr long long DF_SPIN_LIMIT = 1LL << 25;   // ~30 s of polling: far beyond any legitimate wait, short of a wedged box
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// All threads call.  Thread 0 polls, the CTA barrier hands its acquire to everyone.  false = aborted.
+__device__ __forceinline__ bool df_wait(const int* flag, int need, int* abort_flag, int* info, int* s_ok) {
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        if (ld_acquire_gpu(flag) < need) {
+            long long spins = 0;
+            for (;;) {
+                __nanosleep(100);
+                if (ld_acquire_gpu(flag) >= need) break;
+                if (++spins > DF_SPIN_LIMIT || *reinterpret_cast<volatile int*>(abort_flag)) {
+                    atomicExch(abort_flag, 1);
+                    if (info) __stcg(info, -1);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        *s_ok = ok;
+    }
+    __syncthreads();
+    const bool ok = *s_ok != 0;
+    __syncthreads();  // *s_ok is rewritten by the next wait
+    return ok;
+}
+
 struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-warp per row, 8 rows per half-warp
     const double* z;
     double zk;
@@ -411,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
                   const double* __restrict__ hp, int hp_stride, const double* __restrict__ diag_add, int dpad,
                   double* __restrict__ invdiag, const double* __restrict__ y, double* __restrict__ z,
-                  double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info) {
+                  double* __restrict__ logdet_half, double* __restrict__ zz, int* __restrict__ info, int* __restrict__ done_flag) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -438,6 +474,11 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
 
     diag_finish<GEN>(acc, smem, pub, svec, &s_fail, Lb, b, j, n, npad, a, nrm, hp, hp_stride, diag_add, dpad, invdiag, y, zb,
                      logdet_half, zz, info, have_part ? dpart : nullptr);
+    if (done_flag) {  // the first panel tile of this column runs concurrently and waits for inv(L_jj) only before its solve
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(done_flag + b, j + 1);
+    }
 }
 
 // grid.x = (nt-1-j) row tiles, plus one look-ahead CTA per expert when lookahead != 0 (j >= 1, j+1 < nt):
@@ -448,7 +489,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double* __restrict__ a, const double* __restrict__ nrm,
                    const double* __restrict__ hp, int hp_stride, int dpad, const double* __restrict__ invdiag, int lookahead,
                    double* __restrict__ z, int S, double* __restrict__ sk_slots, double* __restrict__ sk_gemv,
-                   int* __restrict__ sk_counters, int row0) {
+                   int* __restrict__ sk_counters, int row0, int* __restrict__ diag_flag) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     __shared__ int s_flag;
@@ -540,6 +581,9 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
     }
     __threadfence_block();
     __syncthreads();
+    if (diag_flag) {  // launched alongside the diagonal-tile kernel of this column: inv(L_jj) is the only thing it owes us
+        if (!df_wait(diag_flag + b, j + 1, diag_flag - 1, nullptr, &s_flag)) return;
+    }
 
     // triangular solve as a product with the inverted diagonal block:  L_ij = Xhat * inv(L_jj)^T
     zero_acc(acc);
@@ -567,41 +611,6 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
 // Waits are bounded (DF_SPIN_LIMIT polls): on a time-out the kernel raises the abort flag, every CTA drains, and
 // info[0] = -1 tells the host; the bound is a guard against a wedged GPU, not part of the protocol.
 // ---------------------------------------------------------------------------------------------
-constexpr long long DF_SPIN_LIMIT = 1LL << 25;   // ~30 s of polling: far beyond any legitimate wait, short of a wedged box
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// All threads call.  Thread 0 polls, the CTA barrier hands its acquire to everyone.  false = aborted.
-__device__ __forceinline__ bool df_wait(const int* flag, int need, int* abort_flag, int* info, int* s_ok) {
-    if (threadIdx.x == 0) {
-        int ok = 1;
-        if (ld_acquire_gpu(flag) < need) {
-            long long spins = 0;
-            for (;;) {
-                __nanosleep(100);
-                if (ld_acquire_gpu(flag) >= need) break;
-                if (++spins > DF_SPIN_LIMIT || *reinterpret_cast<volatile int*>(abort_flag)) {
-                    atomicExch(abort_flag, 1);
-                    if (info) __stcg(info, -1);
-                    ok = 0;
-                    break;
-                }
-            }
-        }
-        *s_ok = ok;
-    }
-    __syncthreads();
-    const bool ok = *s_ok != 0;
-    __syncthreads();  // *s_ok is rewritten by the next wait
-    return ok;
-}
-
 struct PotrfArgs {
     double* L;
     int B, npad, n;
@@ -847,13 +856,15 @@ extern "C" long long gpr_potrf_work_bytes(int B, int npad) {
     if (sms <= 0) sms = 148;
     const int nt = npad / TILE;
     return 256 + align256((long long)B * nt * 4) + align256((long long)B * 32 * TILE * 8) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8 +
-           align256((long long)B * nt * 4) + potrf_chain_slot_tiles(sms) * TILE * TILE * 8;   // + the chain launches' own counters / slots
+           align256((long long)B * nt * 4) + potrf_chain_slot_tiles(sms) * TILE * TILE * 8 +   // + the chain launches' own counters / slots
+           align256((long long)(B + 1) * 4);                                                  // + abort flag and per-expert "diagonal tile done"
 }
 
 // Internal streams / events of the two-stream per-column schedule (created once per device; no device memory)
 struct PotrfAux {
-    cudaStream_t chain = nullptr, bulk = nullptr;
-    cudaEvent_t fork = nullptr, join_chain = nullptr, join_bulk = nullptr, diag[4] = {}, bulk_done[4] = {};
+    cudaStream_t chain = nullptr, chain2 = nullptr, bulk = nullptr;
+    cudaEvent_t fork = nullptr, join_chain = nullptr, join_chain2 = nullptr, join_bulk = nullptr, diag[4] = {}, bulk_done[4] = {},
+                first_done[4] = {};
     bool ready = false;
 };
 static PotrfAux g_potrf_aux[64];
@@ -867,9 +878,11 @@ static PotrfAux* potrf_aux() {
         int lo = 0, hi = 0;
         if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithPriority(&x.chain, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;   // hi = highest priority
+        if (cudaStreamCreateWithPriority(&x.chain2, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithPriority(&x.bulk, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
-        cudaEvent_t* evs[] = {&x.fork, &x.join_chain, &x.join_bulk, &x.diag[0], &x.diag[1], &x.diag[2], &x.diag[3],
-                              &x.bulk_done[0], &x.bulk_done[1], &x.bulk_done[2], &x.bulk_done[3]};
+        cudaEvent_t* evs[] = {&x.fork, &x.join_chain, &x.join_chain2, &x.join_bulk, &x.diag[0], &x.diag[1], &x.diag[2], &x.diag[3],
+                              &x.bulk_done[0], &x.bulk_done[1], &x.bulk_done[2], &x.bulk_done[3],
+                              &x.first_done[0], &x.first_done[1], &x.first_done[2], &x.first_done[3]};
         for (cudaEvent_t* e : evs)
             if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         x.ready = true;
@@ -905,9 +918,8 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         const char* mode = getenv("PYGPR_POTRF_MODE");
         const long long total = (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
         // measured on B200 (tools/potrf_modes.py): dataflow wins from ~8 experts up (+8 % at B=32..63), ties at 4, loses below
-        // (two-stream per-column form: B=1 n=16384 61 ms vs 146 ms dataflow); up to 16 block columns the single launch also wins
-        // for few experts (B=1 n=1024: 1.58 vs 1.83 ms, B=3 n=2048: 3.39 vs 3.90 ms) because launch latencies dominate there
-        bool dataflow = work && nt >= 2 && (B >= 6 || nt <= 16) && total < (1LL << 30);
+        // (three-stream per-column form: B=1 n=16384 59 ms vs 145 ms dataflow, B=3 n=2048 2.6 vs 3.1 ms, B=1 n=1024 a tie)
+        bool dataflow = work && nt >= 2 && B >= 6 && total < (1LL << 30);
         if (mode && !strncmp(mode, "columns", 7)) dataflow = false;
         if (mode && !strcmp(mode, "dataflow") && work && total < (1LL << 30)) dataflow = true;
         if (gt > 0) {  // the shared leading block exists in the dataflow form only
@@ -946,15 +958,18 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         CUDA_TRY(opt_in_smem(potrf_diag_kernel<false>, smem_diag));
         CUDA_TRY(opt_in_smem(potrf_panel_kernel<false>, smem_panel));
     }
-    // Per-column schedule.  With a workspace it runs on two internal streams: the CHAIN  diag(j) -> [tile (j+1, j) + look-ahead
-    // product] -> diag(j+1) -> ...  (few CTAs, latency bound: the register-resident potf2/trti2 is ~0.1 ms per column) on a
-    // high-priority stream, and the BULK of each panel (row tiles j+2 ...) on a low-priority one that only needs diag(j); the
-    // chain of column j+1 needs the bulk of column j-1... so a column costs max(bulk, chain) instead of their sum
-    // (n = 16384, one matrix: 79 -> 61 ms; 4 x 8192: 40 -> 32 ms).  PYGPR_POTRF_MODE=columns1 keeps everything on the caller's stream.
+    // Per-column schedule.  With a workspace it runs on three internal streams: the diagonal tiles (latency bound: the
+    // register-resident potf2/trti2 is ~70 us per column) and the FIRST panel tile + look-ahead product of each column on two
+    // high-priority streams — the first tile's partial products run alongside the diagonal tile of its own column and only its
+    // solve waits, on a flag, for inv(L_jj) — and the BULK of each panel (row tiles j+2 ...) on a low-priority one that only
+    // needs diag(j).  A column then costs max(bulk, diag + solve) instead of diag + first tile + bulk
+    // (one matrix: n = 4096 8.4 -> 5.3 ms, 8192 22 -> 14.5, 16384 79 -> 59; 4 x 8192: 40 -> 30).
+    // PYGPR_POTRF_MODE=columns1 keeps everything on the caller's stream.
     const char* mode1 = getenv("PYGPR_POTRF_MODE");
     PotrfAux* aux = (work && nt >= 3 && !(mode1 && !strcmp(mode1, "columns1"))) ? potrf_aux() : nullptr;
     int* counters_c = nullptr;
     double* slots_c = nullptr;
+    int* dflags = nullptr;  // [0] abort, [1 + b] = number of diagonal tiles of expert b finished
     // the internal streams and events are per device: one factorisation at a time may be ENQUEUED through them
     std::unique_lock<std::mutex> enqueue_lock(g_potrf_enqueue_mutex, std::defer_lock);
     if (aux) enqueue_lock.lock();
@@ -962,56 +977,66 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         char* p = reinterpret_cast<char*>(slots) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
         counters_c = reinterpret_cast<int*>(p);
         slots_c = reinterpret_cast<double*>(p + align256((long long)B * nt * 4));
+        dflags = reinterpret_cast<int*>(reinterpret_cast<char*>(slots_c) + potrf_chain_slot_tiles(sms) * TILE * TILE * 8);
         CUDA_TRY(cudaMemsetAsync(counters_c, 0, (size_t)B * nt * 4, st));
+        CUDA_TRY(cudaMemsetAsync(dflags, 0, (size_t)(B + 1) * 4, st));
         CUDA_TRY(cudaEventRecord(aux->fork, st));
         CUDA_TRY(cudaStreamWaitEvent(aux->chain, aux->fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(aux->chain2, aux->fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(aux->bulk, aux->fork, 0));
     }
-    cudaStream_t sc = aux ? aux->chain : st, sb = aux ? aux->bulk : st;
-    auto launch_panel = [&](cudaStream_t s_, int j, int row0, int ntile_rows, int lookahead, int S, double* sl, int* cnt) {
+    // sd: diagonal tiles; sf: first panel tile + look-ahead product (runs ALONGSIDE the diagonal tile of its column: only its
+    // solve waits, on a flag, for inv(L_jj)); sb: the bulk of the panel
+    cudaStream_t sd = aux ? aux->chain : st, sf = aux ? aux->chain2 : st, sb = aux ? aux->bulk : st;
+    auto launch_panel = [&](cudaStream_t s_, int j, int row0, int ntile_rows, int lookahead, int S, double* sl, int* cnt, int* dflag) {
         dim3 grid((ntile_rows + lookahead) * S, B);
         if (gen)
             potrf_panel_kernel<true><<<grid, NTHREADS, smem_panel, s_>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag, lookahead,
-                                                                         y ? z : nullptr, S, sl, gemv, cnt, row0);
+                                                                         y ? z : nullptr, S, sl, gemv, cnt, row0, dflag);
         else
             potrf_panel_kernel<false><<<grid, NTHREADS, smem_panel, s_>>>(L, npad, n, j, a, nrm, hp, hp_stride, dpad, invdiag, lookahead,
-                                                                          y ? z : nullptr, S, sl, gemv, cnt, row0);
+                                                                          y ? z : nullptr, S, sl, gemv, cnt, row0, dflag);
     };
     bool bulk_prev = false;  // column j-1 had a bulk launch
     for (int j = 0; j < nt; ++j) {
+        if (aux && j >= 1) CUDA_TRY(cudaStreamWaitEvent(sd, aux->first_done[(j - 1) & 3], 0));   // tile (j, j-1) and the look-ahead sums
+        int* dflag = aux ? dflags + 1 : nullptr;
         if (gen)
-            potrf_diag_kernel<true><<<B, NTHREADS, smem_diag, sc>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad, invdiag,
-                                                                     y, z, logdet_half, zz, info);
+            potrf_diag_kernel<true><<<B, NTHREADS, smem_diag, sd>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad, invdiag,
+                                                                     y, z, logdet_half, zz, info, dflag);
         else
-            potrf_diag_kernel<false><<<B, NTHREADS, smem_diag, sc>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad,
-                                                                      invdiag, y, z, logdet_half, zz, info);
+            potrf_diag_kernel<false><<<B, NTHREADS, smem_diag, sd>>>(L, npad, n, j, a, nrm, hp, hp_stride, diag_add, dpad,
+                                                                      invdiag, y, z, logdet_half, zz, info, dflag);
         if (j + 1 >= nt) break;
         const int lookahead = (j >= 1) ? 1 : 0;
         if (!aux) {
             const int ntile_x = nt - 1 - j + lookahead;
             const int S = work ? choose_split((long long)B * ntile_x, j, sms, potrf_slot_tiles(B, nt, sms)) : 1;
-            launch_panel(st, j, 0, nt - 1 - j, lookahead, S, slots, counters);
+            launch_panel(st, j, 0, nt - 1 - j, lookahead, S, slots, counters, nullptr);
             continue;
         }
         const int rows_bulk = nt - 2 - j;
-        CUDA_TRY(cudaEventRecord(aux->diag[j & 3], sc));
+        CUDA_TRY(cudaEventRecord(aux->diag[j & 3], sd));
         if (rows_bulk > 0) {
             CUDA_TRY(cudaStreamWaitEvent(sb, aux->diag[j & 3], 0));
             const int S = choose_split((long long)B * rows_bulk, j, sms, potrf_slot_tiles(B, nt, sms));
-            launch_panel(sb, j, 1, rows_bulk, 0, S, slots, counters);
+            launch_panel(sb, j, 1, rows_bulk, 0, S, slots, counters, nullptr);
             CUDA_TRY(cudaEventRecord(aux->bulk_done[j & 3], sb));
         }
-        if (bulk_prev) CUDA_TRY(cudaStreamWaitEvent(sc, aux->bulk_done[(j - 1) & 3], 0));   // row j+1 of column j-1
+        if (bulk_prev) CUDA_TRY(cudaStreamWaitEvent(sf, aux->bulk_done[(j - 1) & 3], 0));   // row j+1 of column j-1
         {
             const int S = choose_split((long long)B * (1 + lookahead), j, sms, potrf_chain_slot_tiles(sms));
-            launch_panel(sc, j, 0, 1, lookahead, S, slots_c, counters_c);
+            launch_panel(sf, j, 0, 1, lookahead, S, slots_c, counters_c, dflag);
+            CUDA_TRY(cudaEventRecord(aux->first_done[j & 3], sf));
         }
         bulk_prev = rows_bulk > 0;
     }
     if (aux) {
-        CUDA_TRY(cudaEventRecord(aux->join_chain, sc));
+        CUDA_TRY(cudaEventRecord(aux->join_chain, sd));
+        CUDA_TRY(cudaEventRecord(aux->join_chain2, sf));
         CUDA_TRY(cudaEventRecord(aux->join_bulk, sb));
         CUDA_TRY(cudaStreamWaitEvent(st, aux->join_chain, 0));
+        CUDA_TRY(cudaStreamWaitEvent(st, aux->join_chain2, 0));
         CUDA_TRY(cudaStreamWaitEvent(st, aux->join_bulk, 0));
     }
     CUDA_TRY(cudaGetLastError());
