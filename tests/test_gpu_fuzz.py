@@ -24,3 +24,11 @@ def test_repeated_runs_are_bit_identical():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "determinism_check.py"), "6"], capture_output=True, text=True,
                          timeout=600, cwd=ROOT)
     assert res.returncode == 0 and "determinism_check: ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_random_spd_matrices_all_schedules():
+    """tools/fuzz_potrf.py: in-place factorisation + inverse of random SPD batches (ragged orders, 1..12 matrices) under every
+    schedule of the Cholesky against torch.linalg on the same GPU."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_potrf.py"), "3", "8"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and "fuzz_potrf: ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
