@@ -272,6 +272,21 @@ int gpr_potri_batched(double* L, const double* invdiag, int B, int n, int npad, 
 /* prec[i,j] = sum_c Kinv[c,i,j] * (beta[c,i] + beta[c,j]) / 2      GRBCM.aggregate_full_covar gr_bcm.py:105-111 */
 int grbcm_full_combine(const double* Kinv, const double* beta, int nc1, int m, double* prec, void* stream);
 
+/* ---- dense path: model-level support for ANY Covar composition (covar.py:28-81), kernel matrices materialised ---------------- */
+/*
+ * V^T = Ks X^T with X = L^-1 (gpr_tril_inverse) for materialised cross-covariances Ks [B, mpad, npad] (zero padded,
+ * mpad = ceil(m/128)*128):  mean = V^T z = Ks alpha (gpr.py:79-85), var = prior_b - |V|^2 (gpr.py:96-106), vt [B, mpad, npad].
+ */
+int gpr_predict_dense(const double* X, const double* Ks, const double* z, const double* prior, int B, int npad, int m,
+                      double* mean, double* var, double* vt, void* scratch, void* stream);
+long long gpr_predict_dense_scratch_bytes(int B, int npad, int m);
+/* cov[b] = Kss[b] - V^T V   (gpr.py:108-120), Kss [B, m, m] materialised, vt from gpr_predict_dense */
+int gpr_covar_dense(const double* vt, const double* Kss, int B, int npad, int m, double* cov, void* stream);
+/* grad[b,p] = 1/2 sum_ij (Kinv[b] - alpha_b alpha_b^T)_ij dK[b,p,i,j]   (loss.py:77-84,116-121), dK [B, P, n, n] materialised */
+int gpr_trace_grad(const double* Kinv, const double* alpha, int alpha_stride, const double* dK, int B, int P, int n,
+                   double* grad, void* scratch, void* stream);
+long long gpr_trace_grad_scratch_bytes(int B, int P, int n);
+
 /* ---- "next" row N3: data partitioning (sampler.py) -------------------------------------------------------- */
 /*
  * D[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  (GEMM form, cross term on DMMA) — euclidean_dist sampler.py:94-100, used by

@@ -50,6 +50,11 @@ SIGNATURES = {
     "gpr_predict_full": (c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gpr_potri_batched": (c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
     "grbcm_full_combine": (c_int, [_P, _P, _I, _I, _P, _P]),
+    "gpr_predict_dense": (c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gpr_predict_dense_scratch_bytes": (c_longlong, [_I, _I, _I]),
+    "gpr_covar_dense": (c_int, [_P, _P, _I, _I, _I, _P, _P]),
+    "gpr_trace_grad": (c_int, [_P, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "gpr_trace_grad_scratch_bytes": (c_longlong, [_I, _I, _I]),
     "gpr_sq_dist": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "grbcm_partial": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "grbcm_finalize": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),

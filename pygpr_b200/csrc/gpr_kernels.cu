@@ -2293,6 +2293,116 @@ extern "C" int gpr_predict_gemm(const double* X, const double* a, const double* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dense path: any covariance the Covar protocol can express (e.g. Compose([SE, SE, WN]), covar.py:28-81) at the model level.
+// The kernel matrices come materialised from the kernel-level entry points (gpr_se_build / gpr_se_cross summed by the host
+// layer, as Compose.kernel does), K is factorised in place (gpr_potrf_batched, gen = 0), and
+//   gpr_predict_dense : V^T = K* X^T with X = L^-1 (vt_gemm_kernel), mean = V^T z = K* alpha, var = prior - |V|^2   gpr.py:76-106
+//   gpr_covar_dense   : cov = K** - V^T V                                                                            gpr.py:108-120
+//   gpr_trace_grad    : grad_p = 1/2 sum_ij (K^-1 - alpha alpha^T)_ij dK_p,ij  with dK materialised like the reference  loss.py:77-84
+// O(P n^2) memory like the reference — the fused path above is the one for large n.
+// ---------------------------------------------------------------------------------------------
+extern "C" long long gpr_predict_dense_scratch_bytes(int B, int npad, int m) {
+    const long long mpad = (m + TILE - 1) / TILE * TILE;
+    return 2 * align256((long long)B * (npad / TILE) * mpad * 8);
+}
+
+extern "C" int gpr_predict_dense(const double* X, const double* Ks, const double* z, const double* prior, int B, int npad, int m,
+                                 double* mean, double* var, double* vt, void* scratch, void* stream) {
+    ARG_CHECK(X && Ks && z && prior && mean && var && vt && scratch && B > 0 && m > 0 && npad > 0 && npad % TILE == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mpad = (m + TILE - 1) / TILE * TILE, nt = npad / TILE;
+    double* pv = reinterpret_cast<double*>(scratch);
+    double* pm = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + align256((long long)B * nt * mpad * 8));
+    CUDA_TRY(opt_in_smem(vt_gemm_kernel, MAIN_SMEM_BYTES));
+    vt_gemm_kernel<<<dim3(nt, mpad / TILE, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(Ks, X, z, npad, mpad, vt, pv, pm);
+    vt_finalize_kernel<<<dim3((m + 127) / 128, B), 128, 0, st>>>(pv, pm, prior, nt, mpad, m, mean, var, 0, nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+covar_dense_kernel(const double* __restrict__ vt, const double* __restrict__ Kss, int m, int mpad, int npad, double* __restrict__ cov) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long pipe_bars[2 * STAGES];
+    Pipe pipe;
+    pipe_init(pipe, pipe_bars);
+    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    const double* Vb = vt + (long long)b * mpad * npad;
+    double acc[4][8][2];
+    zero_acc(acc);
+    NoHook nh;
+    Seg none{nullptr, 0, nullptr, 0, 0};
+    Seg s0{Vb + (long long)ti * TILE * npad, npad, Vb + (long long)tj * TILE * npad, npad, npad / KC};
+    mainloop<false, XPF_PREDICT>(acc, s0, none, smem, nh, pipe);
+    const double* kb = Kss + (long long)b * m * m;
+    double* cb = cov + (long long)b * m * m;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long r = (long long)ti * TILE + acc_row(mi), c = (long long)tj * TILE + acc_col(ni, e);
+                if (r < m && c < m) cb[r * m + c] = kb[r * m + c] - acc[mi][ni][e];
+            }
+}
+
+extern "C" int gpr_covar_dense(const double* vt, const double* Kss, int B, int npad, int m, double* cov, void* stream) {
+    ARG_CHECK(vt && Kss && cov && B > 0 && m > 0 && npad > 0 && npad % TILE == 0);
+    const int mpad = (m + TILE - 1) / TILE * TILE;
+    CUDA_TRY(opt_in_smem(covar_dense_kernel, MAIN_SMEM_BYTES));
+    covar_dense_kernel<<<dim3(mpad / TILE, mpad / TILE, B), NTHREADS, MAIN_SMEM_BYTES, (cudaStream_t)stream>>>(vt, Kss, m, mpad, npad, cov);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+constexpr int TG_ROWS = 8;  // rows of W o dK_p per block of trace_grad_kernel
+__global__ void trace_grad_kernel(const double* __restrict__ Kinv, const double* __restrict__ alpha, int alpha_stride,
+                                  const double* __restrict__ dK, int P, int n, double* __restrict__ partial, int nchunks) {
+    __shared__ double red[NTHREADS / 32];
+    const int chunk = blockIdx.x, p = blockIdx.y, b = blockIdx.z;
+    const double* Kb = Kinv + (long long)b * n * n;
+    const double* Db = dK + ((long long)b * P + p) * n * n;
+    const double* al = alpha + (long long)b * alpha_stride;
+    double s = 0.0;
+    for (int r = chunk * TG_ROWS; r < (chunk + 1) * TG_ROWS && r < n; ++r) {
+        const double ar = al[r];
+        for (int c = threadIdx.x; c < n; c += NTHREADS) s += (Kb[(long long)r * n + c] - ar * al[c]) * Db[(long long)r * n + c];
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NTHREADS / 32; ++w) t += red[w];
+        partial[((long long)b * P + p) * nchunks + chunk] = t;
+    }
+}
+extern "C" long long gpr_trace_grad_scratch_bytes(int B, int P, int n) {
+    return align256((long long)B * P * ((n + TG_ROWS - 1) / TG_ROWS) * 8);
+}
+
+__global__ void trace_grad_sum_kernel(const double* __restrict__ partial, int BP, int nchunks, double* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BP) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += partial[(long long)i * nchunks + c];  // fixed order
+    grad[i] = 0.5 * s;
+}
+
+extern "C" int gpr_trace_grad(const double* Kinv, const double* alpha, int alpha_stride, const double* dK, int B, int P, int n,
+                              double* grad, void* scratch, void* stream) {
+    ARG_CHECK(Kinv && alpha && dK && grad && scratch && B > 0 && P > 0 && n > 0 && alpha_stride >= n);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nchunks = (n + TG_ROWS - 1) / TG_ROWS;
+    double* partial = reinterpret_cast<double*>(scratch);
+    trace_grad_kernel<<<dim3(nchunks, P, B), NTHREADS, 0, st>>>(Kinv, alpha, alpha_stride, dK, P, n, partial, nchunks);
+    trace_grad_sum_kernel<<<(B * P + 127) / 128, 128, 0, st>>>(partial, B * P, nchunks, grad);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // N1: explicit inverse from the Cholesky factor (tc.cholesky_solve(identity) / cholesky_inverse, gr_bcm.py:101-112)
 //   gpr_potri_batched = transpose_invdiag + trtri_kernel (U = L^-T into the block-upper part of L) + lauum_store_kernel
 //   (K^-1 = U U^T, both triangles written).  grbcm_full_combine: prec = sum_c Kinv_c o (beta_c[i] + beta_c[j]) / 2.

@@ -587,3 +587,83 @@ def grbcm_aggregate_full(model, ys_g, covars_g, ys_l, covars_l):
     total = S[2] + mean_g * p0 * b0                                              # (ys * prec * beta).sum(0), gr_bcm.py:147
     mu = total * torch.diagonal(covars)
     return _back(mu, out_like), _back(covars, out_like)
+
+
+# ---- dense path: model-level support for any Covar composition (kernel matrices materialised by the kernel-level API) ----------
+@dataclass
+class DenseState:
+    """Fit of materialised kernel matrices K [B, n, n] (noise and jitter included): what FitState is to the fused path."""
+    B: int
+    n: int
+    npad: int
+    L: torch.Tensor
+    invdiag: torch.Tensor
+    z: torch.Tensor
+    alpha: Optional[torch.Tensor]
+    logdet_half: torch.Tensor
+    zz: torch.Tensor
+    info: torch.Tensor
+    Linv: Optional[torch.Tensor] = None
+    Kinv: Optional[torch.Tensor] = None
+    shared_from = None
+
+    nlml = FitState.nlml
+    check = FitState.check
+
+
+def fit_dense(K: torch.Tensor, y: torch.Tensor, want_alpha: bool = True) -> DenseState:
+    """tc.cholesky + tc.cholesky_solve of gpr.py:67-72 / loss.py:37-51 for a materialised K [B, n, n] (device, float64)."""
+    B, n, _ = K.shape
+    npad = round_up(n, TILE)
+    dev = K.device
+    buf = torch.zeros(B, npad, npad, dtype=F64, device=dev)
+    buf[:, :n, :n] = K
+    if npad > n:
+        idx = torch.arange(n, npad, device=dev)
+        buf[:, idx, idx] = 1.0
+    ypad = torch.zeros(B, npad, dtype=F64, device=dev)
+    ypad[:, :n] = y
+    invdiag, z, logdet_half, zz, info = potrf_inplace(buf, ypad)
+    alpha = None
+    if want_alpha:
+        alpha = torch.empty(B, npad, dtype=F64, device=dev)
+        twork = _work("trsv", int(_lib.load().gpr_trsv_work_bytes(B)), dev)
+        _lib.call("gpr_trsv_backward", _p(buf), _p(invdiag), B, npad, _p(z), _p(alpha), _p(twork), _stream())
+        _count(1)
+    return DenseState(B, n, npad, buf, invdiag, z, alpha, logdet_half, zz, info)
+
+
+def predict_dense(st: DenseState, Ks: torch.Tensor, prior: torch.Tensor, Kss: Optional[torch.Tensor] = None):
+    """mean [B, m], variance [B, m] (and the full covariance when Kss [B, m, m] is given) from materialised cross-covariances
+    Ks [B, m, n]: gpr.py:76-120 with V^T = K* L^-T as a triangular GEMM against the cached L^-1."""
+    B, m, n = Ks.shape
+    dev = Ks.device
+    lib = _lib.load()
+    mpad = round_up(m, TILE)
+    ksp = torch.zeros(B, mpad, st.npad, dtype=F64, device=dev)
+    ksp[:, :m, :n] = Ks
+    X = tril_inverse(st)
+    mean = torch.empty(B, m, dtype=F64, device=dev)
+    var = torch.empty(B, m, dtype=F64, device=dev)
+    vt = torch.empty(B, mpad, st.npad, dtype=F64, device=dev)
+    scratch = _work("predict_dense", int(lib.gpr_predict_dense_scratch_bytes(B, st.npad, m)), dev)
+    _lib.call("gpr_predict_dense", _p(X), _p(ksp), _p(st.z), _p(prior.contiguous()), B, st.npad, m, _p(mean), _p(var), _p(vt),
+              _p(scratch), _stream())
+    _count(2)
+    covm = None
+    if Kss is not None:
+        covm = torch.empty(B, m, m, dtype=F64, device=dev)
+        _lib.call("gpr_covar_dense", _p(vt), _p(Kss.contiguous()), B, st.npad, m, _p(covm), _stream())
+        _count(1)
+    return mean, var, covm
+
+
+def lml_grad_dense(st: DenseState, dK: torch.Tensor) -> torch.Tensor:
+    """d NLML / d hp [B, P] = 1/2 sum (K^-1 - alpha alpha^T) o dK_p for materialised dK [B, P, n, n]   (loss.py:77-84,116-121)."""
+    B, P, n, _ = dK.shape
+    Kinv = kinv(st)
+    grad = torch.empty(B, P, dtype=F64, device=dK.device)
+    scratch = torch.empty(int(_lib.load().gpr_trace_grad_scratch_bytes(B, P, n)), dtype=torch.uint8, device=dK.device)
+    _lib.call("gpr_trace_grad", _p(Kinv), _p(st.alpha), st.npad, _p(dK.contiguous()), B, P, n, _p(grad), _p(scratch), _stream())
+    _count(2)
+    return grad

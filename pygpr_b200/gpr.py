@@ -118,10 +118,16 @@ class Exact_GP(GPR):
     def _launch_update(self, ws_tag: str = "", shared=None) -> None:
         """Queue the factorisation on the current stream without reading anything back (GRBCM overlaps two of them)."""
         spec = fused_spec(self.cov)
-        if spec is None:
-            raise _unsupported(self.cov)
         x, y, hp = self._device_inputs()
         assert hp.shape[-1] == self.cov.get_params_shape(self.x)[-1]
+        if spec is None:
+            # any other Covar composition: K materialised by the kernel-level API, factorised in place (engine.fit_dense)
+            K = self.cov.kernel(hp, x).reshape(-1, x.shape[1], x.shape[1]).clone()
+            K.diagonal(dim1=-2, dim2=-1).add_(engine.JITTER)           # gpr.py:68
+            self._state = None
+            self._state = engine.fit_dense(K, y)
+            self._dense_inputs = (x, hp)
+            return
         # refit in place: the old factor's buffer (it can fill most of HBM) is handed back to fit()
         old, self._state = self._state, None
         npad = engine.round_up(x.shape[1], engine.TILE)
@@ -142,9 +148,30 @@ class Exact_GP(GPR):
             self._finish_update()
         return None
 
+    def _predict_dense(self, xs: Tensor, full: bool):
+        x, hp = self._dense_inputs
+        B, n, m = x.shape[0], x.shape[1], xs.shape[0]
+        Ks = self.cov.kernel(hp, x, xs).reshape(B, m, n)                                    # gpr.py:79
+        if full:
+            Kss = self.cov.kernel(hp, xs.expand(B, -1, -1) if B > 1 else xs).reshape(B, m, m)  # gpr.py:110
+            prior = torch.diagonal(Kss, dim1=-2, dim2=-1)[:, 0].contiguous()
+        else:
+            Kss = None                                                                      # gpr.py:98 builds [m, m] for its diagonal;
+            prior = self.cov.kernel(hp, xs[:1].expand(B, -1, -1) if B > 1 else xs[:1]).reshape(B)  # stationary kernels: one point is enough
+        return engine.predict_dense(self._state, Ks, prior, Kss)
+
     def predict(self, xp: Tensor, var: str = "full") -> Sequence[Tensor]:
         self.update()
         xs = engine._dev(xp).reshape(-1, xp.shape[-1])
+        if isinstance(self._state, engine.DenseState):
+            mean, v, c = self._predict_dense(xs, var == "full")
+            if var == "full":
+                covars = _back(c.squeeze(0) if not self.batched else c, xp)
+            elif var == "diag":
+                covars = self._shape_out(v)
+            else:
+                covars = NotImplemented
+            return [_back(mean.squeeze(), self.x), covars]
         if var == "full":
             mean, covars = self._predict_full(xs)
             covars = _back(covars.squeeze(0) if not self.batched else covars, xp)
@@ -162,6 +189,8 @@ class Exact_GP(GPR):
         the cross-covariance tiles are regenerated on chip."""
         self.update()
         xs = engine._dev(xp).reshape(-1, xp.shape[-1])
+        if isinstance(self._state, engine.DenseState):
+            return self._shape_out(self._predict_dense(xs, False)[1])
         _, v = engine.predict(self._state, xs, True)
         return self._shape_out(v)
 
@@ -169,6 +198,9 @@ class Exact_GP(GPR):
         """Full predictive covariance (gpr.py:108-120)."""
         self.update()
         xs = engine._dev(xp).reshape(-1, xp.shape[-1])
+        if isinstance(self._state, engine.DenseState):
+            c = self._predict_dense(xs, True)[2]
+            return _back(c.squeeze(0) if not self.batched else c, xp)
         _, c = self._predict_full(xs)
         return _back(c.squeeze(0) if not self.batched else c, xp)
 

@@ -131,7 +131,7 @@ class GRBCM(GPR):
             return None
         if l._state is not None and l._state.shared_from is not None and not l.need_upd and g.need_upd:
             l.need_upd = True                                 # the local factors were built on a communication factor that is stale
-        if not (g.need_upd and l.need_upd):
+        if not (g.need_upd and l.need_upd) or fused_spec(g.cov) is None:
             g.update()
             l.update()
             return None
@@ -178,7 +178,7 @@ class GRBCM(GPR):
         return bool((pl.to(pg.device) == pg).all())
 
     def predict(self, xs, var="diag"):
-        if var == "diag":
+        if var == "diag" and fused_spec(self.gpg.cov) is not None:
             # gr_bcm.py:152-153 with the two predictions overlapped on the device (engine.predict_pair)
             self.update()
             xd = engine._dev(xs).reshape(-1, xs.shape[-1])

@@ -41,8 +41,6 @@ class MLE(Loss):
 
     def _fit(self, params: ndarray, want_alpha: bool):
         spec = fused_spec(self.model.cov)
-        if spec is None:
-            raise _unsupported(self.model.cov)
         xs, ys = self.model.x, self.model.y
         x = engine._dev(xs).reshape(-1, xs.shape[-2], xs.shape[-1])
         y = engine._dev(ys).reshape(-1, ys.shape[-1])
@@ -56,12 +54,30 @@ class MLE(Loss):
             x = x.expand(B, -1, -1).contiguous()
             y = y.expand(B, -1).contiguous()
         assert hp.shape[-1] == self.model.cov.get_params_shape(xs)[-1]
+        if spec is None:
+            # any other Covar composition: materialised K (and dK for the gradient, like the reference, loss.py:94)
+            n = x.shape[1]
+            if want_alpha:
+                K, dK = self.model.cov.kernel_and_grad(hp, x)
+                self._dK = dK.reshape(B, -1, n, n)
+            else:
+                K = self.model.cov.kernel(hp, x)
+            K = K.reshape(B, n, n).clone()
+            K.diagonal(dim1=-2, dim2=-1).add_(engine.JITTER)           # loss.py:38,63,96
+            st = engine.fit_dense(K, y, want_alpha=want_alpha)
+            st.check()
+            return st
         shared = getattr(self, "shared_state", None)        # set by GRBCM_MLE: the communication expert fitted at these params
         if shared is not None and not engine.can_share(shared, x.shape[1], x.shape[2], spec[0]):
             shared = None
         st = engine.fit(x, y, hp, spec[0], want_alpha=want_alpha, shared=shared)
         st.check()                                           # tc.cholesky raises on a non-PD matrix, loss.py:39
         return st
+
+    def _grad(self, st) -> torch.Tensor:
+        if isinstance(st, engine.DenseState):
+            return engine.lml_grad_dense(st, self._dK)
+        return engine.lml_grad(st)
 
     def _out(self, t: torch.Tensor) -> ndarray:
         t = t if self._batched else t.squeeze(0)
@@ -74,11 +90,11 @@ class MLE(Loss):
 
     def grad(self, params: ndarray) -> ndarray:
         st = self._fit(params, want_alpha=True)
-        self.grad_value = self._out(engine.lml_grad(st))     # loss.py:77-90
+        self.grad_value = self._out(self._grad(st))          # loss.py:77-90
         return self.grad_value
 
     def loss_and_grad(self, params: ndarray) -> Tuple[float, ndarray]:
         st = self._fit(params, want_alpha=True)
         self.loss_value = self._out(st.nlml())
-        self.grad_value = self._out(engine.lml_grad(st))     # loss.py:107-128
+        self.grad_value = self._out(self._grad(st))          # loss.py:107-128
         return (self.loss_value, self.grad_value)
