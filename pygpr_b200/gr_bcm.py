@@ -314,7 +314,8 @@ class GRBCM_MLE:
         # communication set) its factor is the leading block of every local expert's factor (engine.fit(shared=...))
         glob = MLE(g.gpg)
         st_g = glob._fit(theta, want_alpha=True)
-        share = st_g if (g.ng >= engine.TILE and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
+        share = st_g if (isinstance(st_g, engine.FitState) and g.ng >= engine.TILE
+                         and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
         if share is not None and want_grad and g.ng % engine.TILE == 0:
             engine.kinv(st_g)      # K_g^-1 and L_g^-T once: the experts' gradients reuse both (gpr_lml_grad_shared)
         for s in range(0, g.nc, step):
@@ -335,7 +336,7 @@ class GRBCM_MLE:
             acc = t.cpu().numpy()
         l = float(st_g.nlml()[0])
         if want_grad:
-            j = engine.lml_grad(st_g)[0].cpu().numpy()      # last: it overwrites the block-upper part of the shared factor
+            j = glob._grad(st_g)[0].cpu().numpy()           # last: it overwrites the block-upper part of the shared factor
             return float(acc[0] + l), acc[1:] + j
         return float(acc[0] + l), None
 
