@@ -114,3 +114,22 @@ def test_sharded_aggregation_gloo_world2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(os.path.join(str(tmp_path), "ok%d" % r)).read() for r in range(2)] == ["1", "1"]
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys;
+    the smoke-sized workload keeps it to seconds here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--small", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("GRBCM predictions/sec") and d["unit"] == "predictions/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
