@@ -205,8 +205,6 @@ extern "C" int gpr_sq_dist(const double* ax, const double* nx, int npadx, const 
     const int smem = feat_smem_bytes(dpad);
     if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the distance tile%s (dpad=%lld)", "", dpad);
     CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
-    static const double one_host = 1.0;
-    (void)one_host;
     dim3 grid((ny_rows + TILE - 1) / TILE, (nx_rows + TILE - 1) / TILE, 1);
     // hp is only read for sig (unused in raw mode); pass nx as a valid device pointer
     se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(ax, nx, npadx, ay, ny, npady, nx, 0, nullptr, nx_rows, ny_rows, dpad,
