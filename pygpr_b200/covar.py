@@ -159,8 +159,11 @@ class Compose:
         return None
 
 
-def fused_spec(cov):
-    """has_noise flag tuple for covariances the fused fit/predict/LML kernels support, else None."""
+def fused_spec(cov, d: Optional[int] = None):
+    """has_noise flag tuple for covariances the fused fit/predict/LML kernels support, else None (-> dense path).
+    d: input dimension, when known — beyond what the on-chip tile generation holds the answer is None as well."""
+    if d is not None and not engine.fused_dim_ok(d):
+        return None
     if isinstance(cov, Squared_exponential):
         return (False,)
     if isinstance(cov, Compose):

@@ -159,6 +159,15 @@ def split_hp(hp: torch.Tensor, d: int, has_noise: bool, jitter: float = JITTER):
     return torch.full_like(sig2, jitter), sig2.contiguous()
 
 
+def fused_dim_ok(d: int) -> bool:
+    """Whether the on-chip kernel-tile generation fits: the two [128, dpad] feature tiles must sit behind the 128x128 tile in
+    the 227 KB of shared memory (factorisation and gradient epilogue are the tightest: d <= 44).  Larger d takes the dense path."""
+    dpad = round_up(d, 4)
+    sld = dpad + 4 if dpad % 8 == 0 else dpad
+    feat = (2 * TILE * sld + 2 * TILE) * 8
+    return TILE * 132 * 8 + feat <= 226 * 1024
+
+
 def can_share(shared: Optional[FitState], n: int, d: int, has_noise: bool) -> bool:
     """Shape conditions for the shared leading block (the caller vouches that rows 0:ng of every expert are the
     communication set and that all hyper-parameter rows equal the communication expert's)."""

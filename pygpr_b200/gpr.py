@@ -117,8 +117,8 @@ class Exact_GP(GPR):
 
     def _launch_update(self, ws_tag: str = "", shared=None) -> None:
         """Queue the factorisation on the current stream without reading anything back (GRBCM overlaps two of them)."""
-        spec = fused_spec(self.cov)
         x, y, hp = self._device_inputs()
+        spec = fused_spec(self.cov, x.shape[-1])
         assert hp.shape[-1] == self.cov.get_params_shape(self.x)[-1]
         if spec is None:
             # any other Covar composition: K materialised by the kernel-level API, factorised in place (engine.fit_dense)

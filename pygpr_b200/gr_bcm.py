@@ -131,7 +131,7 @@ class GRBCM(GPR):
             return None
         if l._state is not None and l._state.shared_from is not None and not l.need_upd and g.need_upd:
             l.need_upd = True                                 # the local factors were built on a communication factor that is stale
-        if not (g.need_upd and l.need_upd) or fused_spec(g.cov) is None:
+        if not (g.need_upd and l.need_upd) or fused_spec(g.cov, self.dim) is None:
             g.update()
             l.update()
             return None
@@ -151,7 +151,7 @@ class GRBCM(GPR):
     def _fused_update(self) -> None:
         """gpg.update() + gpl.update() (gr_bcm.py:152-153 -> gpr.py:65-74) as one launch (engine.fit_grbcm)."""
         g, l = self.gpg, self.gpl
-        spec = fused_spec(g.cov)
+        spec = fused_spec(g.cov, self.dim)
         xg, yg, hp_g = g._device_inputs()
         x, y, hp = l._device_inputs()
         old, l._state, g._state = l._state, None, None
@@ -169,7 +169,7 @@ class GRBCM(GPR):
         g, l = self.gpg, self.gpl
         if os.environ.get("PYGPR_GRBCM_SHARE", "1") == "0":   # A/B knob: treat the experts as unrelated matrices
             return False
-        if fused_spec(g.cov) is None or self.ng < engine.TILE or self.nsc < 1:
+        if fused_spec(g.cov, self.dim) is None or self.ng < engine.TILE or self.nsc < 1:
             return False
         pg = g.params.detach().reshape(-1)
         pl = l.params.detach().reshape(-1, l.params.shape[-1])
@@ -178,7 +178,7 @@ class GRBCM(GPR):
         return bool((pl.to(pg.device) == pg).all())
 
     def predict(self, xs, var="diag"):
-        if var == "diag" and fused_spec(self.gpg.cov) is not None:
+        if var == "diag" and fused_spec(self.gpg.cov, self.dim) is not None:
             # gr_bcm.py:152-153 with the two predictions overlapped on the device (engine.predict_pair)
             self.update()
             xd = engine._dev(xs).reshape(-1, xs.shape[-1])

@@ -40,8 +40,8 @@ class MLE(Loss):
     """
 
     def _fit(self, params: ndarray, want_alpha: bool):
-        spec = fused_spec(self.model.cov)
         xs, ys = self.model.x, self.model.y
+        spec = fused_spec(self.model.cov, xs.shape[-1])
         x = engine._dev(xs).reshape(-1, xs.shape[-2], xs.shape[-1])
         y = engine._dev(ys).reshape(-1, ys.shape[-1])
         hp = engine._dev(torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)))

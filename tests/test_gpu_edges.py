@@ -125,3 +125,25 @@ def test_config2_shape_lml_grad_matches_oracle_at_reduced_n(P, orc):
     gamma = P.get_learn_rate(gp.params, mle, 1e-4)
     go_gamma = orc.learn_rate(["se", "wn"], _hp(1, d), x[None], y[None], 1e-4)
     assert_close(np.atleast_1d(gamma), go_gamma.numpy(), 1e-3, "gamma")
+
+
+def test_wide_inputs_take_the_dense_path(P, orc):
+    """d = 64 is beyond what the on-chip tile generation holds in shared memory (d <= 44): the model falls back to materialised
+    kernel matrices instead of raising, with the reference's results."""
+    from pygpr_b200 import engine
+    g = torch.Generator().manual_seed(9)
+    n, d, m = 200, 64, 50
+    x = torch.rand(n, d, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
+    xs = torch.rand(m, d, generator=g, dtype=torch.float64)
+    gp = P.Exact_GP(x, y, P.Compose([P.Squared_exponential(), P.White_noise()]))
+    gp.set_params(_hp(1, d)[0])
+    ys, cs = gp.predict(xs, var="diag")
+    assert isinstance(gp._state, engine.DenseState) and not engine.fused_dim_ok(d) and engine.fused_dim_ok(44)
+    mean_o, var_o = orc.gp_predict(["se", "wn"], _hp(1, d), x[None], y[None], xs, "diag")
+    assert_close(ys.numpy(), mean_o[0].numpy(), TOL, "mean")
+    assert_close(cs.numpy(), var_o[0].numpy(), TOL, "var")
+    loss, grad = P.MLE(gp).loss_and_grad(gp.params.numpy())
+    lo, go = orc.mle_loss_and_grad(["se", "wn"], _hp(1, d), x[None], y[None])
+    assert_close(np.atleast_1d(loss), lo.numpy(), TOL, "nlml")
+    assert_close(grad, go[0].numpy(), TOL, "grad")
