@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 2
+#define GPR_ABI_VERSION 3
 
 typedef enum {
     GPR_OK = 0,

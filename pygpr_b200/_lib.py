@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygpr_b200.so")
 
 TILE = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes).  Pointers are passed as integers (tensor.data_ptr()).
 _P, _I, _LL = c_void_p, c_int, c_longlong
