@@ -133,3 +133,31 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_shared_block_detection_and_dense_routing_are_host_logic():
+    """Path selection needs no device: GRBCM._shares_hyperparameters (one vector for the whole committee, at least one 128-row
+    block in the communication set), engine.fused_dim_ok / covar.fused_spec (which covariances and input widths the on-chip
+    tile generation covers; everything else goes the dense path)."""
+    import pygpr_b200 as P
+    from pygpr_b200 import engine
+    from pygpr_b200.covar import fused_spec
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+    xl, yl = torch.rand(4, 50, 3), torch.rand(4, 50)
+    big = P.GRBCM(xl, yl, torch.rand(130, 3), torch.rand(130), cov)
+    small = P.GRBCM(xl, yl, torch.rand(100, 3), torch.rand(100), cov)
+    assert big._shares_hyperparameters()                 # default init: identical rows (covar.py:96-100,221-225)
+    assert not small._shares_hyperparameters()           # communication set smaller than one block
+    hp = big.gpl.params.clone(); hp[2, 1] = 1.5
+    big.gpl.set_params(hp)
+    assert not big._shares_hyperparameters()             # per-expert vectors
+    big.gpl.set_params(big.gpg.params.repeat(4, 1))
+    assert big._shares_hyperparameters()
+    os.environ["PYGPR_GRBCM_SHARE"] = "0"
+    try:
+        assert not big._shares_hyperparameters()
+    finally:
+        del os.environ["PYGPR_GRBCM_SHARE"]
+    assert engine.fused_dim_ok(16) and engine.fused_dim_ok(44) and not engine.fused_dim_ok(45) and not engine.fused_dim_ok(64)
+    assert fused_spec(cov, 16) == (True,) and fused_spec(P.Squared_exponential(), 8) == (False,) and fused_spec(cov, 64) is None
+    assert fused_spec(P.Compose([P.Squared_exponential(), P.Squared_exponential(), P.White_noise()]), 4) is None
