@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 3
+#define GPR_ABI_VERSION 4
 
 typedef enum {
     GPR_OK = 0,
@@ -38,6 +38,9 @@ typedef enum {
 
 int gpr_abi_version(void);
 const char* gpr_last_error(void);
+/* developer A/B knobs of the schedules: "potrf_mode" = auto|columns|columns1|dataflow, "trsv_mode" = auto|single.  Their
+ * initial values come from PYGPR_POTRF_MODE / PYGPR_TRSV_MODE, read once when the library is loaded. */
+int gpr_set_option(const char* name, const char* value);
 /* number of SMs / max opt-in shared memory of the current device (0 on error) */
 int gpr_device_sm_count(void);
 
@@ -295,6 +298,26 @@ long long gpr_trace_grad_scratch_bytes(int B, int P, int n);
  */
 int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay, const double* ny, int npady,
                 int nx_rows, int ny_rows, int dpad, double* D, void* stream);
+
+/* ---- "next" row N4: FP64-accurate products on the INT8 tcgen05 tensor cores (emulated FP64 / reduced-precision opt-in) ----- */
+/*
+ * C = beta*C + A B^T with A [M, K], B [N, K] given as balanced radix-256 digit planes (Ozaki-style splitting): stands in for
+ * the FP64 GEMMs behind tc.cholesky_solve(K*^T, L) gpr.py:100 and tc.bmm gpr.py:80,115 wherever they are expressed as a
+ * product with a cached L^-1.  Every plane product runs on tcgen05.mma kind::i8 with exact int32 accumulation in TMEM;
+ * the FP64 recombination happens in the epilogue.  `slices` (1..8) is the accuracy knob: the result carries
+ * ~2^(2-8*slices) of the product of the row maxima (6: FP64 grade, 3-4: the FP32-grade opt-in mode of north_star).
+ *   gpr_ozaki_split      X [rows, k] (leading dimension ld) -> planes [slices][rpad][kpad] int8 + scale [rpad]
+ *                        (rpad = gpr_ozaki_rows_padded(rows), kpad = gpr_ozaki_k_padded(k); planes of
+ *                        gpr_ozaki_planes_bytes bytes; padding rows/columns are zero)
+ *   gpr_ozaki_gemm_nt    both operands split with the SAME slices and k;  b_lower != 0: B[j, k] = 0 for k > j (a lower
+ *                        triangular B, e.g. L^-1) and the zero k-blocks are skipped;  K * slices < 2^17 (int32 headroom)
+ */
+long long gpr_ozaki_rows_padded(int rows);
+long long gpr_ozaki_k_padded(int k);
+long long gpr_ozaki_planes_bytes(int rows, int k, int slices);
+int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, void* planes, double* scale, void* stream);
+int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
+                      int K, int slices, int b_lower, double beta, double* C, long long ldc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,19 +7,20 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_int, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygpr_b200.so")
 
 TILE = 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes).  Pointers are passed as integers (tensor.data_ptr()).
 _P, _I, _LL = c_void_p, c_int, c_longlong
 SIGNATURES = {
     "gpr_abi_version": (c_int, []),
     "gpr_last_error": (c_char_p, []),
+    "gpr_set_option": (c_int, [c_char_p, c_char_p]),
     "gpr_device_sm_count": (c_int, []),
     "gpr_predict_scratch_bytes": (c_longlong, [_I]),
     "gpr_tril_inverse": (c_int, [_P, _P, _I, _I, _P, _P, _P]),
@@ -58,6 +59,11 @@ SIGNATURES = {
     "gpr_sq_dist": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "grbcm_partial": (c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "grbcm_finalize": (c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "gpr_ozaki_rows_padded": (c_longlong, [_I]),
+    "gpr_ozaki_k_padded": (c_longlong, [_I]),
+    "gpr_ozaki_planes_bytes": (c_longlong, [_I, _I, _I]),
+    "gpr_ozaki_split": (c_int, [_P, _LL, _I, _I, _I, _P, _P, _P]),
+    "gpr_ozaki_gemm_nt": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, c_double, _P, _LL, _P]),
 }
 
 _lib = None

@@ -1,0 +1,37 @@
+"""Developer A/B knobs of the host layer and of the library's schedules (not part of the reference's API).
+
+Every knob takes its initial value from the environment ONCE, at import; afterwards it is a plain attribute
+(``options.share = False``) or, for the two schedule overrides that live in the library, a setter call.
+
+    PYGPR_GRBCM_SHARE=0        options.share        treat GRBCM experts as unrelated matrices (no shared leading block)
+    PYGPR_GRBCM_FUSED_FIT=0    options.fused_fit    fit the communication expert in its own launch
+    PYGPR_PREDICT_CHUNK=n      options.predict_chunk  test points per prediction batch of GRBCM.predict
+    PYGPR_PREDICT_FORM=...     options.predict_form   auto | subst | gemm  (engine.predict)
+    PYGPR_POTRF_MODE=...       set_potrf_mode()     auto | columns | columns1 | dataflow
+    PYGPR_TRSV_MODE=...        set_trsv_mode()      auto | single
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+from . import _lib
+
+
+@dataclass
+class Options:
+    share: bool = os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0"
+    fused_fit: bool = os.environ.get("PYGPR_GRBCM_FUSED_FIT", "1") != "0"
+    predict_chunk: int = int(os.environ.get("PYGPR_PREDICT_CHUNK", "16384"))
+    predict_form: str = os.environ.get("PYGPR_PREDICT_FORM", "auto")
+
+
+options = Options()
+
+
+def set_potrf_mode(mode: str) -> None:
+    _lib.call("gpr_set_option", b"potrf_mode", mode.encode())
+
+
+def set_trsv_mode(mode: str) -> None:
+    _lib.call("gpr_set_option", b"trsv_mode", mode.encode())

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libpygpr_b200.so")
-SOURCES = [os.path.join(HERE, "gpr_kernels.cu")]
+SOURCES = [os.path.join(HERE, "gpr_kernels.cu"), os.path.join(HERE, "ozaki_gemm.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "gpr_core.cuh"), os.path.join(ROOT, "include", "pygpr_b200.h")]
 
 NVCC_FLAGS = [

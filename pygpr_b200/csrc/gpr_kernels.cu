@@ -42,6 +42,30 @@ static int fail(int code, const char* fmt, const char* a = "", long long v = 0) 
         if (!(cond)) return fail(GPR_ERR_BAD_ARG, "bad argument: %s (line %lld)", #cond, __LINE__); \
     } while (0)
 
+// Schedule overrides (developer A/B knobs).  Read from the environment ONCE, when the library is loaded
+// (PYGPR_POTRF_MODE=auto|columns|columns1|dataflow, PYGPR_TRSV_MODE=auto|single); gpr_set_option changes them at run time.
+enum { POTRF_AUTO = 0, POTRF_COLUMNS = 1, POTRF_COLUMNS1 = 2, POTRF_DATAFLOW = 3 };
+enum { TRSV_AUTO = 0, TRSV_SINGLE = 1 };
+static int parse_potrf_mode(const char* v) {
+    if (!v) return POTRF_AUTO;
+    if (!strcmp(v, "columns1")) return POTRF_COLUMNS1;
+    if (!strncmp(v, "columns", 7)) return POTRF_COLUMNS;
+    if (!strcmp(v, "dataflow")) return POTRF_DATAFLOW;
+    return POTRF_AUTO;
+}
+static int parse_trsv_mode(const char* v) { return (v && !strcmp(v, "single")) ? TRSV_SINGLE : TRSV_AUTO; }
+static int g_potrf_mode = parse_potrf_mode(getenv("PYGPR_POTRF_MODE"));
+static int g_trsv_mode = parse_trsv_mode(getenv("PYGPR_TRSV_MODE"));
+
+extern "C" int gpr_set_option(const char* name, const char* value) {
+    if (name && !strcmp(name, "potrf_mode")) { g_potrf_mode = parse_potrf_mode(value); return GPR_OK; }
+    if (name && !strcmp(name, "trsv_mode")) { g_trsv_mode = parse_trsv_mode(value); return GPR_OK; }
+    return fail(GPR_ERR_BAD_ARG, "unknown option %s", name ? name : "(null)");
+}
+
+// shared with the other translation units of the library (ozaki_gemm.cu)
+extern "C" int gpr_internal_fail(int code, const char* fmt, const char* a, long long v) { return fail(code, fmt, a, v); }
+
 extern "C" int gpr_abi_version(void) { return GPR_ABI_VERSION; }
 extern "C" const char* gpr_last_error(void) { return g_err; }
 extern "C" int gpr_device_sm_count(void) {
@@ -913,13 +937,13 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
     // single-launch dataflow form when there are enough tile tasks per block column to keep the SMs busy across the
     // dependency chain of any one expert; the per-column form with split-K for few experts (PYGPR_POTRF_MODE overrides)
     {
-        const char* mode = getenv("PYGPR_POTRF_MODE");
+        const int mode = g_potrf_mode;
         const long long total = (long long)B * ((long long)gt * (nt - gt) + (long long)(nt - gt) * (nt - gt + 1) / 2);
         // measured on B200 (tools/potrf_modes.py): dataflow wins from ~8 experts up (+8 % at B=32..63), ties at 4, loses below
         // (three-stream per-column form: B=1 n=16384 59 ms vs 145 ms dataflow, B=3 n=2048 2.6 vs 3.1 ms, B=1 n=1024 a tie)
         bool dataflow = work && nt >= 2 && B >= 6 && total < (1LL << 30);
-        if (mode && !strncmp(mode, "columns", 7)) dataflow = false;
-        if (mode && !strcmp(mode, "dataflow") && work && total < (1LL << 30)) dataflow = true;
+        if (mode == POTRF_COLUMNS || mode == POTRF_COLUMNS1) dataflow = false;
+        if (mode == POTRF_DATAFLOW && work && total < (1LL << 30)) dataflow = true;
         if (gt > 0) {  // the shared leading block exists in the dataflow form only
             if (!work || total >= (1LL << 30)) return fail(GPR_ERR_BAD_ARG, "shared leading block needs a workspace%s", "");
             dataflow = true;
@@ -963,8 +987,7 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
     // needs diag(j).  A column then costs max(bulk, diag + solve) instead of diag + first tile + bulk
     // (one matrix: n = 4096 8.4 -> 5.3 ms, 8192 22 -> 14.5, 16384 79 -> 59; 4 x 8192: 40 -> 30).
     // PYGPR_POTRF_MODE=columns1 keeps everything on the caller's stream.
-    const char* mode1 = getenv("PYGPR_POTRF_MODE");
-    PotrfAux* aux = (work && nt >= 3 && !(mode1 && !strcmp(mode1, "columns1"))) ? potrf_aux() : nullptr;
+    PotrfAux* aux = (work && nt >= 3 && g_potrf_mode != POTRF_COLUMNS1) ? potrf_aux() : nullptr;
     int* counters_c = nullptr;
     double* slots_c = nullptr;
     int* dflags = nullptr;  // [0] abort, [1 + b] = number of diagonal tiles of expert b finished
@@ -1317,9 +1340,8 @@ extern "C" int gpr_trsv_backward(const double* L, const double* invdiag, int B, 
     const int nt = npad / TILE;
     int sms = gpr_device_sm_count();
     if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
-    const char* mode = getenv("PYGPR_TRSV_MODE");
     bool owner = work && B < sms && nt >= 4 && z != alpha;
-    if (mode && !strcmp(mode, "single")) owner = false;
+    if (g_trsv_mode == TRSV_SINGLE) owner = false;
     if (owner) {
         int G = (2 * sms) / B;
         if (G > nt) G = nt;

@@ -25,10 +25,12 @@ def world(group=None) -> Tuple[int, int]:
 
 
 def shard_bounds(nc: int, world_size: int, rank: int) -> Tuple[int, int]:
-    """Contiguous block [lo, hi) of the nc local experts owned by `rank` (ceil(nc/G) per rank)."""
-    per = -(-nc // world_size)
-    lo = min(rank * per, nc)
-    return lo, min(lo + per, nc)
+    """Contiguous block [lo, hi) of the nc local experts owned by `rank`: a balanced split, floor(nc/G) each and one more
+    on the first nc % G ranks (255 over 8 -> 32 x 7 + 31, the split of SURVEY 8e; 9 over 8 -> 2,1,1,...: no empty rank
+    while nc >= G).  A rank with lo == hi owns nothing and contributes zero partial sums."""
+    base, extra = divmod(nc, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
 
 
 def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:

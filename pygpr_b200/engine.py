@@ -340,8 +340,8 @@ _sm_count = {}
 def _use_gemm_form(st: FitState, m: int) -> bool:
     """Prediction form: blocked substitution (one serial task per expert and 128 test points — the bench path) or the
     triangular GEMM with L^-1 (independent tiles; needs the inverse once per fit).  PYGPR_PREDICT_FORM=subst|gemm forces."""
-    import os
-    form = os.environ.get("PYGPR_PREDICT_FORM", "auto")
+    from .config import options
+    form = options.predict_form
     if form in ("subst", "gemm"):
         return form == "gemm"
     dev = st.L.device.index
@@ -579,7 +579,8 @@ def grbcm_aggregate_full(model, ys_g, covars_g, ys_l, covars_l):
     var_g = torch.diagonal(cov_g).contiguous()                                   # gr_bcm.py:122
     var_l = torch.diagonal(cov_l, dim1=-2, dim2=-1).contiguous()                 # gr_bcm.py:123
     S, brow, prow = grbcm_partial(mean_l, var_l, var_g, model.expert_offset, want_rows=True)
-    gdist.all_reduce_sum_(S, model.group)
+    if model.sharded:
+        gdist.all_reduce_sum_(S, model.group)
     _, _, b0, p0 = grbcm_finalize(S, mean_g, var_g, want_rows=True)
     model.beta = _back(torch.cat((b0[None], brow)), out_like)
     model.prec = _back(torch.cat((p0[None], prow)), out_like)
@@ -591,7 +592,8 @@ def grbcm_aggregate_full(model, ys_g, covars_g, ys_l, covars_l):
     prec = torch.empty(m, m, dtype=F64, device=mean_g.device)
     _lib.call("grbcm_full_combine", _p(kinv), _p(betas.contiguous()), betas.shape[0], m, _p(prec), _stream())
     _count(1)
-    gdist.all_reduce_sum_(prec, model.group)
+    if model.sharded:
+        gdist.all_reduce_sum_(prec, model.group)
     covars = spd_inverse(prec[None])[0]                                          # gr_bcm.py:112
     total = S[2] + mean_g * p0 * b0                                              # (ys * prec * beta).sum(0), gr_bcm.py:147
     mu = total * torch.diagonal(covars)
@@ -676,3 +678,41 @@ def lml_grad_dense(st: DenseState, dK: torch.Tensor) -> torch.Tensor:
     _lib.call("gpr_trace_grad", _p(Kinv), _p(st.alpha), st.npad, _p(dK.contiguous()), B, P, n, _p(grad), _p(scratch), _stream())
     _count(2)
     return grad
+
+
+# ---- "next" row N4: FP64-accurate products on the INT8 tcgen05 tensor cores (csrc/ozaki_gemm.cu) ------------------------------
+@dataclass
+class DigitPlanes:
+    """Balanced radix-256 digit planes of a matrix X [rows, k] (gpr_ozaki_split): planes [slices, rpad, kpad] int8, scale [rpad]."""
+    rows: int
+    k: int
+    slices: int
+    planes: torch.Tensor
+    scale: torch.Tensor
+
+
+def ozaki_split(X: torch.Tensor, slices: int) -> DigitPlanes:
+    """Digit planes of a row-major FP64 matrix (last dimension contiguous)."""
+    assert X.dim() == 2 and X.stride(1) == 1 and X.dtype == F64
+    rows, k = X.shape
+    lib = _lib.load()
+    rpad, kpad = int(lib.gpr_ozaki_rows_padded(rows)), int(lib.gpr_ozaki_k_padded(k))
+    planes = torch.empty(slices, rpad, kpad, dtype=torch.int8, device=X.device)
+    scale = torch.empty(rpad, dtype=F64, device=X.device)
+    _lib.call("gpr_ozaki_split", _p(X), X.stride(0), rows, k, slices, _p(planes), _p(scale), _stream())
+    _count(1)
+    return DigitPlanes(rows, k, slices, planes, scale)
+
+
+def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = None, beta: float = 0.0,
+                  b_lower: bool = False) -> torch.Tensor:
+    """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt)."""
+    assert A.k == B.k and A.slices == B.slices
+    if out is None:
+        out = torch.empty(A.rows, B.rows, dtype=F64, device=A.planes.device)
+        beta = 0.0
+    assert out.shape == (A.rows, B.rows) and out.stride(1) == 1
+    _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), A.rows, _p(B.planes), _p(B.scale), B.rows, A.k, A.slices,
+              int(b_lower), float(beta), _p(out), out.stride(0), _stream())
+    _count(1)
+    return out

@@ -1,12 +1,11 @@
 """Generalized Robust Bayesian Committee Machine with the reference's API (PyGPR/gr_bcm.py)."""
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import dist as gdist
 from . import engine
+from .config import options
 from .covar import _back, fused_spec
 from .gpr import GPR, Exact_GP
 
@@ -35,10 +34,13 @@ class GRBCM(GPR):
             lo, hi = gdist.shard_bounds(nc_given, ws, rank)
             xl, yl = xl[lo:hi], yl[lo:hi]
             self.expert_offset, self.nc_total = lo, nc_given
+            self.sharded = True
         else:
             self.expert_offset = int(kargs.get("expert_offset", 0))
             self.nc_total = int(kargs.get("nc_total", nc_given))
-        self.sharded = self.nc_total != xl.shape[0]
+            # a model that holds every expert is NOT sharded, whatever torch.distributed's state: it enters no collective
+            # (replicated models on several ranks would otherwise sum their identical partial sums world_size times)
+            self.sharded = bool(kargs.get("sharded", self.nc_total != xl.shape[0] or self.expert_offset != 0)) and ws > 1
 
         nc = xl.shape[0]
         nls = xl.shape[1]
@@ -57,6 +59,7 @@ class GRBCM(GPR):
         self.ng = ng
         self.dim = dim
         self._weights = None
+        self._share_key, self._share_val = None, False
         self._beta = NotImplemented
         self._prec = NotImplemented
 
@@ -92,13 +95,20 @@ class GRBCM(GPR):
         axis are formed per rank and all-reduced; ``beta``/``prec`` then hold row 0 + this rank's rows."""
         if var != "diag":
             return self._aggregate_full(ys_g, covars_g, ys_l, covars_l)
-        out_like = ys_g
         mean_g, var_g = engine._dev(ys_g).reshape(-1), engine._dev(covars_g).reshape(-1)
         m = mean_g.shape[0]
-        mean_l = engine._dev(ys_l).reshape(-1, m)
-        var_l = engine._dev(covars_l).reshape(-1, m)
-        S, brow, prow = engine.grbcm_partial(mean_l, var_l, var_g, self.expert_offset, want_rows=True)
-        gdist.all_reduce_sum_(S, self.group)                  # the only data-path collective: [3, m] doubles
+        return self._aggregate_device(mean_g, var_g, engine._dev(ys_l).reshape(-1, m), engine._dev(covars_l).reshape(-1, m), ys_g)
+
+    def _aggregate_device(self, mean_g, var_g, mean_l, var_l, out_like):
+        """aggregate() on device tensors (mean_g, var_g [m]; mean_l, var_l [nc, m]): nothing but the two result vectors
+        leaves the device (and those only when the caller's tensors live on the host)."""
+        if mean_l.shape[0] == 0:                              # a rank without local experts (more ranks than experts)
+            S = torch.zeros(3, mean_g.shape[0], dtype=mean_g.dtype, device=mean_g.device)
+            brow = prow = torch.empty(0, mean_g.shape[0], dtype=mean_g.dtype, device=mean_g.device)
+        else:
+            S, brow, prow = engine.grbcm_partial(mean_l, var_l, var_g, self.expert_offset, want_rows=True)
+        if self.sharded:
+            gdist.all_reduce_sum_(S, self.group)              # the only data-path collective: [3, m] doubles
         mu, v, b0, p0 = engine.grbcm_finalize(S, mean_g, var_g, want_rows=True)
         # self.beta / self.prec (gr_bcm.py:135-136): kept on the device and moved to the callers' device on first read — a
         # [nc+1, m] pair that most callers never look at should not cost a device->host copy per prediction
@@ -117,7 +127,7 @@ class GRBCM(GPR):
         if self._shares_hyperparameters():
             # one hyper-parameter vector for the whole committee: the local experts' factors start with the communication
             # expert's (gr_bcm.py:19-26 puts its training set first in every expert), so it is fitted first and reused
-            if g.need_upd and os.environ.get("PYGPR_GRBCM_FUSED_FIT", "1") != "0":
+            if g.need_upd and options.fused_fit:
                 self._fused_update()                         # both factorisations in one launch
             else:
                 if g.need_upd:
@@ -167,36 +177,41 @@ class GRBCM(GPR):
         setting, and what GRBCM_MLE trains) and the communication set holds at least one 128-row block — the conditions of
         the shared leading block (engine.fit(shared=...)); a ragged rest of the communication set is each expert's own."""
         g, l = self.gpg, self.gpl
-        if os.environ.get("PYGPR_GRBCM_SHARE", "1") == "0":   # A/B knob: treat the experts as unrelated matrices
+        if not options.share:                                        # A/B knob: treat the experts as unrelated matrices
             return False
-        if fused_spec(g.cov, self.dim) is None or self.ng < engine.TILE or self.nsc < 1:
+        if fused_spec(g.cov, self.dim) is None or self.ng < engine.TILE or self.nsc < 1 or self.nc < 1:
             return False
-        pg = g.params.detach().reshape(-1)
-        pl = l.params.detach().reshape(-1, l.params.shape[-1])
-        if pl.shape[-1] != pg.shape[0]:
-            return False
-        return bool((pl.to(pg.device) == pg).all())
+        # the comparison reads every hyper-parameter row back: do it once per (params, params) pair, not once per predict
+        key = (id(g.params), g.params._version, id(l.params), l.params._version)
+        if self._share_key != key:
+            pg = g.params.detach().reshape(-1)
+            pl = l.params.detach().reshape(-1, l.params.shape[-1])
+            self._share_val = bool(pl.shape[-1] == pg.shape[0] and (pl.to(pg.device) == pg).all())
+            self._share_key = key
+        return self._share_val
 
     def predict(self, xs, var="diag"):
         if var == "diag" and fused_spec(self.gpg.cov, self.dim) is not None:
-            # gr_bcm.py:152-153 with the two predictions overlapped on the device (engine.predict_pair)
+            # gr_bcm.py:152-155 with the two predictions overlapped on the device (engine.predict_pair) and the per-expert
+            # means / variances handed to the aggregation kernels where they are: [nc, m] intermediates never visit the host
             self.update()
             xd = engine._dev(xs).reshape(-1, xs.shape[-1])
             # test points go through in chunks (SURVEY 8d): the per-chunk scratch (the communication expert's V_g^T is
             # [chunk, ng]) stays bounded however many points are asked for; the kernels see chunks as independent batches
-            step = max(int(os.environ.get("PYGPR_PREDICT_CHUNK", "16384")), 1)
-            if xd.shape[0] <= step:
+            step = max(int(options.predict_chunk), 1)
+            if self.nc == 0:
+                mg, vg = engine.predict(self.gpg._state, xd, True)
+                ml = vl = mg[:0]
+            elif xd.shape[0] <= step:
                 (mg, vg), (ml, vl) = engine.predict_pair(self.gpg._state, self.gpl._state, xd)
             else:
                 parts = [engine.predict_pair(self.gpg._state, self.gpl._state, xd[s:s + step].contiguous())
                          for s in range(0, xd.shape[0], step)]
                 mg, vg = (torch.cat([p[0][k] for p in parts], dim=1) for k in (0, 1))
                 ml, vl = (torch.cat([p[1][k] for p in parts], dim=1) for k in (0, 1))
-            ys_g, covars_g = _back(mg.squeeze(), self.gpg.x), self.gpg._shape_out(vg)
-            ys_l, covars_l = _back(ml.squeeze(), self.gpl.x), self.gpl._shape_out(vl)
-        else:
-            ys_g, covars_g = self.gpg.predict(xs, var=var)    # gr_bcm.py:152
-            ys_l, covars_l = self.gpl.predict(xs, var=var)    # gr_bcm.py:153
+            return self._aggregate_device(mg[0], vg[0], ml, vl, self.gpg.x)   # gr_bcm.py:155
+        ys_g, covars_g = self.gpg.predict(xs, var=var)        # gr_bcm.py:152
+        ys_l, covars_l = self.gpl.predict(xs, var=var)        # gr_bcm.py:153
         if self.nc == 1:
             ys_l = ys_l.reshape(1, -1)
         return self.aggregate(ys_g, covars_g, ys_l, covars_l, var=var)  # gr_bcm.py:155
@@ -314,8 +329,7 @@ class GRBCM_MLE:
         # communication set) its factor is the leading block of every local expert's factor (engine.fit(shared=...))
         glob = MLE(g.gpg)
         st_g = glob._fit(theta, want_alpha=True)
-        share = st_g if (isinstance(st_g, engine.FitState) and g.ng >= engine.TILE
-                         and os.environ.get("PYGPR_GRBCM_SHARE", "1") != "0") else None
+        share = st_g if (isinstance(st_g, engine.FitState) and g.ng >= engine.TILE and options.share) else None
         if share is not None and want_grad and g.ng % engine.TILE == 0:
             engine.kinv(st_g)      # K_g^-1 and L_g^-T once: the experts' gradients reuse both (gpr_lml_grad_shared)
         for s in range(0, g.nc, step):
@@ -330,7 +344,7 @@ class GRBCM_MLE:
             else:
                 acc[0] += np.sum(part.loss(th))
         t = torch.from_numpy(acc)
-        if gdist.is_dist():
+        if g.sharded:
             t = engine._dev(t)
             gdist.all_reduce_sum_(t, g.group)         # [1+P] doubles
             acc = t.cpu().numpy()

@@ -26,3 +26,13 @@ def golden():
         return dict(np.load(golden_path(name)))
 
     return _load
+
+
+@pytest.fixture(autouse=True)
+def _restore_library_modes(request):
+    """Tests that switch the library's schedule overrides (config.set_potrf_mode / set_trsv_mode) leave them at auto."""
+    yield
+    if request.node.get_closest_marker("gpu") is not None:
+        from pygpr_b200 import config
+        config.set_potrf_mode("auto")
+        config.set_trsv_mode("auto")

@@ -57,7 +57,8 @@ def test_se_kernels(eng, orc, B, n, d, m):
 @pytest.mark.parametrize("form", ["subst", "gemm"])
 def test_fit_predict(eng, orc, monkeypatch, B, n, d, m, per, form):
     """form: blocked substitution (the bench kernel) / triangular GEMM with L^-1 (what few-task predictions use)."""
-    monkeypatch.setenv("PYGPR_PREDICT_FORM", form)
+    from pygpr_b200 import config
+    monkeypatch.setattr(config.options, "predict_form", form)
     x, y, xs, hp = _data(2, B, n, d, m, per_expert=per)
     st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True)
     torch.cuda.synchronize()
@@ -126,7 +127,8 @@ def test_grbcm_aggregate(eng, orc):
 def test_fit_schedules(eng, orc, monkeypatch, mode, B, n, d):
     """Both schedules of the batched Cholesky (one launch pair per block column with split-K / one dataflow launch with
     per-row progress counters) give the reference's factor, forward solve and NLML."""
-    monkeypatch.setenv("PYGPR_POTRF_MODE", mode)
+    from pygpr_b200 import config
+    config.set_potrf_mode(mode)
     x, y, xs, hp = _data(7, B, n, d, 16, per_expert=True)
     st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True)
     torch.cuda.synchronize()
@@ -140,7 +142,8 @@ def test_fit_schedules(eng, orc, monkeypatch, mode, B, n, d):
 def test_dataflow_info_and_repeat(eng, orc, monkeypatch):
     """Dataflow schedule: a non-PD expert is reported in info without disturbing the others or hanging the waits, and
     the progress counters are reset between calls (two calls in a row agree bit for bit)."""
-    monkeypatch.setenv("PYGPR_POTRF_MODE", "dataflow")
+    from pygpr_b200 import config
+    config.set_potrf_mode("dataflow")
     x, y, xs, hp = _data(8, 6, 300, 4, 8)
     K = orc.compose_kernel(SPEC, hp, x)
     K.diagonal(dim1=-2, dim2=-1).add_(1e-7)
@@ -166,9 +169,10 @@ def test_backward_solve_forms(eng, orc, monkeypatch, B, n, d):
     """alpha = L^-T z: the cooperative column-owner form (several CTAs per expert, used for few experts) and the
     one-CTA-per-expert form agree with each other and with the reference's cholesky_solve (gpr.py:70-72)."""
     x, y, xs, hp = _data(9, B, n, d, 8, per_expert=True)
-    monkeypatch.setenv("PYGPR_TRSV_MODE", "single")
+    from pygpr_b200 import config
+    config.set_trsv_mode("single")
     a1 = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True).alpha.clone()
-    monkeypatch.setenv("PYGPR_TRSV_MODE", "auto")
+    config.set_trsv_mode("auto")
     a2 = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True).alpha.clone()
     torch.cuda.synchronize()
     _, alpha_ref = orc.gp_fit(SPEC, hp, x, y)

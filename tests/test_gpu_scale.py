@@ -53,7 +53,8 @@ def test_fit_predict_at_baseline_sizes(monkeypatch, B, n, d, m, form):
     """Expert orders of configs 4 (8192, and the 4096 communication expert) and 2 (16384): both schedules of the
     factorisation are exercised (B=6 -> dataflow, B<6 -> per-column with split-K)."""
     from pygpr_b200 import engine as eng
-    monkeypatch.setenv("PYGPR_PREDICT_FORM", form)
+    from pygpr_b200 import config
+    monkeypatch.setattr(config.options, "predict_form", form)
     x, y, xs, hp = _data(11, B, n, d, m)
     st = eng.fit(x, y, hp, True)
     mean, var = eng.predict(st, xs, True)

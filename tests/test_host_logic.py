@@ -153,11 +153,12 @@ def test_shared_block_detection_and_dense_routing_are_host_logic():
     assert not big._shares_hyperparameters()             # per-expert vectors
     big.gpl.set_params(big.gpg.params.repeat(4, 1))
     assert big._shares_hyperparameters()
-    os.environ["PYGPR_GRBCM_SHARE"] = "0"
+    from pygpr_b200 import config
+    config.options.share = False
     try:
         assert not big._shares_hyperparameters()
     finally:
-        del os.environ["PYGPR_GRBCM_SHARE"]
+        config.options.share = True
     assert engine.fused_dim_ok(16) and engine.fused_dim_ok(44) and not engine.fused_dim_ok(45) and not engine.fused_dim_ok(64)
     assert fused_spec(cov, 16) == (True,) and fused_spec(P.Squared_exponential(), 8) == (False,) and fused_spec(cov, 64) is None
     assert fused_spec(P.Compose([P.Squared_exponential(), P.Squared_exponential(), P.White_noise()]), 4) is None

@@ -6,6 +6,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import pygpr_b200 as P
 from pygpr_b200 import engine as eng
+from pygpr_b200 import config
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 bad = 0
@@ -20,7 +21,7 @@ for (nc, nls, ng, d, m) in [(40, 640, 384, 6, 300), (9, 1500, 256, 16, 129), (3,
     hp[:, 0] = 1.0; hp[:, 1:d + 1] = 2.0 / math.sqrt(d); hp[:, d + 1] = 0.3
     cov = P.Compose([P.Squared_exponential(), P.White_noise()])
     for share in ("1", "0"):
-        os.environ["PYGPR_GRBCM_SHARE"] = share
+        config.options.share = share != "0"
         ref = None
         for r in range(reps):
             model = P.GRBCM(xl, yl, xg, yg, cov)

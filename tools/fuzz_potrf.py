@@ -4,6 +4,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from pygpr_b200 import engine as eng
+from pygpr_b200 import config
 
 g = torch.Generator(device="cuda").manual_seed(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 worst = 0.0
@@ -14,7 +15,7 @@ for case in range(int(sys.argv[2]) if len(sys.argv) > 2 else 30):
     K = A @ A.transpose(1, 2) / (n + 8) + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")
     Lref = torch.linalg.cholesky(K)
     for mode in ("auto", "columns", "columns1", "dataflow"):
-        os.environ["PYGPR_POTRF_MODE"] = mode
+        config.set_potrf_mode(mode)
         npad = eng.round_up(n, 128)
         buf = torch.zeros(B, npad, npad, dtype=torch.float64, device="cuda")
         buf[:, :n, :n] = K
@@ -25,7 +26,7 @@ for case in range(int(sys.argv[2]) if len(sys.argv) > 2 else 30):
         e2 = float((ldh - Lref.diagonal(dim1=-2, dim2=-1).log().sum(-1)).abs().max() / max(1.0, float(ldh.abs().max())))
         worst = max(worst, e, e2)
         assert e < 1e-10 and e2 < 1e-12, (case, mode, B, n, e, e2)
-    os.environ["PYGPR_POTRF_MODE"] = "auto"
+    config.set_potrf_mode("auto")
     Kinv = eng.spd_inverse(K)
     e3 = float((Kinv @ K - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max())
     worst = max(worst, e3 * 1e-3)

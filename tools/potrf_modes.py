@@ -3,6 +3,7 @@ import math, os, sys
 import torch
 sys.path.insert(0, ".")
 from pygpr_b200 import engine as eng
+from pygpr_b200 import config
 
 
 def data(B, n, d, seed=0):
@@ -15,7 +16,7 @@ def data(B, n, d, seed=0):
 
 
 def fit(mode, x, y, hp, L=None):
-    os.environ["PYGPR_POTRF_MODE"] = mode
+    config.set_potrf_mode(mode)
     return eng.fit(x, y, hp, True, L_out=L)
 
 
@@ -36,8 +37,8 @@ def check(B, n, d):
     buf[:, :n, :n] = K + torch.diag_embed((hp[:, d + 1] ** 2 + 1e-7)[:, None].expand(B, n))
     idx = torch.arange(n, a.npad, device="cuda"); buf[:, idx, idx] = 1.0
     b1, b2 = buf.clone(), buf.clone()
-    os.environ["PYGPR_POTRF_MODE"] = "columns"; r1 = eng.potrf_inplace(b1, None)
-    os.environ["PYGPR_POTRF_MODE"] = "dataflow"; r2 = eng.potrf_inplace(b2, None)
+    config.set_potrf_mode("columns"); r1 = eng.potrf_inplace(b1, None)
+    config.set_potrf_mode("dataflow"); r2 = eng.potrf_inplace(b2, None)
     torch.cuda.synchronize()
     print("   inplace dL", float(((b1 - b2) * tril).abs().max()), "vs gen", float(((b1 - a.L) * tril).abs().max()), flush=True)
 

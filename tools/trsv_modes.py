@@ -4,6 +4,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from pygpr_b200 import engine as eng, _lib
+from pygpr_b200 import config
 from potrf_modes import data
 
 for B, n, d in [(1, 16384, 8), (1, 4096, 16), (8, 8192, 16), (32, 8192, 16), (63, 4096, 8), (120, 4096, 8)]:
@@ -14,7 +15,7 @@ for B, n, d in [(1, 16384, 8), (1, 4096, 16), (8, 8192, 16), (32, 8192, 16), (63
     work = torch.empty(int(_lib.load().gpr_trsv_work_bytes(B)), dtype=torch.uint8, device="cuda")
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     for mode in ("single", "auto"):
-        os.environ["PYGPR_TRSV_MODE"] = mode
+        config.set_trsv_mode(mode)
         best = 1e9
         for _ in range(4):
             e0.record()
