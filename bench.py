@@ -122,60 +122,64 @@ def measure_dgemm_peak(dev):
     return 2.0 * n ** 3 / best * 1e-9
 
 
-def cpu_sample(w, m_s=256, nc_s=2):
-    """Bounded CPU sample of the same workload through the oracle: nc_s local experts + the communication expert,
-    m_s test points; returns (fit_s, predict_s) for the sample."""
-    from oracle import pygpr_oracle as orc
+L2_NOTE = ("no flush: every step streams this rank's expert factors (137 GB at config 4 on one GPU, 17 GB per GPU on eight: far "
+           "beyond the 126 MB L2), so no input of a step survives in L2 from the previous one")
+
+
+def config_of(w, m):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": w["name"], "m_per_step": m, "l2": L2_NOTE}
+
+
+def cpu_sample(w, m_s, nc_s):
+    """Bounded CPU sample of the same workload: the first nc_s local experts + the communication expert, m_s test points,
+    through the UNMODIFIED reference when a copy is importable (baseline/_ref; kind "reference"), else the oracle port."""
+    import warnings
+    from oracle import cpu_arm
+    warnings.simplefilter("ignore")
     xl, yl, xg, yg = make_data(w)
     d = w["d"]
-    xl, yl = xl[:nc_s], yl[:nc_s]
-    hp_l, hp_g = make_hp(nc_s, d), make_hp(1, d)[0]
-    xs = test_points(m_s, d)
-    spec = ["se", "wn"]
-    t0 = time.perf_counter()
-    fits = orc.grbcm_fit(spec, hp_g, hp_l, xl, yl, xg, yg, expert_chunk=1)
-    t1 = time.perf_counter()
-    out = orc.grbcm_predict(spec, hp_g, hp_l, xl, yl, xg, yg, xs, expert_chunk=1, fits=fits)
-    t2 = time.perf_counter()
-    return t1 - t0, t2 - t1, fits, (xl, yl, xg, yg, hp_g, hp_l)
+    cs = cpu_arm.CpuSample(xl[:nc_s].clone(), yl[:nc_s].clone(), xg, yg, make_hp(nc_s, d), make_hp(1, d)[0])
+    cs.fit()
+    return cs
+
+
+def scale_to_job(w, nc_s):
+    """Local experts are equal-sized and independent: the whole job costs the sample times the N^2 work ratio."""
+    nc = w["M_sub"] - 1
+    n_l, n_g = 2 * w["m0"], w["m0"]
+    return (nc * n_l ** 2 + n_g ** 2) / float(nc_s * n_l ** 2 + n_g ** 2)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port: /root/reference is Python and cannot be compiled
-    into oracle/_ref, nor does it exist on the GPU box) on the host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (the unmodified package from
+    baseline/_ref driven through its public API; the oracle port only if no copy is present), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import pygpr_oracle as orc
     w = workload(args.small)
     nc = w["M_sub"] - 1
-    nc_s, m_s = (4, 4096) if not args.small else (4, 256)
+    nc_s, m_s = (8, args.m) if not args.small else (4, min(args.m, 256))
     torch.set_num_threads(os.cpu_count() or 1)
-    fit_s, _, fits, (xl, yl, xg, yg, hp_g, hp_l) = cpu_sample(w, m_s, nc_s)
+    cs = cpu_sample(w, m_s, nc_s)
     xs = test_points(m_s, w["d"])
-    spec = ["se", "wn"]
-
-    def step():
-        orc.grbcm_predict(spec, hp_g, hp_l, xl, yl, xg, yg, xs, expert_chunk=1, fits=fits)
-
     for _ in range(args.warmup):
-        step()
+        cs.predict(xs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        cs.predict(xs)
     dt = (time.perf_counter() - t0) / args.steps
-    # scale the sample to the whole job: local experts are equal-sized and independent (BASELINE.md §3)
-    n_l, n_g = 2 * w["m0"], w["m0"]
-    work_full = nc * n_l ** 2 + n_g ** 2
-    work_s = nc_s * n_l ** 2 + n_g ** 2
-    value = m_s / (dt * work_full / work_s)
-    sample = ("%d of %d local experts + communication expert, %d test points per step; predictions/s scaled by the "
-              "N^2 work ratio %.1f to the whole job" % (nc_s, nc, m_s, work_full / work_s))
+    ratio = scale_to_job(w, nc_s)
+    value = m_s / (dt * ratio)
+    sample = ("%s: %d of %d local experts (chunks of 2) + communication expert, %d test points per step, factors resident; "
+              "predictions/s scaled by the N^2 work ratio %.2f to the whole job" %
+              ("unmodified reference (baseline/_ref) through GRBCM / Exact_GP.predict / aggregate" if cs.kind == "reference"
+               else "oracle port (no reference copy present)", nc_s, nc, m_s, ratio))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": w["name"], "m_per_step": m_s},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
-                             "fit_s_sample": fit_s},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(w, m_s),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cs.kind, "sample": sample,
+                             "fit_s_sample": cs.fit_s},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
@@ -260,6 +264,7 @@ def main():
     xs_dev = xs_host.to(dev)
 
     pk_ms = []
+    last = {}
 
     def step_device():
         # communication expert on a side stream, local experts on this one (engine.predict_pair); k0..k1 brackets the
@@ -269,6 +274,7 @@ def main():
         (mg, vg), (ml, vl) = eng.predict_pair(model.gpg._state, st, xs_dev)
         k1.record()
         pk_ms.append((k0, k1))
+        last.update(mg=mg, vg=vg, ml=ml, vl=vl)
         S, _, _ = eng.grbcm_partial(ml, vl, vg[0], lo)
         gdist.all_reduce_sum_(S)
         return eng.grbcm_finalize(S, mg[0], vg[0])[:2]
@@ -308,6 +314,10 @@ def main():
         grad_ms = max_over_ranks(e0.elapsed_time(e1))
         assert bool(torch.isfinite(g).all())
 
+    # checksum of the aggregate, identical on every rank after the all-reduce: equal across N = 1/2/4/8 to ~1e-12 means the
+    # sharded aggregation reproduces the single-GPU one (the driver-side multi-GPU parity check)
+    agg_checksum = [float(mu.sum()), float(var.sum())]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,16 +340,17 @@ def main():
             "kernel_ms": kern_ms, "flops_per_launch": pred_flops_kernel}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": w["name"], "m_per_step": m, "experts_per_rank": nc_loc,
-                                            "l2": "per-step working set (factors %.1f GB) exceeds the 126 MB L2" % (nc_loc * n_l * n_l * 8 / 1e9),
-                                            "parallelism": "experts sharded over %d GPU(s); all-reduce of [3,m] sums" % world,
-                                            "shared_leading_block": shared},
+            "data": "synthetic", "config": config_of(w, m),
+            "run": {"experts_per_rank": nc_loc, "parallelism": "experts sharded over %d GPU(s); all-reduce of [3,m] sums" % world,
+                    "shared_leading_block": shared, "factors_gb_this_rank": nc_loc * n_l * n_l * 8 / 1e9},
             "roofline": roof,
             "fit": {"ms": fit_ms, "tflops": fit_flops / fit_ms * 1e-9, "frac_of_peak": fit_flops / fit_ms * 1e-9 / (peak_tf * world),
                     "flops": fit_flops, "unshared_count_tflops": fit_flops_unshared / fit_ms * 1e-9,
                     "what": "batched Cholesky incl. kernel build, forward+backward solve; N^3/3 per expert, minus the shared "
                             "communication block (n_g^3/3 per expert) when one hyper-parameter vector is shared"},
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "gpu_launches": launches, "agg_checksum": agg_checksum,
+            # bytes that really cross PCIe per e2e step: the pinned test points in, the two result vectors out (the per-expert
+            # [nc, m] means / variances stay on the device, gr_bcm.GRBCM._aggregate_device)
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m * d * 8, "d2h_bytes_per_step": 2 * m * 8,
                     "ms_per_step": e2e_ms}}
     if grad_ms is not None:
@@ -351,19 +362,43 @@ def main():
                                     "communication block's share (2 n_g^3/3 per expert) when one hyper-parameter vector is shared",
                             "cholesky_plus_grad_tflops": (gflops + fit_flops) / (grad_ms + fit_ms) * 1e-9}
     if not args.no_cpu_baseline:
+        # ---- CPU arm on a bounded sample + PARITY of this run's GPU results against it ---------------------------------------
+        # rank 0 owns local experts 0..nc_s-1 at every N (contiguous shards), so the same experts are compared in every SCALE line
+        from oracle import cpu_arm
         torch.set_num_threads(os.cpu_count() or 1)
-        nc_s, m_s = (4, 4096) if not args.small else (4, 256)
-        fit_s, pred_s, _, _ = cpu_sample(w, m_s, nc_s)
-        work_full = nc_total * n_l ** 2 + n_g ** 2
-        work_s = nc_s * n_l ** 2 + n_g ** 2
-        line["cpu_baseline"] = {"value": m_s / (pred_s * work_full / work_s), "unit": UNIT, "cores": torch.get_num_threads(),
-                                "kind": "port",
-                                "sample": "oracle (torch-CPU restatement of the reference): %d of %d local experts + comm expert, %d test "
-                                          "points, predict %.2f s (fit %.2f s); scaled by the N^2 work ratio %.1f" %
-                                          (nc_s, nc_total, m_s, pred_s, fit_s, work_full / work_s)}
+        nc_s = min(8 if not args.small else 4, nc_loc - nc_loc % 2)
+        cs = cpu_sample(w, m, nc_s)
+        xs_cpu = xs_host.clone()
+        cs.predict(xs_cpu)                                     # warm-up
+        t0 = time.perf_counter(); ref = cs.predict(xs_cpu); pred_s = time.perf_counter() - t0
+        ratio = scale_to_job(w, nc_s)
+        line["cpu_baseline"] = {"value": m / (pred_s * ratio), "unit": UNIT, "cores": torch.get_num_threads(), "kind": cs.kind,
+                                "sample": "%s: %d of %d local experts + comm expert, %d test points, predict %.2f s (fit %.2f s); "
+                                          "scaled by the N^2 work ratio %.2f" %
+                                          ("unmodified reference (baseline/_ref)" if cs.kind == "reference" else "oracle port", nc_s,
+                                           nc_total, m, pred_s, cs.fit_s, ratio)}
+        ml_g, vl_g = last["ml"][:nc_s], last["vl"][:nc_s]
+        S_s, _, _ = eng.grbcm_partial(ml_g.contiguous(), vl_g.contiguous(), last["vg"][0], 0)
+        mu_s, var_s = eng.grbcm_finalize(S_s, last["mg"][0], last["vg"][0])[:2]
+        nl_g_ref, nl_l_ref = cs.nlml()
+        gr_ref = cs.grad_comm()
+        _, gr_gpu = P.MLE(model.gpg).loss_and_grad(make_hp(1, d)[0].numpy())
+        par = {"vs": cs.kind, "experts": nc_s, "test_points": m, "tolerance": 1e-8, "metric": "max|a-b| / max|b|",
+               "mean_expert": cpu_arm.rel_err(ml_g.cpu(), ref["mean_l"]), "var_expert": cpu_arm.rel_err(vl_g.cpu(), ref["var_l"]),
+               "mean_comm": cpu_arm.rel_err(last["mg"][0].cpu(), ref["mean_g"]), "var_comm": cpu_arm.rel_err(last["vg"][0].cpu(), ref["var_g"]),
+               "mean_aggregate_sample": cpu_arm.rel_err(mu_s.cpu(), ref["mu"]), "var_aggregate_sample": cpu_arm.rel_err(var_s.cpu(), ref["var"]),
+               "nlml_expert": cpu_arm.rel_err(st.nlml()[:nc_s].cpu(), nl_l_ref),
+               "nlml_comm": abs(float(model.gpg._state.nlml()[0]) - nl_g_ref) / abs(nl_g_ref),
+               "grad_comm": cpu_arm.rel_err(gr_gpu, gr_ref)}
+        par["worst"] = max(v for k, v in par.items() if k.startswith(("mean", "var", "nlml", "grad")))
+        par["ok"] = par["worst"] <= par["tolerance"]
+        line["parity"] = par
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if "parity" in line and not line["parity"]["ok"]:
+        sys.stderr.write("bench.py: PARITY FAILED against the CPU arm: %r\n" % (line["parity"],))
+        return 3
     return 0
 
 

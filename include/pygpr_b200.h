@@ -278,7 +278,9 @@ int grbcm_full_combine(const double* Kinv, const double* beta, int nc1, int m, d
 /* ---- dense path: model-level support for ANY Covar composition (covar.py:28-81), kernel matrices materialised ---------------- */
 /*
  * V^T = Ks X^T with X = L^-1 (gpr_tril_inverse) for materialised cross-covariances Ks [B, mpad, npad] (zero padded,
- * mpad = ceil(m/128)*128):  mean = V^T z = Ks alpha (gpr.py:79-85), var = prior_b - |V|^2 (gpr.py:96-106), vt [B, mpad, npad].
+ * mpad = ceil(m/128)*128):  mean = V^T z = Ks alpha (gpr.py:79-85), var = prior[b, i] - |V_i|^2 (gpr.py:96-106), vt [B, mpad, npad].
+ * prior [B, m] is the prior variance k(x*_i, x*_i) PER TEST POINT — diag(cov.kernel(params, xp)), gpr.py:98,102 — so that
+ * non-stationary compositions of the Covar protocol are handled like the reference handles them.
  */
 int gpr_predict_dense(const double* X, const double* Ks, const double* z, const double* prior, int B, int npad, int m,
                       double* mean, double* var, double* vt, void* scratch, void* stream);
@@ -309,15 +311,19 @@ int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay,
  *   gpr_ozaki_split      X [rows, k] (leading dimension ld) -> planes [slices][rpad][kpad] int8 + scale [rpad]
  *                        (rpad = gpr_ozaki_rows_padded(rows), kpad = gpr_ozaki_k_padded(k); planes of
  *                        gpr_ozaki_planes_bytes bytes; padding rows/columns are zero)
- *   gpr_ozaki_gemm_nt    both operands split with the SAME slices and k;  b_lower != 0: B[j, k] = 0 for k > j (a lower
- *                        triangular B, e.g. L^-1) and the zero k-blocks are skipped;  K * slices < 2^17 (int32 headroom)
+ *   gpr_ozaki_gemm_nt    both operands split with the SAME slices and k;  b_lower = -1: dense B;  b_lower = o >= 0:
+ *                        B[j, k] = 0 for k > j + o (a lower-triangular / lower-trapezoidal B, e.g. rows of L^-1) and the zero
+ *                        k-blocks are skipped;  K * slices < 2^17 (int32 headroom).  batch > 1: `batch` independent products
+ *                        in one launch — the plane arrays hold the operands of all batch entries stacked along the (padded)
+ *                        row dimension (split the stacked matrices; rows must then be multiples of 128), C at c_batch_stride.
  */
 long long gpr_ozaki_rows_padded(int rows);
 long long gpr_ozaki_k_padded(int k);
 long long gpr_ozaki_planes_bytes(int rows, int k, int slices);
 int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, void* planes, double* scale, void* stream);
 int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
-                      int K, int slices, int b_lower, double beta, double* C, long long ldc, void* stream);
+                      int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch, long long c_batch_stride,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ SIGNATURES = {
     "gpr_ozaki_k_padded": (c_longlong, [_I]),
     "gpr_ozaki_planes_bytes": (c_longlong, [_I, _I, _I]),
     "gpr_ozaki_split": (c_int, [_P, _LL, _I, _I, _I, _P, _P, _P]),
-    "gpr_ozaki_gemm_nt": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, c_double, _P, _LL, _P]),
+    "gpr_ozaki_gemm_nt": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, c_double, _P, _LL, _I, _LL, _P]),
 }
 
 _lib = None

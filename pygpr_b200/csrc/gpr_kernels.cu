@@ -2244,24 +2244,26 @@ vt_gemm_kernel(const double* __restrict__ Ks, const double* __restrict__ X, cons
 
 __global__ void vt_finalize_kernel(const double* __restrict__ pv, const double* __restrict__ pm, const double* __restrict__ prior,
                                    int nt, int mpad, int m, double* __restrict__ mean, double* __restrict__ var, int gt_part,
-                                   double* __restrict__ mean_part, double* __restrict__ var_part) {
+                                   double* __restrict__ mean_part, double* __restrict__ var_part, int prior_per_point = 0) {
     const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
+    // prior variance k(x*, x*): one value per expert (stationary kernels) or one per test point (gpr.py:98,102 in general)
+    const double pr = prior_per_point ? prior[(long long)b * m + r] : prior[b];
     double sm = 0.0, sv = 0.0;
     for (int j = 0; j < nt; ++j) {
         if (j == gt_part && mean_part) {  // the part of the sums that belongs to the first gt_part block rows (the shared ones)
             mean_part[(long long)b * m + r] = sm;
-            var_part[(long long)b * m + r] = prior[b] - sv;
+            var_part[(long long)b * m + r] = pr - sv;
         }
         sm += pm[((long long)b * nt + j) * mpad + r];
         sv += pv[((long long)b * nt + j) * mpad + r];
     }
     if (gt_part >= nt && mean_part) {
         mean_part[(long long)b * m + r] = sm;
-        var_part[(long long)b * m + r] = prior[b] - sv;
+        var_part[(long long)b * m + r] = pr - sv;
     }
     mean[(long long)b * m + r] = sm;
-    var[(long long)b * m + r] = prior[b] - sv;
+    var[(long long)b * m + r] = pr - sv;
 }
 
 static inline long long predict_gemm_layout(int B, int npad, int dpad, int mpad, long long* o_nrm, long long* o_ks, long long* o_pv,
@@ -2316,7 +2318,7 @@ extern "C" int gpr_predict_gemm(const double* X, const double* a, const double* 
 // Dense path: any covariance the Covar protocol can express (e.g. Compose([SE, SE, WN]), covar.py:28-81) at the model level.
 // The kernel matrices come materialised from the kernel-level entry points (gpr_se_build / gpr_se_cross summed by the host
 // layer, as Compose.kernel does), K is factorised in place (gpr_potrf_batched, gen = 0), and
-//   gpr_predict_dense : V^T = K* X^T with X = L^-1 (vt_gemm_kernel), mean = V^T z = K* alpha, var = prior - |V|^2   gpr.py:76-106
+//   gpr_predict_dense : V^T = K* X^T with X = L^-1 (vt_gemm_kernel), mean = V^T z = K* alpha, var = prior[b, i] - |V_i|^2   gpr.py:76-106
 //   gpr_covar_dense   : cov = K** - V^T V                                                                            gpr.py:108-120
 //   gpr_trace_grad    : grad_p = 1/2 sum_ij (K^-1 - alpha alpha^T)_ij dK_p,ij  with dK materialised like the reference  loss.py:77-84
 // O(P n^2) memory like the reference — the fused path above is the one for large n.
@@ -2335,7 +2337,7 @@ extern "C" int gpr_predict_dense(const double* X, const double* Ks, const double
     double* pm = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + align256((long long)B * nt * mpad * 8));
     CUDA_TRY(opt_in_smem(vt_gemm_kernel, MAIN_SMEM_BYTES));
     vt_gemm_kernel<<<dim3(nt, mpad / TILE, B), NTHREADS, MAIN_SMEM_BYTES, st>>>(Ks, X, z, npad, mpad, vt, pv, pm);
-    vt_finalize_kernel<<<dim3((m + 127) / 128, B), 128, 0, st>>>(pv, pm, prior, nt, mpad, m, mean, var, 0, nullptr, nullptr);
+    vt_finalize_kernel<<<dim3((m + 127) / 128, B), 128, 0, st>>>(pv, pm, prior, nt, mpad, m, mean, var, 0, nullptr, nullptr, 1);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }

@@ -214,7 +214,8 @@ template <int S>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ C, long long ldc,
-            int M, int N, int kpad, int stages, int b_lower, double beta, int group_m, int tmem_cols) {
+            int M, int N, int kpad, int stages, int b_lower, double beta, int group_m, int tmem_cols,
+            int a_batch_rows, int b_batch_rows, long long c_batch_stride) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled tiles want (at least) 512 B alignment
@@ -236,9 +237,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int gsz = min(tiles_m - first_m, group_m);
     const int tm = first_m + in_group % gsz;
     int tn = in_group / gsz;
-    if (b_lower) tn = tiles_n - 1 - tn;
+    if (b_lower >= 0) tn = tiles_n - 1 - tn;
     int nkb = kpad / BK;
-    if (b_lower) nkb = min(nkb, ((tn + 1) * BN + BK - 1) / BK);   // B[j, k] = 0 for k > j
+    if (b_lower >= 0) nkb = min(nkb, (b_lower + (tn + 1) * BN + BK - 1) / BK);   // B[j, k] = 0 for k > j + b_lower
+    // batched product: batch entry blockIdx.y owns a_batch_rows / b_batch_rows consecutive (padded) rows of the plane arrays
+    const int a_row0 = blockIdx.y * a_batch_rows + tm * BM, b_row0 = blockIdx.y * b_batch_rows + tn * BN;
+    scaleA += (long long)blockIdx.y * a_batch_rows;
+    scaleB += (long long)blockIdx.y * b_batch_rows;
+    C += (long long)blockIdx.y * c_batch_stride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -272,8 +278,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 const uint32_t full = bar_full + 8u * stage;
                 const uint32_t dst = base + (uint32_t)(stage * sbytes);
                 mbar_expect_tx(full, (uint32_t)sbytes);
-                tma_load_3d(dst, &mapA, full, kb * BK, tm * BM, 0);
-                tma_load_3d(dst + (uint32_t)(S * A_PLANE), &mapB, full, kb * BK, tn * BN, 0);
+                tma_load_3d(dst, &mapA, full, kb * BK, a_row0, 0);
+                tma_load_3d(dst + (uint32_t)(S * A_PLANE), &mapB, full, kb * BK, b_row0, 0);
             }
             __syncwarp();
             if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -393,8 +399,10 @@ extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, i
 }
 
 extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
-                                 int K, int slices, int b_lower, double beta, double* C, long long ldc, void* stream) {
-    if (!(planesA && planesB && scaleA && scaleB && C && M > 0 && N > 0 && K > 0 && ldc >= N && slices >= 1 && slices <= oz::MAX_SLICES))
+                                 int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch,
+                                 long long c_batch_stride, void* stream) {
+    if (!(planesA && planesB && scaleA && scaleB && C && M > 0 && N > 0 && K > 0 && ldc >= N && slices >= 1 && slices <= oz::MAX_SLICES &&
+          batch >= 1 && batch <= 65535 && b_lower >= -1))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_gemm_nt%s (slices=%lld)", "", slices);
     // int32 headroom of a diagonal: (g+1) products of |q| <= 128 over K terms
     if ((long long)K * slices * 16384LL >= (1LL << 31))
@@ -402,9 +410,9 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
     const int kpad = oz::round_up(K, oz::BK);
     const int rpadA = oz::round_up(M, oz::BM), rpadB = oz::round_up(N, oz::BM);
     CUtensorMap mapA, mapB;
-    int rc = oz::make_map(&mapA, planesA, rpadA, kpad, slices, oz::BM);
+    int rc = oz::make_map(&mapA, planesA, rpadA * batch, kpad, slices, oz::BM);
     if (rc != GPR_OK) return rc;
-    rc = oz::make_map(&mapB, planesB, rpadB, kpad, slices, oz::BN);
+    rc = oz::make_map(&mapB, planesB, rpadB * batch, kpad, slices, oz::BN);
     if (rc != GPR_OK) return rc;
     const int sbytes = oz::stage_bytes(slices);
     int stages = (oz::SMEM_LIMIT - 2048) / sbytes;
@@ -420,8 +428,9 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
     case S:                                                                                                                    \
         e = cudaFuncSetAttribute(oz::gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
         if (e == cudaSuccess)                                                                                                  \
-            oz::gemm_kernel<S><<<tiles_m * tiles_n, oz::NTHREADS, smem, (cudaStream_t)stream>>>(                                \
-                mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols);                    \
+            oz::gemm_kernel<S><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                   \
+                mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA, rpadB,       \
+                c_batch_stride);                                                                                               \
         break;
     switch (slices) {
         OZ_LAUNCH(1) OZ_LAUNCH(2) OZ_LAUNCH(3) OZ_LAUNCH(4) OZ_LAUNCH(5) OZ_LAUNCH(6) OZ_LAUNCH(7) OZ_LAUNCH(8)

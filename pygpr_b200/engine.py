@@ -646,8 +646,10 @@ def fit_dense(K: torch.Tensor, y: torch.Tensor, want_alpha: bool = True) -> Dens
 
 def predict_dense(st: DenseState, Ks: torch.Tensor, prior: torch.Tensor, Kss: Optional[torch.Tensor] = None):
     """mean [B, m], variance [B, m] (and the full covariance when Kss [B, m, m] is given) from materialised cross-covariances
-    Ks [B, m, n]: gpr.py:76-120 with V^T = K* L^-T as a triangular GEMM against the cached L^-1."""
+    Ks [B, m, n] and the prior variance PER TEST POINT prior [B, m] (= diag cov.kernel(params, xp), gpr.py:98,102):
+    gpr.py:76-120 with V^T = K* L^-T as a triangular GEMM against the cached L^-1."""
     B, m, n = Ks.shape
+    assert prior.shape == (B, m)
     dev = Ks.device
     lib = _lib.load()
     mpad = round_up(m, TILE)

@@ -154,10 +154,16 @@ class Exact_GP(GPR):
         Ks = self.cov.kernel(hp, x, xs).reshape(B, m, n)                                    # gpr.py:79
         if full:
             Kss = self.cov.kernel(hp, xs.expand(B, -1, -1) if B > 1 else xs).reshape(B, m, m)  # gpr.py:110
-            prior = torch.diagonal(Kss, dim1=-2, dim2=-1)[:, 0].contiguous()
+            prior = torch.diagonal(Kss, dim1=-2, dim2=-1).contiguous()
         else:
-            Kss = None                                                                      # gpr.py:98 builds [m, m] for its diagonal;
-            prior = self.cov.kernel(hp, xs[:1].expand(B, -1, -1) if B > 1 else xs[:1]).reshape(B)  # stationary kernels: one point is enough
+            # gpr.py:98 builds the whole [m, m] matrix for its diagonal; here the diagonal is taken block by block (128 test
+            # points at a time), PER TEST POINT: the Covar protocol also admits non-stationary kernels
+            Kss = None
+            prior = torch.empty(B, m, dtype=Ks.dtype, device=Ks.device)
+            for s in range(0, m, 128):
+                blk = xs[s:s + 128]
+                kb = self.cov.kernel(hp, blk.expand(B, -1, -1) if B > 1 else blk).reshape(B, blk.shape[0], blk.shape[0])
+                prior[:, s:s + 128] = torch.diagonal(kb, dim1=-2, dim2=-1)
         return engine.predict_dense(self._state, Ks, prior, Kss)
 
     def predict(self, xp: Tensor, var: str = "full") -> Sequence[Tensor]:

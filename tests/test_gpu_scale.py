@@ -144,3 +144,55 @@ def test_grbcm_shard_sum_equals_full_sum_at_scale():
     assert_close(mu2.cpu().numpy(), torch.as_tensor(mu).cpu().numpy(), 1e-12, "mu_A sharded")
     assert_close(var2.cpu().numpy(), torch.as_tensor(var).cpu().numpy(), 1e-12, "var_A sharded")
     assert bool((var2 > 0).all())
+
+
+def test_benchmarked_grbcm_path_against_oracle(monkeypatch):
+    """The code path bench.py times, at its per-expert sizes: communication set 4096 (32 shared block columns), local blocks 4096
+    (expert order 8192), d = 16, one shared hyper-parameter vector -> gpr_potrf_grbcm (one dataflow launch for both
+    factorisations) + gpr_predict_gemm / gpr_predict_shared.  Checked against the CPU ORACLE (gr_bcm.py:19-29,116-155,
+    gpr.py:65-106, loss.py:49-51) for the communication expert and two local experts, incl. the aggregate over those two, and
+    against the general (unshared) path for all six."""
+    import pygpr_b200 as P
+    from pygpr_b200 import config
+    from oracle import pygpr_oracle as orc
+    g = torch.Generator().manual_seed(31)
+    nc, m0, d, m = 6, 4096, 16, 384
+    xall = torch.rand(nc + 1, m0, d, generator=g, dtype=torch.float64)
+    yall = torch.sin(xall.sum(-1)) + 0.1 * torch.randn(nc + 1, m0, generator=g, dtype=torch.float64)
+    xs = torch.rand(m, d, generator=g, dtype=torch.float64)
+    hp = torch.empty(nc, d + 2, dtype=torch.float64)
+    hp[:, 0] = 1.0; hp[:, 1:d + 1] = 2.0 / math.sqrt(d); hp[:, d + 1] = 0.3
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+
+    def run(share):
+        monkeypatch.setattr(config.options, "share", share)
+        mdl = P.GRBCM(xall[1:].contiguous(), yall[1:].contiguous(), xall[0], yall[0], cov)
+        mdl.gpl.set_params(hp); mdl.gpg.set_params(hp[0])
+        mu, var = mdl.predict(xs, var="diag")
+        assert (mdl.gpl._state.shared_from is not None) == share
+        return mdl, mu, var
+
+    mdl, mu, var = run(True)
+    st, stg = mdl.gpl._state, mdl.gpg._state
+    from pygpr_b200 import engine as eng
+    (mg, vg), (ml, vl) = eng.predict_pair(stg, st, xs.cuda())
+    # oracle: communication expert + local experts 0, 1
+    ns = 2
+    mu_o, var_o, parts = orc.grbcm_predict(["se", "wn"], hp[0], hp[:ns], xall[1:1 + ns], yall[1:1 + ns], xall[0], yall[0], xs, expert_chunk=1)
+    assert_close(mg[0].cpu().numpy(), parts["mean_g"].numpy(), TOL, "communication expert mean")
+    assert_close(vg[0].cpu().numpy(), parts["var_g"].numpy(), TOL, "communication expert variance")
+    assert_close(ml[:ns].cpu().numpy(), parts["mean_l"].numpy(), TOL, "local expert means")
+    assert_close(vl[:ns].cpu().numpy(), parts["var_l"].numpy(), TOL, "local expert variances")
+    S, _, _ = eng.grbcm_partial(ml[:ns].contiguous(), vl[:ns].contiguous(), vg[0], 0)
+    mu2, var2 = eng.grbcm_finalize(S, mg[0], vg[0])[:2]
+    assert_close(mu2.cpu().numpy(), mu_o.numpy(), TOL, "aggregate over the two experts (mean)")
+    assert_close(var2.cpu().numpy(), var_o.numpy(), TOL, "aggregate over the two experts (variance)")
+    xa, ya = orc.grbcm_inputs(xall[1:1 + ns], yall[1:1 + ns], xall[0], yall[0])
+    nl_o = torch.cat([orc.mle_loss(["se", "wn"], hp[i:i + 1], xa[i:i + 1], ya[i:i + 1]) for i in range(ns)])
+    assert_close(st.nlml()[:ns].cpu().numpy(), nl_o.numpy(), TOL, "NLML of the local experts")
+    assert_close(stg.nlml().cpu().numpy(), orc.mle_loss(["se", "wn"], hp[:1], xall[:1], yall[:1]).numpy(), TOL, "NLML of the communication expert")
+    # all six experts: shared-block path == general path
+    mdl0, mu0, var0 = run(False)
+    assert_close(torch.as_tensor(mu).numpy(), torch.as_tensor(mu0).numpy(), 1e-10, "shared == general (mean)")
+    assert_close(torch.as_tensor(var).numpy(), torch.as_tensor(var0).numpy(), 1e-10, "shared == general (variance)")
+    assert_close(st.nlml().cpu().numpy(), mdl0.gpl._state.nlml().cpu().numpy(), 1e-11, "shared == general (NLML)")
