@@ -185,6 +185,74 @@ def run_reference(args):
     return 0
 
 
+def train_workload(small: bool):
+    """BASELINE config 5 (reading A): 512 subsets x 8192 points, d = 32 -> local experts of order 16384 + a communication expert of
+    order 8192, P = 34 hyper-parameters, ONE shared vector; 64 local experts per rank (the 8-GPU share of the 511)."""
+    if small:
+        return dict(name="grbcm_train_small_d8: 6 experts/rank of order 1024 + comm 512", per_rank=6, m0=512, d=8)
+    return dict(name="grbcm_train_n4M_d32_512x8192(A): 64 local experts per rank of order 16384 + comm expert of order 8192, P=34",
+                per_rank=64, m0=8192, d=32)
+
+
+def run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf):
+    """One evaluation of the summed NLML and its gradient at one shared hyper-parameter vector through the PUBLIC training API
+    (GRBCM_MLE.loss_and_grad -> MLE -> gpr_potrf_batched_shared + gpr_lml_grad_shared, experts in HBM-sized chunks, [1+P]
+    all-reduce over the ranks): the inner step of config 5's training loop (loss.py:92-128, hp_update.py:6-28)."""
+    tw = train_workload(args.small)
+    per, m0, d = tw["per_rank"], tw["m0"], tw["d"]
+    g = torch.Generator().manual_seed(100 + rank)
+    xl = torch.rand(per, m0, d, generator=g, dtype=torch.float64)
+    yl = torch.sin(xl.sum(-1)) + 0.1 * torch.randn(per, m0, generator=g, dtype=torch.float64)
+    g0 = torch.Generator().manual_seed(99)                   # the communication set is the same on every rank
+    xg = torch.rand(m0, d, generator=g0, dtype=torch.float64)
+    yg = torch.sin(xg.sum(-1)) + 0.1 * torch.randn(m0, generator=g0, dtype=torch.float64)
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+    model = P.GRBCM(xl.to(dev), yl.to(dev), xg.to(dev), yg.to(dev), cov, expert_offset=rank * per, nc_total=per * world)
+    theta = make_hp(1, d)[0]
+    mle = P.GRBCM_MLE(model)                                  # chunk = what fits in the free HBM
+    mle.set_params(theta)
+    chunk = mle._auto_chunk()
+    mle.loss(theta.numpy())                                   # warm-up: allocations, kernel loading
+    barrier(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); f_loss = mle.loss(theta.numpy()); e1.record(); barrier()
+    loss_ms = max_over_ranks(e0.elapsed_time(e1))
+    barrier(); e0.record(); f, grad = mle.loss_and_grad(theta.numpy()); e1.record(); barrier()
+    lg_ms = max_over_ranks(e0.elapsed_time(e1))
+    assert math.isfinite(f) and bool(torch.isfinite(torch.from_numpy(grad)).all()) and abs(f - f_loss) <= 1e-9 * abs(f)
+    n_l, n_g = 2.0 * m0, float(m0)
+    nc_total = per * world
+    # executed flops: Cholesky (n^3 - ng^3)/3 + L^-T and K^-1/gradient 2 (n^3 - ng^3)/3 per local expert (shared leading block),
+    # + the replicated communication expert's n_g^3 on every rank; SURVEY 8(d)'s count N^3 per expert beside it
+    flops = nc_total * (n_l ** 3 - n_g ** 3) + world * n_g ** 3
+    flops_unshared = nc_total * n_l ** 3 + world * n_g ** 3
+    out = {"workload": tw["name"], "experts_per_rank": per, "experts_total": nc_total, "chunk_experts": chunk, "P": d + 2,
+           "loss_and_grad_ms": lg_ms, "loss_ms": loss_ms, "tflops": flops / lg_ms * 1e-9, "frac_of_peak": flops / lg_ms * 1e-9 / (peak_tf * world),
+           "unshared_count_tflops": flops_unshared / lg_ms * 1e-9, "nlml": f, "grad_norm": float((grad * grad).sum() ** 0.5),
+           "collective": "all_reduce(sum, f64) of [1+P] = %d doubles per evaluation over %d rank(s)" % (1 + d + 2, world),
+           "what": "GRBCM_MLE.loss_and_grad at one shared hyper-parameter vector, wall time of the public call incl. host->device "
+                   "staging of each expert chunk and the [1+P] read-back"}
+    del mle, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def train_parity(P, small):
+    """Config-5 shape at reduced N against the CPU arm (the unmodified reference when present): GRBCM_MLE's summed NLML and
+    gradient for 2 local experts + communication expert, d = 32 (d = 8 for --small)."""
+    from oracle import cpu_arm
+    d, m0 = (8, 256) if small else (32, 1024)
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(3, m0, d, generator=g, dtype=torch.float64)
+    y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(3, m0, generator=g, dtype=torch.float64)
+    theta = make_hp(1, d)[0]
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+    model = P.GRBCM(x[1:], y[1:], x[0], y[0], cov)
+    f, grad = P.GRBCM_MLE(model, chunk=1).loss_and_grad(theta.numpy())
+    cs = cpu_arm.CpuSample(x[1:], y[1:], x[0], y[0], theta.repeat(2, 1), theta)
+    f_ref, g_ref = cs.loss_and_grad_sum()
+    return {"vs": cs.kind, "experts": 2, "order": 2 * m0, "d": d, "nlml": abs(f - f_ref) / abs(f_ref), "grad": cpu_arm.rel_err(grad, g_ref)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +263,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="smoke-sized workload (not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-grad", action="store_true", help="skip the LML-gradient timing")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 training evaluation (GRBCM_MLE.loss_and_grad)")
+    ap.add_argument("--emulate", type=int, default=6, help="also time the opt-in emulated-FP64 prediction (INT8 tcgen05 tensor cores) "
+                                                            "with this many digit planes; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -295,6 +366,7 @@ def main():
     kern_ms = max_over_ranks(kern_ms)
     value = m / (step_ms * 1e-3)
     clocks = cs.summary()
+    ml_fp64, vl_fp64, mg_fp64, vg_fp64 = last["ml"], last["vl"], last["mg"], last["vg"]
 
     # ---- e2e: public API, host tensors in and out -------------------------------------------------------------------
     for _ in range(2):
@@ -314,9 +386,65 @@ def main():
         grad_ms = max_over_ranks(e0.elapsed_time(e1))
         assert bool(torch.isfinite(g).all())
 
+    # ---- opt-in emulated-FP64 prediction: the same step with the local experts' products on the INT8 tcgen05 tensor cores -------
+    emu = None
+    if args.emulate > 0 and shared and eng.can_emulate(model.gpg._state, st):
+        from pygpr_b200 import config
+        config.options.emulate_slices = args.emulate
+        barrier(); e0.record(); eng.ensure_inverse_factors(model.gpg._state, st); e1.record(); barrier()
+        prep_ms = max_over_ranks(e0.elapsed_time(e1))        # once per fit: L^-T of every expert (in place)
+        for _ in range(2):
+            step_device()
+        barrier(); e0.record()
+        for _ in range(args.steps):
+            mu_e, var_e = step_device()
+        e1.record(); barrier()
+        emu_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        config.options.emulate_slices = 0
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        emu = {"slices": args.emulate, "plane_products": args.emulate * (args.emulate + 1) // 2, "value": m / (emu_ms * 1e-3), "unit": UNIT,
+               "ms_per_step": emu_ms, "speedup_vs_fp64_path": step_ms / emu_ms, "prepare_ms_once_per_fit": prep_ms,
+               "tflops_equiv": (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m / emu_ms * 1e-9,
+               "aggregate_mean_vs_fp64_path": rel(mu_e, mu), "aggregate_var_vs_fp64_path": rel(var_e, var),
+               "expert_mean_vs_fp64_path": rel(last["ml"], ml_fp64), "expert_var_vs_fp64_path": rel(last["vl"], vl_fp64),
+               "what": "GRBCM.predict with options.emulate_slices: per expert V_l^T = K* X_l^T (X_l = rows of L^-1) as one Ozaki-split "
+                       "GEMM on tcgen05.mma kind::i8 (TMA operand loads, TMEM int32 accumulators, FP64 recombination); opt-in, "
+                       "the headline `value` is the FP64 DMMA path"}
+        emu_last = dict(last)
+        last.update(ml=ml_fp64, vl=vl_fp64, mg=mg_fp64, vg=vg_fp64)
+
     # checksum of the aggregate, identical on every rank after the all-reduce: equal across N = 1/2/4/8 to ~1e-12 means the
     # sharded aggregation reproduces the single-GPU one (the driver-side multi-GPU parity check)
     agg_checksum = [float(mu.sum()), float(var.sum())]
+
+    # ---- everything the parity leg needs from the GPU, taken now: the prediction model's HBM is handed to the training step next ----
+    nc_s = min(8 if not args.small else 4, nc_loc - nc_loc % 2)
+
+    def sample_side(src):
+        """Per-expert values of the first nc_s local experts + their aggregate (through the aggregation KERNELS), on the host."""
+        ml_s, vl_s = src["ml"][:nc_s].contiguous(), src["vl"][:nc_s].contiguous()
+        S_s, _, _ = eng.grbcm_partial(ml_s, vl_s, src["vg"][0], 0)
+        mu_s, var_s = eng.grbcm_finalize(S_s, src["mg"][0], src["vg"][0])[:2]
+        return {"ml": ml_s.cpu(), "vl": vl_s.cpu(), "mg": src["mg"][0].cpu(), "vg": src["vg"][0].cpu(), "mu": mu_s.cpu(), "var": var_s.cpu()}
+
+    gpu_side = None
+    if rank == 0 and not args.no_cpu_baseline:
+        gpu_side = sample_side(last)
+        gpu_side["nlml_l"] = st.nlml()[:nc_s].cpu()
+        gpu_side["nlml_g"] = float(model.gpg._state.nlml()[0])
+        gpu_side["grad_g"] = P.MLE(model.gpg).loss_and_grad(make_hp(1, d)[0].numpy())[1]
+        if emu is not None:
+            gpu_side["emu"] = sample_side(emu_last)
+
+    # ---- config 5: one training evaluation through GRBCM_MLE (all ranks; takes over the HBM the prediction model held) ----------
+    train = None
+    if not args.no_train:
+        del model, st, last, ml_fp64, vl_fp64, mg_fp64, vg_fp64
+        if emu is not None:
+            del emu_last
+        eng.release_scratch()
+        torch.cuda.empty_cache()
+        train = run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf)
 
     if rank != 0:
         if world > 1:
@@ -353,6 +481,10 @@ def main():
             # [nc, m] means / variances stay on the device, gr_bcm.GRBCM._aggregate_device)
             "e2e": {"value": m / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": m * d * 8, "d2h_bytes_per_step": 2 * m * 8,
                     "ms_per_step": e2e_ms}}
+    if emu is not None:
+        line["emulated_fp64"] = emu
+    if train is not None:
+        line["train"] = train
     if grad_ms is not None:
         gflops_unshared = nc_total * float(n_l) ** 3 * 2.0 / 3.0
         gflops = nc_total * (float(n_l) ** 3 - float(n_g) ** 3) * 2.0 / 3.0 if shared else gflops_unshared
@@ -366,7 +498,6 @@ def main():
         # rank 0 owns local experts 0..nc_s-1 at every N (contiguous shards), so the same experts are compared in every SCALE line
         from oracle import cpu_arm
         torch.set_num_threads(os.cpu_count() or 1)
-        nc_s = min(8 if not args.small else 4, nc_loc - nc_loc % 2)
         cs = cpu_sample(w, m, nc_s)
         xs_cpu = xs_host.clone()
         cs.predict(xs_cpu)                                     # warm-up
@@ -377,22 +508,29 @@ def main():
                                           "scaled by the N^2 work ratio %.2f" %
                                           ("unmodified reference (baseline/_ref)" if cs.kind == "reference" else "oracle port", nc_s,
                                            nc_total, m, pred_s, cs.fit_s, ratio)}
-        ml_g, vl_g = last["ml"][:nc_s], last["vl"][:nc_s]
-        S_s, _, _ = eng.grbcm_partial(ml_g.contiguous(), vl_g.contiguous(), last["vg"][0], 0)
-        mu_s, var_s = eng.grbcm_finalize(S_s, last["mg"][0], last["vg"][0])[:2]
         nl_g_ref, nl_l_ref = cs.nlml()
         gr_ref = cs.grad_comm()
-        _, gr_gpu = P.MLE(model.gpg).loss_and_grad(make_hp(1, d)[0].numpy())
+        gs = gpu_side
         par = {"vs": cs.kind, "experts": nc_s, "test_points": m, "tolerance": 1e-8, "metric": "max|a-b| / max|b|",
-               "mean_expert": cpu_arm.rel_err(ml_g.cpu(), ref["mean_l"]), "var_expert": cpu_arm.rel_err(vl_g.cpu(), ref["var_l"]),
-               "mean_comm": cpu_arm.rel_err(last["mg"][0].cpu(), ref["mean_g"]), "var_comm": cpu_arm.rel_err(last["vg"][0].cpu(), ref["var_g"]),
-               "mean_aggregate_sample": cpu_arm.rel_err(mu_s.cpu(), ref["mu"]), "var_aggregate_sample": cpu_arm.rel_err(var_s.cpu(), ref["var"]),
-               "nlml_expert": cpu_arm.rel_err(st.nlml()[:nc_s].cpu(), nl_l_ref),
-               "nlml_comm": abs(float(model.gpg._state.nlml()[0]) - nl_g_ref) / abs(nl_g_ref),
-               "grad_comm": cpu_arm.rel_err(gr_gpu, gr_ref)}
-        par["worst"] = max(v for k, v in par.items() if k.startswith(("mean", "var", "nlml", "grad")))
+               "mean_expert": cpu_arm.rel_err(gs["ml"], ref["mean_l"]), "var_expert": cpu_arm.rel_err(gs["vl"], ref["var_l"]),
+               "mean_comm": cpu_arm.rel_err(gs["mg"], ref["mean_g"]), "var_comm": cpu_arm.rel_err(gs["vg"], ref["var_g"]),
+               "mean_aggregate_sample": cpu_arm.rel_err(gs["mu"], ref["mu"]), "var_aggregate_sample": cpu_arm.rel_err(gs["var"], ref["var"]),
+               "nlml_expert": cpu_arm.rel_err(gs["nlml_l"], nl_l_ref), "nlml_comm": abs(gs["nlml_g"] - nl_g_ref) / abs(nl_g_ref),
+               "grad_comm": cpu_arm.rel_err(gs["grad_g"], gr_ref)}
+        if train is not None:
+            tp = train_parity(P, args.small)
+            train["parity_at_reduced_n"] = tp
+            par["train_nlml_reduced_n"], par["train_grad_reduced_n"] = tp["nlml"], tp["grad"]
+        par["worst"] = max(v for k, v in par.items() if k.startswith(("mean", "var", "nlml", "grad", "train")))
         par["ok"] = par["worst"] <= par["tolerance"]
         line["parity"] = par
+        if emu is not None:
+            ge = gs["emu"]
+            emu["parity"] = {"vs": cs.kind, "experts": nc_s, "mean_expert": cpu_arm.rel_err(ge["ml"], ref["mean_l"]),
+                             "var_expert": cpu_arm.rel_err(ge["vl"], ref["var_l"]),
+                             "mean_aggregate_sample": cpu_arm.rel_err(ge["mu"], ref["mu"]),
+                             "var_aggregate_sample": cpu_arm.rel_err(ge["var"], ref["var"])}
+            emu["parity"]["ok"] = max(v for k, v in emu["parity"].items() if k.startswith(("mean", "var"))) <= 1e-8
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

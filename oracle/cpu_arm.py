@@ -94,6 +94,23 @@ class CpuSample:
         g = orc.mle_loss(SPEC, self.hp_g[None], self.xg[None], self.yg[None])
         return float(g[0]), l.numpy()
 
+    def loss_and_grad_sum(self):
+        """GRBCM training objective at the shared vector: NLML_g + sum_i NLML_i and its gradient (loss.py:92-128 per model; the sum
+        is what gr_bcm.py:36-97 was written to minimise) — for the config-5 parity at reduced N."""
+        if self.kind == "reference":
+            R = self.R
+            f, j = R.MLE(self.models[0].gpg).loss_and_grad(self.hp_g.numpy())
+            f, j = float(f), np.asarray(j, dtype=np.float64).reshape(-1).copy()
+            for i, m in enumerate(self.models):
+                l, g = R.MLE(m.gpl).loss_and_grad(self.hp_l[i * self.chunk:(i + 1) * self.chunk].numpy())
+                f += float(np.sum(l))
+                j += np.asarray(g, dtype=np.float64).reshape(self.chunk, -1).sum(0)
+            return f, j
+        x, y = orc.grbcm_inputs(self.xl, self.yl, self.xg, self.yg)
+        l, g = orc.mle_loss_and_grad_chunked(SPEC, self.hp_l, x, y, chunk=1)
+        lg, gg = orc.mle_loss_and_grad(SPEC, self.hp_g[None], self.xg[None], self.yg[None])
+        return float(l.sum() + lg.sum()), (g.sum(0) + gg[0]).numpy()
+
     def grad_comm(self):
         """NLML gradient of the communication expert (loss.py:92-128) — order ng <= 4096 keeps the reference's dK in RAM."""
         if self.kind == "reference":

@@ -7,6 +7,8 @@ Every knob takes its initial value from the environment ONCE, at import; afterwa
     PYGPR_GRBCM_FUSED_FIT=0    options.fused_fit    fit the communication expert in its own launch
     PYGPR_PREDICT_CHUNK=n      options.predict_chunk  test points per prediction batch of GRBCM.predict
     PYGPR_PREDICT_FORM=...     options.predict_form   auto | subst | gemm  (engine.predict)
+    PYGPR_EMULATE_FP64=s       options.emulate_slices  GRBCM predictions through the emulated-FP64 GEMM with s digit planes (0 = off)
+    PYGPR_EMULATE_CHUNK=e      options.emulate_chunk   experts per batched emulated product
     PYGPR_POTRF_MODE=...       set_potrf_mode()     auto | columns | columns1 | dataflow
     PYGPR_TRSV_MODE=...        set_trsv_mode()      auto | single
 """
@@ -24,6 +26,10 @@ class Options:
     fused_fit: bool = os.environ.get("PYGPR_GRBCM_FUSED_FIT", "1") != "0"
     predict_chunk: int = int(os.environ.get("PYGPR_PREDICT_CHUNK", "16384"))
     predict_form: str = os.environ.get("PYGPR_PREDICT_FORM", "auto")
+    # opt-in: the local experts' prediction products on the INT8 tensor cores with this many digit planes per operand
+    # (0 = off, the FP64 DMMA path; 6 = FP64 grade, ~1e-11 on V; 3-4 = the FP32-grade mode).  engine.predict_shared_emulated
+    emulate_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64", "0"))
+    emulate_chunk: int = int(os.environ.get("PYGPR_EMULATE_CHUNK", "8"))
 
 
 options = Options()

@@ -2195,6 +2195,90 @@ extern "C" int gpr_tril_inverse(double* L, const double* invdiag, int B, int npa
     return GPR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Emulated-FP64 prediction (opt-in, engine.predict_shared_emulated): every local expert's V_l^T = K* X_l^T is ONE GEMM against the
+// rows X_l = (L^-1)[row0:, :] of the explicit inverse, run on the INT8 tensor cores by ozaki_gemm.cu.  The pieces that live here:
+//   gpr_trtri_batched      U = L^-T of every expert, in place in the strict block-upper part of L (block columns < gt — the shared
+//                          communication block — must already hold L_g^-T: gpr_copy_leading_block mode 2)
+//   gpr_tril_inverse_rows  X[b] = rows row0.. of L_b^-1 as a dense row-major [npad - row0, npad] matrix (transposed out of U,
+//                          diagonal blocks from invdiag, zeros right of the diagonal block) — the operand the digit split reads
+//   gpr_vt_reduce          mean_i = mean_g + V_l^T z_l,  var_i = var_g - |V_l|^2 per test point   (gpr.py:80-85,100-104 for an
+//                          expert that extends the communication expert); fixed-order sums, no atomics
+// ---------------------------------------------------------------------------------------------
+extern "C" int gpr_trtri_batched(double* L, const double* invdiag, int B, int npad, void* scratch, void* stream, int gt) {
+    ARG_CHECK(L && invdiag && scratch && B > 0 && npad > 0 && npad % TILE == 0 && gt >= 0 && gt < npad / TILE);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    int sms = gpr_device_sm_count();
+    if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
+    double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + trtri_work_bytes(B, npad, sms));
+    transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
+    return launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st, gt);
+}
+
+__global__ void tril_rows_from_upper_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad, int row0,
+                                            double* __restrict__ X) {
+    __shared__ double t[32][33];
+    const int b = blockIdx.z;
+    const int r0 = row0 + blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int br = r0 / TILE, bc = c0 / TILE, nt = npad / TILE;
+    const double* Lb = L + (long long)b * npad * npad;
+    double* Xb = X + (long long)b * (npad - row0) * npad + (long long)(r0 - row0) * npad;
+    if (bc > br) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) Xb[(long long)r * npad + c0 + threadIdx.x] = 0.0;
+    } else if (bc == br) {
+        const double* inv = invdiag + ((long long)b * nt + br) * TILE * TILE;
+        for (int r = threadIdx.y; r < 32; r += blockDim.y)
+            Xb[(long long)r * npad + c0 + threadIdx.x] = inv[(r0 - br * TILE + r) * TILE + (c0 - bc * TILE + threadIdx.x)];
+    } else {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = Lb[(long long)(c0 + r) * npad + r0 + threadIdx.x];
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) Xb[(long long)r * npad + c0 + threadIdx.x] = t[threadIdx.x][r];
+    }
+}
+
+extern "C" int gpr_tril_inverse_rows(const double* L, const double* invdiag, int B, int npad, int row0, double* X, void* stream) {
+    ARG_CHECK(L && invdiag && X && B > 0 && npad > 0 && npad % TILE == 0 && row0 >= 0 && row0 < npad && row0 % 32 == 0);
+    tril_rows_from_upper_kernel<<<dim3(npad / 32, (npad - row0) / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(L, invdiag, npad, row0, X);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// one warp per (expert, test point): V [E, m, ldv] rows of length nl
+__global__ void __launch_bounds__(256) vt_reduce_kernel(const double* __restrict__ V, long long ldv, const double* __restrict__ z,
+                                                        long long z_stride, const double* __restrict__ mean_g,
+                                                        const double* __restrict__ var_g, int m, int nl, double* __restrict__ mean,
+                                                        double* __restrict__ var) {
+    const int e = blockIdx.y, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= m) return;
+    const double* v = V + ((long long)e * m + t) * ldv;
+    const double* ze = z + (long long)e * z_stride;
+    double sm = 0.0, sv = 0.0;
+    for (int c = lane * 2; c < nl; c += 64) {
+        const double2 a = *reinterpret_cast<const double2*>(v + c);
+        const double2 b = *reinterpret_cast<const double2*>(ze + c);
+        sm = fma(a.x, b.x, sm); sm = fma(a.y, b.y, sm);
+        sv = fma(a.x, a.x, sv); sv = fma(a.y, a.y, sv);
+    }
+    for (int o = 16; o; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if (lane == 0) {
+        mean[(long long)e * m + t] = mean_g[t] + sm;
+        var[(long long)e * m + t] = var_g[t] - sv;
+    }
+}
+
+extern "C" int gpr_vt_reduce(const double* V, long long ldv, const double* z, long long z_stride, const double* mean_g,
+                             const double* var_g, int E, int m, int nl, double* mean, double* var, void* stream) {
+    ARG_CHECK(V && z && mean_g && var_g && mean && var && E > 0 && m > 0 && nl > 0 && nl % 2 == 0 && ldv >= nl && ldv % 2 == 0);
+    vt_reduce_kernel<<<dim3((m + 7) / 8, E), 256, 0, (cudaStream_t)stream>>>(V, ldv, z, z_stride, mean_g, var_g, m, nl, mean, var);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 vt_gemm_kernel(const double* __restrict__ Ks, const double* __restrict__ X, const double* __restrict__ z, int npad, int mpad,
                double* __restrict__ vt, double* __restrict__ pv, double* __restrict__ pm) {

@@ -157,14 +157,16 @@ __device__ __forceinline__ void issue_k_block(uint32_t tmem, uint32_t a_lo, uint
 // digit planes:  X [rows, k] (FP64, leading dimension ld)  ->  planes [slices][rpad][kpad] int8, scale [rpad]
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_kernel(const double* __restrict__ X, long long ld, int rows, int k, int rpad, int kpad,
-                                                    int slices, int8_t* __restrict__ planes, double* __restrict__ scale) {
+                                                    int slices, double bound, int8_t* __restrict__ planes, double* __restrict__ scale) {
     const int r = blockIdx.x;
     const long long plane_stride = (long long)rpad * kpad;
     int8_t* out = planes + (long long)r * kpad;
     __shared__ double red[8];
     __shared__ int e_sh;
-    double amax = 0.0;
-    if (r < rows) {
+    // row scale from the row maximum, or — when the caller knows a bound on |x| (bound > 0, e.g. sig^2 for an SE kernel matrix) —
+    // from that bound for every row: one pass over the data instead of two
+    double amax = bound > 0.0 ? bound : 0.0;
+    if (r < rows && !(bound > 0.0)) {
         const double* x = X + (long long)r * ld;
         for (int c = threadIdx.x; c < k; c += blockDim.x) amax = fmax(amax, fabs(x[c]));
     }
@@ -388,11 +390,12 @@ extern "C" long long gpr_ozaki_planes_bytes(int rows, int k, int slices) {
     return (long long)slices * oz::round_up(rows, oz::BM) * oz::round_up(k, oz::BK);
 }
 
-extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, void* planes, double* scale, void* stream) {
+extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, double bound, void* planes, double* scale,
+                               void* stream) {
     if (!(X && planes && scale && rows > 0 && k > 0 && ld >= k && slices >= 1 && slices <= oz::MAX_SLICES))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_split%s (slices=%lld)", "", slices);
     const int rpad = oz::round_up(rows, oz::BM), kpad = oz::round_up(k, oz::BK);
-    oz::split_kernel<<<rpad, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, k, rpad, kpad, slices, static_cast<int8_t*>(planes), scale);
+    oz::split_kernel<<<rpad, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, k, rpad, kpad, slices, bound, static_cast<int8_t*>(planes), scale);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return gpr_internal_fail(GPR_ERR_CUDA, "%s (cuda error %lld)", cudaGetErrorString(e), (long long)e);
     return GPR_OK;

@@ -403,6 +403,9 @@ def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     Returns ((mean_g, var_g), (mean_l, var_l)), all ordered on the current stream."""
     dev = xs.device
     if st_l.shared_from is st_g:
+        from .config import options
+        if options.emulate_slices > 0 and can_emulate(st_g, st_l):
+            return predict_shared_emulated(st_g, st_l, xs, options.emulate_slices, options.emulate_chunk)
         return predict_shared(st_g, st_l, xs)
     main = torch.cuda.current_stream(dev)
     side = side_stream(dev, high_priority=False)
@@ -693,28 +696,129 @@ class DigitPlanes:
     scale: torch.Tensor
 
 
-def ozaki_split(X: torch.Tensor, slices: int) -> DigitPlanes:
-    """Digit planes of a row-major FP64 matrix (last dimension contiguous)."""
+def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0) -> DigitPlanes:
+    """Digit planes of a row-major FP64 matrix (last dimension contiguous).  bound > 0: |X| <= bound is known, every row is
+    scaled by it (one pass over X); otherwise each row by its own maximum."""
     assert X.dim() == 2 and X.stride(1) == 1 and X.dtype == F64
     rows, k = X.shape
     lib = _lib.load()
     rpad, kpad = int(lib.gpr_ozaki_rows_padded(rows)), int(lib.gpr_ozaki_k_padded(k))
     planes = torch.empty(slices, rpad, kpad, dtype=torch.int8, device=X.device)
     scale = torch.empty(rpad, dtype=F64, device=X.device)
-    _lib.call("gpr_ozaki_split", _p(X), X.stride(0), rows, k, slices, _p(planes), _p(scale), _stream())
+    _lib.call("gpr_ozaki_split", _p(X), X.stride(0), rows, k, slices, float(bound), _p(planes), _p(scale), _stream())
     _count(1)
     return DigitPlanes(rows, k, slices, planes, scale)
 
 
 def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = None, beta: float = 0.0,
-                  b_lower: bool = False) -> torch.Tensor:
-    """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt)."""
-    assert A.k == B.k and A.slices == B.slices
+                  b_lower: Optional[int] = None, batch: int = 1) -> torch.Tensor:
+    """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt).
+
+    b_lower = o: B[j, k] = 0 for k > j + o (True means o = 0), the zero k-blocks are skipped.  batch > 1: A and B hold `batch`
+    operands stacked along the rows (rows % 128 == 0 each); the result is [batch, M, N]."""
+    assert A.k == B.k and A.slices == B.slices and A.rows % batch == 0 and B.rows % batch == 0
+    M, N = A.rows // batch, B.rows // batch
+    assert batch == 1 or (M % 128 == 0 and N % 128 == 0)
+    shape = (M, N) if batch == 1 else (batch, M, N)
     if out is None:
-        out = torch.empty(A.rows, B.rows, dtype=F64, device=A.planes.device)
+        out = torch.empty(shape, dtype=F64, device=A.planes.device)
         beta = 0.0
-    assert out.shape == (A.rows, B.rows) and out.stride(1) == 1
-    _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), A.rows, _p(B.planes), _p(B.scale), B.rows, A.k, A.slices,
-              int(b_lower), float(beta), _p(out), out.stride(0), _stream())
+    if batch == 1 and out.dim() == 3 and out.shape[0] == 1:
+        out = out[0]
+    assert tuple(out.shape) == shape and out.stride(-1) == 1
+    off = -1 if b_lower is None or b_lower is False else (0 if b_lower is True else int(b_lower))
+    _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), M, _p(B.planes), _p(B.scale), N, A.k, A.slices,
+              off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0, _stream())
     _count(1)
     return out
+
+
+def ensure_inverse_factors(st_g: FitState, st_l: FitState) -> None:
+    """L^-T of every local expert, in place in the strict block-upper part of its factor (once per fit): the emulated-FP64
+    prediction multiplies with rows of the explicit inverse.  The shared communication block's L_g^-T is copied, not recomputed."""
+    if getattr(st_l, "upper_is_inverse", False):
+        return
+    assert st_l.shared_from is st_g and st_g.n % TILE == 0
+    tril_inverse(st_g)                                        # L_g^-T into the block-upper part of the communication factor
+    if not st_l.shared_upper:
+        _lib.call("gpr_copy_leading_block", _p(st_l.L), st_l.B, st_l.npad, _p(st_g.L), st_g.npad, st_g.n, 2, _stream())
+        _count(1)
+        st_l.shared_upper = True
+    scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(st_l.B, st_l.npad)), dtype=torch.uint8, device=st_l.L.device)
+    _lib.call("gpr_trtri_batched", _p(st_l.L), _p(st_l.invdiag), st_l.B, st_l.npad, _p(scratch), _stream(), st_g.n // TILE)
+    _count(2)
+    st_l.upper_is_inverse = True
+    # keep the digit planes of X_l across predictions when HBM allows (8 planes at most, + the transient chunk buffers)
+    free, _ = torch.cuda.mem_get_info(st_l.L.device)
+    nl = st_l.n - st_g.n
+    if free > st_l.B * nl * st_l.npad * 8 + (16 << 30):
+        st_l.plane_cache = {}
+
+
+def can_emulate(st_g: FitState, st_l: FitState) -> bool:
+    """Shapes the emulated-FP64 prediction handles: shared leading block, everything a whole number of 128-row blocks."""
+    return (st_l.shared_from is st_g and st_g.B == 1 and st_g.n % TILE == 0 and st_l.n % TILE == 0 and st_l.n > st_g.n)
+
+
+def _f64_work(kind: str, numel: int, dev: torch.device) -> torch.Tensor:
+    return _work(kind, numel * 8, dev)[: numel * 8].view(F64)
+
+
+def predict_shared_emulated(st_g: FitState, st_l: FitState, xs: torch.Tensor, slices: int = 6, chunk: int = 8):
+    """predict_shared with the local experts' long product on the INT8 tensor cores (opt-in).
+
+    For every local expert  V_l^T = K* X_l^T  with X_l = rows ng.. of L^-1 (lower trapezoidal) is ONE emulated-FP64 GEMM
+    (gpr_ozaki_gemm_nt, `slices` digit planes per operand, exact int32 accumulation); mean and variance follow as in
+    predict_shared (mean_g + V_l^T z_l, var_g - |V_l|^2).  The communication expert itself stays on the FP64 path.  Experts go
+    through in chunks of `chunk` (transient K*, X_l, digit planes and V_l^T; the digit planes of X_l are kept in
+    ``st_l.plane_cache`` when that dict exists).  Same return value as predict_pair."""
+    assert can_emulate(st_g, st_l)
+    m, dev, lib = xs.shape[0], xs.device, _lib.load()
+    if m % TILE:                                              # whole 128-row tiles of test points: repeat the last one, drop it again
+        pad = round_up(m, TILE) - m
+        (mg, vg), (ml, vl) = predict_shared_emulated(st_g, st_l, torch.cat((xs, xs[-1:].expand(pad, -1))).contiguous(), slices, chunk)
+        return (mg[:, :m].contiguous(), vg[:, :m].contiguous()), (ml[:, :m].contiguous(), vl[:, :m].contiguous())
+    ng, n, npad, B = st_g.n, st_l.n, st_l.npad, st_l.B
+    nl = n - ng
+    # communication expert: FP64 GEMM form, as in predict_shared
+    mg = torch.empty(1, m, dtype=F64, device=dev)
+    vg = torch.empty(1, m, dtype=F64, device=dev)
+    vt = _work("predict_vt", m * st_g.npad * 8, dev)
+    Linv = tril_inverse(st_g)
+    scratch_g = _work("predict_gemm", int(lib.gpr_predict_gemm_scratch_bytes(1, st_g.npad, st_g.dpad, m)), dev)
+    _lib.call("gpr_predict_gemm", _p(Linv), _p(st_g.a), _p(st_g.nrm), _p(st_g.z), _p(st_g.hp), st_g.hp.shape[-1],
+              _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt), _p(scratch_g), _stream(),
+              0, None, None)
+    _count(3)
+    ensure_inverse_factors(st_g, st_l)
+    ml = torch.empty(B, m, dtype=F64, device=dev)
+    vl = torch.empty(B, m, dtype=F64, device=dev)
+    cache = getattr(st_l, "plane_cache", None)
+    E = max(1, min(chunk, B))
+    sig2 = float(st_l.hp[0, 0]) ** 2
+    as_, nrms = scale_inputs(xs, st_l.hp[:1], 1, m)          # one hyper-parameter vector: the scaled test points are shared
+    as_e = as_.expand(E, -1, -1).contiguous()
+    nrms_e = nrms.expand(E, -1).contiguous()
+    Ks = _f64_work("emu_ks", E * m * n, dev).view(E, m, n)
+    X = _f64_work("emu_x", E * nl * npad, dev).view(E, nl, npad)
+    V = _f64_work("emu_v", E * m * nl, dev).view(E, m, nl)
+    for e0 in range(0, B, E):
+        e1 = min(e0 + E, B)
+        ne = e1 - e0
+        # K* of the chunk's experts [ne, m, n] (covar.py:151-160), then its digit planes
+        _lib.call("gpr_se_cross", _p(as_e), _p(nrms_e), m, _p(st_l.a[e0:e1]), _p(st_l.nrm[e0:e1]), npad, _p(st_l.hp[e0:e1]),
+                  st_l.hp.shape[-1], ne, m, n, st_l.dpad, _p(Ks), _stream())
+        _count(1)
+        pa = ozaki_split(Ks[:ne].reshape(ne * m, n), slices, bound=sig2)     # 0 < K* <= sig^2 (covar.py:149)
+        pb = cache.get(e0) if cache is not None else None
+        if pb is None or pb.slices != slices:
+            _lib.call("gpr_tril_inverse_rows", _p(st_l.L[e0:e1]), _p(st_l.invdiag[e0:e1]), ne, npad, ng, _p(X), _stream())
+            _count(1)
+            pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices)
+            if cache is not None:
+                cache[e0] = pb
+        ozaki_gemm_nt(pa, pb, out=V[:ne], b_lower=ng, batch=ne)
+        _lib.call("gpr_vt_reduce", _p(V), nl, _p(st_l.z[e0:e1, ng:]), st_l.z.stride(0), _p(mg), _p(vg), ne, m, nl, _p(ml[e0:e1]),
+                  _p(vl[e0:e1]), _stream())
+        _count(1)
+    return (mg, vg), (ml, vl)

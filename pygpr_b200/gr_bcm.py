@@ -298,8 +298,9 @@ class GRBCM_MLE:
 
     Same duck type as ``Loss`` (``loss / grad / loss_and_grad`` on numpy, ``loss_value / grad_value``, ``model`` with
     ``params / set_params``), so ``CG``, ``CG_Quad``, ``BFGS_Quad``, ``Nelder_Mead`` and ``get_learn_rate`` drive it unchanged.
-    Local experts are evaluated in batches of ``chunk`` (0 = all at once) to bound HBM; with experts sharded over ranks
-    the ``[1+P]`` partial sums are all-reduced (NCCL), the replicated communication expert is added once.
+    Local experts are evaluated in batches of ``chunk`` to bound HBM (0 = as many as fit in the free device memory, each
+    expert needing one [npad, npad] factor); with experts sharded over ranks the ``[1+P]`` partial sums are all-reduced (NCCL),
+    the replicated communication expert is added once.
     """
 
     def __init__(self, model: "GRBCM", chunk: int = 0) -> None:
@@ -324,17 +325,23 @@ class GRBCM_MLE:
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         P = theta.shape[-1]
         acc = np.zeros(1 + P)
-        step = self.chunk if self.chunk > 0 else max(g.nc, 1)
+        step = self.chunk if self.chunk > 0 else self._auto_chunk()
         # the communication expert at theta: its NLML/gradient is added once below, and (one shared vector, tile-aligned
         # communication set) its factor is the leading block of every local expert's factor (engine.fit(shared=...))
-        glob = MLE(g.gpg)
+        glob = getattr(self, "_glob", None)
+        if glob is None:
+            glob = self._glob = MLE(g.gpg)
         st_g = glob._fit(theta, want_alpha=True)
         share = st_g if (isinstance(st_g, engine.FitState) and g.ng >= engine.TILE and options.share) else None
         if share is not None and want_grad and g.ng % engine.TILE == 0:
             engine.kinv(st_g)      # K_g^-1 and L_g^-T once: the experts' gradients reuse both (gpr_lml_grad_shared)
         for s in range(0, g.nc, step):
             e = min(s + step, g.nc)
-            part = MLE(Exact_GP(g.gpl.x[s:e], g.gpl.y[s:e], g.gpl.cov))
+            part = getattr(self, "_part", None)
+            if part is None:
+                part = self._part = MLE(Exact_GP(g.gpl.x[s:e], g.gpl.y[s:e], g.gpl.cov))
+            else:                                            # same instance, next batch of experts: its factor buffer is reused
+                part.model.x, part.model.y = g.gpl.x[s:e], g.gpl.y[s:e]
             part.shared_state = share
             th = np.tile(theta, (e - s, 1))
             if want_grad:
@@ -353,6 +360,18 @@ class GRBCM_MLE:
             j = glob._grad(st_g)[0].cpu().numpy()           # last: it overwrites the block-upper part of the shared factor
             return float(acc[0] + l), acc[1:] + j
         return float(acc[0] + l), None
+
+    def _auto_chunk(self) -> int:
+        """Experts per batch when the caller gave none: what fits in the free device memory (one factor per expert plus the
+        inputs and workspaces, a few GB held back), all of them if possible.  The previous batch's factor buffer is reused."""
+        g = self.grbcm
+        if g.nc <= 1:
+            return 1
+        npad = engine.round_up(g.ng + g.nsc, engine.TILE)
+        per = npad * npad * 8 + 3 * npad * engine.TILE * 8
+        free, _ = torch.cuda.mem_get_info(engine.device())
+        held = self._part._L_buf.numel() * 8 if getattr(self, "_part", None) is not None and self._part._L_buf is not None else 0
+        return int(max(1, min(g.nc, (free + held - (6 << 30)) // per)))
 
     def loss(self, params):
         self.loss_value, _ = self._eval(params, False)

@@ -36,8 +36,32 @@ class MLE(Loss):
     Takes and returns numpy (scipy drives the optimisers on the host, loss.py:37,57,90,128).  One
     factorisation per call, like the reference, but the gradient never forms dK: K^-1 is assembled tile
     by tile from L^-T and reduced against K_se generated on chip (N^3 flops instead of (1/3+2P) N^3).
-    The model's own fitted state is not touched.
+
+    Memory: every evaluation needs one [B, npad, npad] factor buffer.  The instance keeps its buffer between calls (an
+    optimiser makes hundreds of evaluations on the same shapes); when a fresh buffer would not fit beside the model's own fitted
+    factor (config 4 on one GPU: 137 GB each), the model's buffer is borrowed instead and the model marked stale — its next
+    predict refits, exactly as after set_params (gpr.py:28-31).  Otherwise the model's fitted state is not touched.
     """
+
+    _L_buf = None
+
+    def _factor_buffer(self, B: int, npad: int, dev) -> "torch.Tensor | None":
+        """A [B, npad, npad] buffer to factorise into: this instance's own from the previous call, else the model's (borrowed)
+        when there is no room for another one, else None (engine.fit allocates; the result is kept for the next call)."""
+        shape = (B, npad, npad)
+        buf = self._L_buf
+        if buf is not None and tuple(buf.shape[1:]) == shape[1:] and buf.shape[0] >= B and buf.device == dev:
+            return buf[:B]                                   # a smaller batch (the last chunk of GRBCM_MLE) uses the front
+        self._L_buf = buf = None
+        need = B * npad * npad * 8
+        free, _ = torch.cuda.mem_get_info(dev)
+        st = getattr(self.model, "_state", None)
+        if need + (2 << 30) > free and isinstance(st, engine.FitState) and tuple(st.L.shape) == shape and st.L.device == dev:
+            self.model._state = None                         # the model's factor is overwritten: it refits on its next use
+            self.model.need_upd = True
+            self._L_buf = st.L
+            return st.L
+        return None
 
     def _fit(self, params: ndarray, want_alpha: bool):
         xs, ys = self.model.x, self.model.y
@@ -70,7 +94,10 @@ class MLE(Loss):
         shared = getattr(self, "shared_state", None)        # set by GRBCM_MLE: the communication expert fitted at these params
         if shared is not None and not engine.can_share(shared, x.shape[1], x.shape[2], spec[0]):
             shared = None
-        st = engine.fit(x, y, hp, spec[0], want_alpha=want_alpha, shared=shared)
+        npad = engine.round_up(x.shape[1], engine.TILE)
+        st = engine.fit(x, y, hp, spec[0], want_alpha=want_alpha, shared=shared, L_out=self._factor_buffer(B, npad, x.device))
+        if self._L_buf is None or st.L.numel() > self._L_buf.numel():
+            self._L_buf = st.L
         st.check()                                           # tc.cholesky raises on a non-PD matrix, loss.py:39
         return st
 
