@@ -151,7 +151,7 @@ def scale_to_job(w, nc_s):
     return (nc * n_l ** 2 + n_g ** 2) / float(nc_s * n_l ** 2 + n_g ** 2)
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's own CPU implementation of the path on the host cores (the unmodified package from
     baseline/_ref driven through its public API; the oracle port only if no copy is present), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -181,7 +181,8 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cs.kind, "sample": sample,
                              "fit_s_sample": cs.fit_s},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
 
 
@@ -253,7 +254,18 @@ def train_parity(P, small):
     return {"vs": cs.kind, "experts": 2, "order": 2 * m0, "d": d, "nlml": abs(f - f_ref) / abs(f_ref), "grad": cpu_arm.rel_err(grad, g_ref)}
 
 
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on communicator creation,
+    whatever NCCL_DEBUG_FILE says on some hosts), so file descriptor 1 is pointed at stderr for the whole run and the line goes
+    to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -269,7 +281,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -531,7 +543,8 @@ def main():
                              "mean_aggregate_sample": cpu_arm.rel_err(ge["mu"], ref["mu"]),
                              "var_aggregate_sample": cpu_arm.rel_err(ge["var"], ref["var"])}
             emu["parity"]["ok"] = max(v for k, v in emu["parity"].items() if k.startswith(("mean", "var"))) <= 1e-8
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if world > 1:
         dist.destroy_process_group()
     if "parity" in line and not line["parity"]["ok"]:

@@ -315,17 +315,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         for (int c0 = 0; c0 < BN; c0 += 16) {
+            // all diagonals of these 16 columns in flight at once, ONE wait: S TMEM round trips overlap instead of serialising
+            uint32_t v[S][16];
+#pragma unroll
+            for (int g = 0; g < S; ++g) tmem_ld16(lane_base + (uint32_t)(g * BN + c0), v[g]);
+#pragma unroll
+            for (int g = 0; g < S; ++g) tmem_ld_wait(v[g]);
             double acc[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.0;
 #pragma unroll
-            for (int g = S - 1; g >= 0; --g) {              // Horner in 1/256, smallest diagonal first
-                uint32_t v[16];
-                tmem_ld16(lane_base + (uint32_t)(g * BN + c0), v);
-                tmem_ld_wait(v);
+            for (int g = S - 1; g >= 0; --g)               // Horner in 1/256, smallest diagonal first
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], 0.00390625, (double)(int)v[i]);
-            }
+                for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], 0.00390625, (double)(int)v[g][i]);
             const int col0 = tn * BN + c0;
             if (row < M) {
                 double* crow = C + (long long)row * ldc + col0;

@@ -696,15 +696,19 @@ class DigitPlanes:
     scale: torch.Tensor
 
 
-def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0) -> DigitPlanes:
+def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0, out: Optional[DigitPlanes] = None) -> DigitPlanes:
     """Digit planes of a row-major FP64 matrix (last dimension contiguous).  bound > 0: |X| <= bound is known, every row is
-    scaled by it (one pass over X); otherwise each row by its own maximum."""
+    scaled by it (one pass over X); otherwise each row by its own maximum.  out: planes / scale buffers to write into."""
     assert X.dim() == 2 and X.stride(1) == 1 and X.dtype == F64
     rows, k = X.shape
     lib = _lib.load()
     rpad, kpad = int(lib.gpr_ozaki_rows_padded(rows)), int(lib.gpr_ozaki_k_padded(k))
-    planes = torch.empty(slices, rpad, kpad, dtype=torch.int8, device=X.device)
-    scale = torch.empty(rpad, dtype=F64, device=X.device)
+    if out is None:
+        planes = torch.empty(slices, rpad, kpad, dtype=torch.int8, device=X.device)
+        scale = torch.empty(rpad, dtype=F64, device=X.device)
+    else:
+        planes = out.planes.view(-1)[: slices * rpad * kpad].view(slices, rpad, kpad)
+        scale = out.scale[:rpad]
     _lib.call("gpr_ozaki_split", _p(X), X.stride(0), rows, k, slices, float(bound), _p(planes), _p(scale), _stream())
     _count(1)
     return DigitPlanes(rows, k, slices, planes, scale)
@@ -799,22 +803,27 @@ def predict_shared_emulated(st_g: FitState, st_l: FitState, xs: torch.Tensor, sl
     as_, nrms = scale_inputs(xs, st_l.hp[:1], 1, m)          # one hyper-parameter vector: the scaled test points are shared
     as_e = as_.expand(E, -1, -1).contiguous()
     nrms_e = nrms.expand(E, -1).contiguous()
+    # transient staging, reused by every chunk (stream-ordered): K* and X_l in FP64, their digit planes, V_l^T.  (Preparing chunk
+    # c+1 on a side stream while the tensor cores work on chunk c was measured and dropped: the GEMM's 222 KB of shared memory per
+    # SM leaves no room for the kernel-matrix builder beside it, so the two only time-slice.)
     Ks = _f64_work("emu_ks", E * m * n, dev).view(E, m, n)
     X = _f64_work("emu_x", E * nl * npad, dev).view(E, nl, npad)
     V = _f64_work("emu_v", E * m * nl, dev).view(E, m, nl)
+    bufa = DigitPlanes(E * m, n, slices, _work("emu_pa", slices * E * m * n, dev), _f64_work("emu_sa", E * m, dev))
+    bufb = DigitPlanes(E * nl, npad, slices, _work("emu_pb", slices * E * nl * npad, dev), _f64_work("emu_sb", E * nl, dev)) if cache is None else None
     for e0 in range(0, B, E):
         e1 = min(e0 + E, B)
         ne = e1 - e0
-        # K* of the chunk's experts [ne, m, n] (covar.py:151-160), then its digit planes
+        # K* of the chunk's experts [ne, m, n] (covar.py:151-160), then its digit planes; 0 < K* <= sig^2 (covar.py:149)
         _lib.call("gpr_se_cross", _p(as_e), _p(nrms_e), m, _p(st_l.a[e0:e1]), _p(st_l.nrm[e0:e1]), npad, _p(st_l.hp[e0:e1]),
                   st_l.hp.shape[-1], ne, m, n, st_l.dpad, _p(Ks), _stream())
         _count(1)
-        pa = ozaki_split(Ks[:ne].reshape(ne * m, n), slices, bound=sig2)     # 0 < K* <= sig^2 (covar.py:149)
+        pa = ozaki_split(Ks[:ne].reshape(ne * m, n), slices, bound=sig2, out=bufa)
         pb = cache.get(e0) if cache is not None else None
         if pb is None or pb.slices != slices:
             _lib.call("gpr_tril_inverse_rows", _p(st_l.L[e0:e1]), _p(st_l.invdiag[e0:e1]), ne, npad, ng, _p(X), _stream())
             _count(1)
-            pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices)
+            pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices, out=bufb)
             if cache is not None:
                 cache[e0] = pb
         ozaki_gemm_nt(pa, pb, out=V[:ne], b_lower=ng, batch=ne)

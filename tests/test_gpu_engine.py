@@ -247,3 +247,51 @@ def test_vt_forms_agree(eng, orc):
     z = st.z[0, :st.n].cpu()
     assert_close(mp[0].cpu().numpy(), (V[:, :256] @ z[:256]).numpy(), 1e-10, "mean_part")
     assert_close(vp[0].cpu().numpy(), (float(st.prior[0]) - (V[:, :256] ** 2).sum(-1)).numpy(), 1e-10, "var_part")
+
+
+# ---- emulated FP64 on the INT8 tcgen05 tensor cores (csrc/ozaki_gemm.cu): integer work is checked BIT-EXACT ----------------------
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 100, 130), (300, 257, 1000), (1, 1, 1)])
+@pytest.mark.parametrize("slices", [1, 3, 6, 8])
+def test_ozaki_digit_planes_and_product_bit_exact(eng, M, N, K, slices):
+    """gpr_ozaki_split's digit planes / row scales equal the numpy restatement (oracle/ozaki_ref.py) bit for bit, and
+    gpr_ozaki_gemm_nt's C equals the restatement's (exact integer diagonals, same FP64 recombination order) bit for bit."""
+    from oracle import ozaki_ref
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp(2.0 * torch.randn(M, 1, generator=g, dtype=torch.float64))
+    B = torch.randn(N, K, generator=g, dtype=torch.float64)
+    A[0, :] = 0.0 if M > 1 else A[0, :]                      # an all-zero row: scale 0, digits 0
+    pa, pb = eng.ozaki_split(A.cuda(), slices), eng.ozaki_split(B.cuda(), slices)
+    npa, nsa = ozaki_ref.split(A.numpy(), slices)
+    npb, nsb = ozaki_ref.split(B.numpy(), slices)
+    assert np.array_equal(pa.planes.cpu().numpy(), npa) and np.array_equal(pb.planes.cpu().numpy(), npb)
+    assert np.array_equal(pa.scale.cpu().numpy(), nsa) and np.array_equal(pb.scale.cpu().numpy(), nsb)
+    C = eng.ozaki_gemm_nt(pa, pb).cpu().numpy()
+    assert np.array_equal(C, ozaki_ref.gemm_nt(npa, nsa, M, npb, nsb, N, slices))
+    if slices >= 6:
+        ref = (A @ B.T).numpy()
+        assert np.abs(C - ref).max() <= (1e-11 if slices == 6 else 1e-13) * np.abs(ref).max()
+
+
+def test_ozaki_gemm_accumulate_lower_and_batched(eng):
+    """beta = 1 accumulation, the lower-trapezoidal B option (zero k-blocks skipped) and the batched launch against FP64 products."""
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 256, 192, 320
+    A = torch.randn(M, K, generator=g, dtype=torch.float64).cuda()
+    off = 128
+    Bm = torch.randn(N, K, generator=g, dtype=torch.float64)
+    Bm = (Bm * (torch.arange(K)[None, :] <= (torch.arange(N)[:, None] + off))).cuda()   # B[j, k] = 0 for k > j + off
+    C0 = torch.randn(M, N, generator=g, dtype=torch.float64).cuda()
+    pa, pb = eng.ozaki_split(A, 7), eng.ozaki_split(Bm, 7)
+    C = eng.ozaki_gemm_nt(pa, pb, out=C0.clone(), beta=1.0, b_lower=off)
+    ref = C0 + A @ Bm.T
+    assert float((C - ref).abs().max() / ref.abs().max()) <= 1e-13
+    assert torch.equal(eng.ozaki_gemm_nt(pa, pb, b_lower=off), eng.ozaki_gemm_nt(pa, pb))   # skipping zeros changes nothing
+    nb = 3
+    Ab = torch.randn(nb, 128, 192, generator=g, dtype=torch.float64).cuda()
+    Bb = torch.randn(nb, 256, 192, generator=g, dtype=torch.float64).cuda()
+    pab, pbb = eng.ozaki_split(Ab.reshape(nb * 128, 192), 7), eng.ozaki_split(Bb.reshape(nb * 256, 192), 7)
+    Cb = eng.ozaki_gemm_nt(pab, pbb, batch=nb)
+    refb = torch.bmm(Ab, Bb.transpose(1, 2))
+    assert float((Cb - refb).abs().max() / refb.abs().max()) <= 1e-13
+    for i in range(nb):   # a batch entry equals the same product launched alone, bit for bit
+        assert torch.equal(Cb[i], eng.ozaki_gemm_nt(eng.ozaki_split(Ab[i], 7), eng.ozaki_split(Bb[i], 7)))

@@ -193,3 +193,35 @@ def test_shared_block_detection_and_dense_routing_are_host_logic():
     assert engine.fused_dim_ok(16) and engine.fused_dim_ok(44) and not engine.fused_dim_ok(45) and not engine.fused_dim_ok(64)
     assert fused_spec(cov, 16) == (True,) and fused_spec(P.Squared_exponential(), 8) == (False,) and fused_spec(cov, 64) is None
     assert fused_spec(P.Compose([P.Squared_exponential(), P.Squared_exponential(), P.White_noise()]), 4) is None
+
+
+def test_ozaki_reference_arithmetic():
+    """oracle/ozaki_ref.py (the numpy restatement the GPU digit planes are checked against bit for bit): balanced radix-256
+    digits in [-128, 127], leading digit within [-64, 64], exact reconstruction of the fixed-point value, known answers, and the
+    error of the recombined product falling by 2^-8 per slice."""
+    import numpy as np
+    from oracle import ozaki_ref
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((5, 70)) * np.exp(3 * rng.standard_normal((5, 1)))
+    X[3] = 0.0
+    for S in (1, 4, 7, 8):
+        planes, scale = ozaki_ref.split(X, S)
+        assert planes.dtype == np.int8 and planes.shape == (S, 128, 128) and np.abs(planes[0].astype(int)).max() <= 64
+        assert scale[3] == 0.0 and not planes[:, 3].any() and not planes[:, 5:].any() and not planes[:, :, 70:].any()
+        e = np.log2(scale[:5][scale[:5] > 0]) + 8
+        assert np.all(e == np.round(e))                                      # power-of-two scales
+        # value = 2^e sum_t q_t 256^-(t+1), exact to half a unit of the last digit
+        rec = sum(planes[t, :5, :70].astype(np.float64) * 256.0 ** -(t + 1) for t in range(S)) * (scale[:5, None] * 256.0)
+        assert np.all(np.abs(rec - X) <= 0.5 * 256.0 ** -S * (scale[:5, None] * 256.0) * (1 + 1e-12))
+    # known answers: 0.5 = 2^2 * 32/256 -> leading digit 32 at exponent 2 (|x| 2^-e < 1/4); -0.75 -> -48
+    p, sc = ozaki_ref.split(np.array([[0.5, -0.25, 0.0]]), 2)
+    assert sc[0] == 2.0 ** (2 - 8) and p[:, 0, :3].tolist() == [[32, -16, 0], [0, 0, 0]]
+    p, sc = ozaki_ref.split(np.array([[-0.75, 0.75 / 256 + 0.75 / 65536]]), 3)
+    assert p[:, 0, :2].tolist() == [[-48, 0], [0, 48], [0, 48]]
+    A, B = rng.standard_normal((40, 300)), rng.standard_normal((24, 300))
+    ref = A @ B.T
+    errs = []
+    for S in (3, 4, 5, 6, 7):
+        pa, sa = ozaki_ref.split(A, S); pb, sb = ozaki_ref.split(B, S)
+        errs.append(np.abs(ozaki_ref.gemm_nt(pa, sa, 40, pb, sb, 24, S) - ref).max() / np.abs(ref).max())
+    assert errs[-1] < 1e-13 and all(b < a / 50 for a, b in zip(errs, errs[1:]))
