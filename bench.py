@@ -29,6 +29,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -412,10 +413,18 @@ def main():
             mu_e, var_e = step_device()
         e1.record(); barrier()
         emu_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        # the same through the public API with host tensors (pinned H2D of the test points, D2H of mean / variance in the timed region)
+        model.predict(xs_host, var="diag")
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.predict(xs_host, var="diag")
+        barrier(); emu_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
         config.options.emulate_slices = 0
         rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
         emu = {"slices": args.emulate, "plane_products": args.emulate * (args.emulate + 1) // 2, "value": m / (emu_ms * 1e-3), "unit": UNIT,
                "ms_per_step": emu_ms, "speedup_vs_fp64_path": step_ms / emu_ms, "prepare_ms_once_per_fit": prep_ms,
+               "e2e": {"value": m / (emu_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": emu_e2e_ms, "h2d_bytes_per_step": m * d * 8,
+                       "d2h_bytes_per_step": 2 * m * 8},
                "tflops_equiv": (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m / emu_ms * 1e-9,
                "aggregate_mean_vs_fp64_path": rel(mu_e, mu), "aggregate_var_vs_fp64_path": rel(var_e, var),
                "expert_mean_vs_fp64_path": rel(last["ml"], ml_fp64), "expert_var_vs_fp64_path": rel(last["vl"], vl_fp64),
@@ -439,6 +448,7 @@ def main():
         mu_s, var_s = eng.grbcm_finalize(S_s, src["mg"][0], src["vg"][0])[:2]
         return {"ml": ml_s.cpu(), "vl": vl_s.cpu(), "mg": src["mg"][0].cpu(), "vg": src["vg"][0].cpu(), "mu": mu_s.cpu(), "var": var_s.cpu()}
 
+    nl_fit = st.nlml().cpu().numpy()
     gpu_side = None
     if rank == 0 and not args.no_cpu_baseline:
         gpu_side = sample_side(last)
@@ -447,6 +457,23 @@ def main():
         gpu_side["grad_g"] = P.MLE(model.gpg).loss_and_grad(make_hp(1, d)[0].numpy())[1]
         if emu is not None:
             gpu_side["emu"] = sample_side(emu_last)
+
+    # ---- NLML + gradient of the local experts through the PUBLIC API: MLE(model.gpl).loss_and_grad (loss.py:92-128).  One factor
+    # buffer per evaluation; beside the model's 137 GB there is no room for a second one on one GPU, so MLE borrows the model's
+    # (the model is marked stale, as after set_params) — nothing below needs the prediction factors any more
+    mle_api = None
+    if not args.no_grad:
+        mle = P.MLE(model.gpl)
+        hp_np = make_hp(hi - lo, d).numpy()
+        mle.loss(hp_np)                                       # warm-up (takes over the factor buffer)
+        barrier(); e0.record(); nl_api, gr_api = mle.loss_and_grad(hp_np); e1.record(); barrier()
+        api_ms = max_over_ranks(e0.elapsed_time(e1))
+        api_flops = nc_total * float(n_l) ** 3                # N^3 per expert: Cholesky N^3/3 + L^-T N^3/3 + K^-1 N^3/3 (general path)
+        mle_api = {"ms": api_ms, "tflops": api_flops / api_ms * 1e-9, "frac_of_peak": api_flops / api_ms * 1e-9 / (peak_tf * world),
+                   "what": "MLE(model.gpl).loss_and_grad(hp [nc, P]) — per-expert NLML and gradient through the reference-shaped API, "
+                           "incl. the [nc, 1+P] read-back; experts treated as unrelated matrices (N^3 flops each)",
+                   "nlml_vs_fit": float(np.abs(np.asarray(nl_api) - nl_fit).max() / np.abs(nl_fit).max())}
+        del mle
 
     # ---- config 5: one training evaluation through GRBCM_MLE (all ranks; takes over the HBM the prediction model held) ----------
     train = None
@@ -497,6 +524,8 @@ def main():
         line["emulated_fp64"] = emu
     if train is not None:
         line["train"] = train
+    if mle_api is not None:
+        line["mle_public_api"] = mle_api
     if grad_ms is not None:
         gflops_unshared = nc_total * float(n_l) ** 3 * 2.0 / 3.0
         gflops = nc_total * (float(n_l) ** 3 - float(n_g) ** 3) * 2.0 / 3.0 if shared else gflops_unshared

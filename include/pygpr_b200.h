@@ -12,7 +12,9 @@
  *   - the library never allocates or frees persistent device memory: workspaces are passed in;
  *   - return value: 0 on success, negative gpr_status on failure (gpr_last_error() has the text);
  *     numerical failure of a factorisation is reported LAPACK-style through info[B]
- *     (0 = ok, k>0 = leading minor of order k is not positive definite), never as a return code;
+ *     (0 = ok, k>0 = leading minor of order k is not positive definite), never as a return code; INT_MIN in every entry
+ *     means the single-launch factorisation was aborted by its hang guard (a tile task waited > 30 s for its
+ *     dependencies on a wedged GPU) — a scheduling stall, not a numerical verdict;
  *   - matrices that are factorised are stored PADDED to a multiple of GPR_TILE (=128) in both
  *     dimensions (`npad`); the padding block is the identity, so factors of the padded matrix
  *     equal the padded factors.  Inputs are stored pre-scaled by the ARD length-scales

@@ -277,8 +277,15 @@ extern "C" int gpr_se_kernel_grad(const double* Kse, const double* x, const doub
 // j-1 and parked in the unused upper block (j-1, j) of L; the diagonal kernel then costs O(1) tiles, not O(j).
 // ---------------------------------------------------------------------------------------------
 // ---- inter-CTA progress flags (release / acquire at GPU scope; bounded polling as a hang guard) ----------------------------
-constexpr long long DF_SPIN_LIMIT = 1LL << 25;   // ~30 s of polling: far beyond any legitimate wait, short of a wedged box
+constexpr unsigned long long DF_WAIT_LIMIT_NS = 30ull * 1000ull * 1000ull * 1000ull;   // 30 s of ELAPSED time (globaltimer): far beyond
+                                                                                         // any legitimate wait, short of a wedged box
+#define GPR_INFO_STALLED (-2147483647 - 1)   // info[] sentinel: the launch was aborted by the hang guard (not a numerical verdict)
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -287,18 +294,20 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// All threads call.  Thread 0 polls, the CTA barrier hands its acquire to everyone.  false = aborted.
+// All threads call.  Thread 0 polls, the CTA barrier hands its acquire to everyone.  false = aborted: the abort flag is raised
+// and every CTA drains; report_stall_kernel, enqueued behind the launch, then marks EVERY info entry GPR_INFO_STALLED so the host
+// can tell a scheduling stall from a non-positive-definite matrix (no tile task can overwrite it any more at that point).
 __device__ __forceinline__ bool df_wait(const int* flag, int need, int* abort_flag, int* info, int* s_ok) {
+    (void)info;
     if (threadIdx.x == 0) {
         int ok = 1;
         if (ld_acquire_gpu(flag) < need) {
-            long long spins = 0;
+            const unsigned long long t0 = globaltimer_ns();
             for (;;) {
                 __nanosleep(100);
                 if (ld_acquire_gpu(flag) >= need) break;
-                if (++spins > DF_SPIN_LIMIT || *reinterpret_cast<volatile int*>(abort_flag)) {
+                if (*reinterpret_cast<volatile int*>(abort_flag) || globaltimer_ns() - t0 > DF_WAIT_LIMIT_NS) {
                     atomicExch(abort_flag, 1);
-                    if (info) __stcg(info, -1);
                     ok = 0;
                     break;
                 }
@@ -310,6 +319,13 @@ __device__ __forceinline__ bool df_wait(const int* flag, int need, int* abort_fl
     const bool ok = *s_ok != 0;
     __syncthreads();  // *s_ok is rewritten by the next wait
     return ok;
+}
+
+__global__ void report_stall_kernel(const int* __restrict__ abort_flag, int* __restrict__ info, int B, int* __restrict__ info2, int B2) {
+    if (*abort_flag == 0) return;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) info[i] = GPR_INFO_STALLED;
+    if (info2)
+        for (int i = threadIdx.x; i < B2; i += blockDim.x) info2[i] = GPR_INFO_STALLED;
 }
 
 struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-warp per row, 8 rows per half-warp
@@ -630,8 +646,8 @@ potrf_panel_kernel(double* __restrict__ L, int npad, int n, int j, const double*
 // overlaps other experts' products instead of serialising the column, and no look-ahead round trip through HBM.
 //   D(b, j):  T = K_jj - L[j,0:j] L[j,0:j]^T  -> potf2/trti2 -> L_jj, inv(L_jj), z_j      waits (j, j-1) for the last block
 //   P(b,i,j): X = K_ij - L[i,0:j] L[j,0:j]^T ; waits for D(b, j) only before  L_ij = X inv(L_jj)^T
-// Waits are bounded (DF_SPIN_LIMIT polls): on a time-out the kernel raises the abort flag, every CTA drains, and
-// info[0] = -1 tells the host; the bound is a guard against a wedged GPU, not part of the protocol.
+// Waits are bounded (DF_WAIT_LIMIT_NS of elapsed time): on a time-out the kernel raises the abort flag, every CTA drains, and
+// info[*] = GPR_INFO_STALLED tells the host (report_stall_kernel); the bound is a guard against a wedged GPU, not part of the protocol.
 // ---------------------------------------------------------------------------------------------
 struct PotrfArgs {
     double* L;
@@ -964,6 +980,7 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
                 CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<false>, smem_df));
                 potrf_dataflow_kernel<false><<<grid, NTHREADS, smem_df, st>>>(A, A);
             }
+            if (info) report_stall_kernel<<<1, 128, 0, st>>>(ctl + 1, info, B, nullptr, 0);
             CUDA_TRY(cudaGetLastError());
             return GPR_OK;
         }
@@ -1120,6 +1137,7 @@ extern "C" int gpr_potrf_grbcm(double* L, const double* a, const double* nrm, co
                 0, nullptr, 0, nullptr, nullptr, z, B, npad, gt, nullptr, nullptr, nullptr, ld_blk_g, zz_blk_g};
     CUDA_TRY(opt_in_smem(potrf_dataflow_kernel<true>, smem_df));
     potrf_dataflow_kernel<true><<<(int)total, NTHREADS, smem_df, st>>>(A, G);
+    if (info) report_stall_kernel<<<1, 128, 0, st>>>(ctl + 1, info, B, info_g, 1);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }
@@ -1732,28 +1750,43 @@ extern "C" int gpr_predict_full(const double* L, const double* invdiag, const do
 // ---------------------------------------------------------------------------------------------
 // K8: GRBCM aggregation (HBM-trivial elementwise + sum over the expert axis)        gr_bcm.py:116-149
 // ---------------------------------------------------------------------------------------------
-__global__ void grbcm_partial_kernel(const double* __restrict__ mean_l, const double* __restrict__ var_l,
-                                     const double* __restrict__ var_g, int nc_local, int first_global_index, int m,
-                                     double* __restrict__ S, double* __restrict__ beta_rows, double* __restrict__ prec_rows) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m) return;
-    const double pg = 1.0 / var_g[c];              // gr_bcm.py:128
-    const double lpg = log(pg);
+// 32 test points x 8 expert groups per block: a warp reads 32 consecutive values of one expert row (256 B, coalesced), the 8
+// warps take the experts i = w, w+8, ... and their partial sums are added in the fixed order w = 0..7 (deterministic; the
+// one-thread-per-test-point version walked 255 dependent log() chains per thread on 32 blocks: 0.9 % of the HBM rate)
+constexpr int AGG_GROUPS = 8;
+__global__ void __launch_bounds__(32 * AGG_GROUPS)
+grbcm_partial_kernel(const double* __restrict__ mean_l, const double* __restrict__ var_l, const double* __restrict__ var_g,
+                     int nc_local, int first_global_index, int m, double* __restrict__ S, double* __restrict__ beta_rows,
+                     double* __restrict__ prec_rows) {
+    __shared__ double part[3][AGG_GROUPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     double sb = 0.0, sp = 0.0, sm = 0.0;
-    for (int i = 0; i < nc_local; ++i) {
-        const double p = 1.0 / var_l[(long long)i * m + c];             // gr_bcm.py:129
-        double beta = 0.5 * (log(p) - lpg);                              // gr_bcm.py:131
-        if (first_global_index + i == 0) beta = 1.0;                     // gr_bcm.py:132
-        const double pb = p * beta;                                      // gr_bcm.py:140
-        sb += beta;
-        sp += pb;
-        sm += mean_l[(long long)i * m + c] * pb;
-        if (beta_rows) beta_rows[(long long)i * m + c] = beta;
-        if (prec_rows) prec_rows[(long long)i * m + c] = p;
+    if (c < m) {
+        const double pg = 1.0 / var_g[c];              // gr_bcm.py:128
+        const double lpg = log(pg);
+        for (int i = w; i < nc_local; i += AGG_GROUPS) {
+            const double p = 1.0 / var_l[(long long)i * m + c];             // gr_bcm.py:129
+            double beta = 0.5 * (log(p) - lpg);                              // gr_bcm.py:131
+            if (first_global_index + i == 0) beta = 1.0;                     // gr_bcm.py:132
+            const double pb = p * beta;                                      // gr_bcm.py:140
+            sb += beta;
+            sp += pb;
+            sm += mean_l[(long long)i * m + c] * pb;
+            if (beta_rows) beta_rows[(long long)i * m + c] = beta;
+            if (prec_rows) prec_rows[(long long)i * m + c] = p;
+        }
     }
-    S[c] = sb;
-    S[m + c] = sp;
-    S[2 * (long long)m + c] = sm;
+    part[0][w][lane] = sb;
+    part[1][w][lane] = sp;
+    part[2][w][lane] = sm;
+    __syncthreads();
+    if (w < 3 && c < m) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < AGG_GROUPS; ++g) t += part[w][g][lane];
+        S[(long long)w * m + c] = t;
+    }
 }
 
 __global__ void grbcm_finalize_kernel(const double* __restrict__ S, const double* __restrict__ mean_g,
@@ -1774,8 +1807,8 @@ __global__ void grbcm_finalize_kernel(const double* __restrict__ S, const double
 extern "C" int grbcm_partial(const double* mean_l, const double* var_l, const double* var_g, int nc_local,
                              int first_global_index, int m, double* S, double* beta_rows, double* prec_rows, void* stream) {
     ARG_CHECK(var_g && S && m > 0 && nc_local >= 0 && (nc_local == 0 || (mean_l && var_l)));
-    grbcm_partial_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_l, var_l, var_g, nc_local, first_global_index,
-                                                                            m, S, beta_rows, prec_rows);
+    grbcm_partial_kernel<<<(m + 31) / 32, 32 * AGG_GROUPS, 0, (cudaStream_t)stream>>>(mean_l, var_l, var_g, nc_local,
+                                                                                      first_global_index, m, S, beta_rows, prec_rows);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;
 }

@@ -18,6 +18,7 @@ from ._lib import TILE
 
 F64 = torch.float64
 JITTER = 1e-7  # gpr.py:68, loss.py:38,63,96
+INFO_STALLED = -2 ** 31  # info[] sentinel of an aborted launch (GPR_INFO_STALLED in the library)
 
 # number of library kernels launched so far (bench.py reports the delta over its timed region)
 LAUNCHES = 0
@@ -146,6 +147,10 @@ class FitState:
         bad = torch.nonzero(self.info)
         if bad.numel():
             b = int(bad[0, 0])
+            if int(self.info[b]) == INFO_STALLED:            # the hang guard of the dataflow launch fired: not a numerical verdict
+                raise _lib.GprError("factorisation aborted: a tile task waited longer than the library's time limit for its "
+                                    "dependencies (a scheduling stall on a wedged or heavily shared GPU); the matrices were NOT "
+                                    "found to be non-positive-definite — retry")
             raise torch.linalg.LinAlgError(
                 "cholesky: expert %d: the leading minor of order %d is not positive-definite" % (b, int(self.info[b])))
 
@@ -773,7 +778,8 @@ def predict_shared_emulated(st_g: FitState, st_l: FitState, xs: torch.Tensor, sl
 
     For every local expert  V_l^T = K* X_l^T  with X_l = rows ng.. of L^-1 (lower trapezoidal) is ONE emulated-FP64 GEMM
     (gpr_ozaki_gemm_nt, `slices` digit planes per operand, exact int32 accumulation); mean and variance follow as in
-    predict_shared (mean_g + V_l^T z_l, var_g - |V_l|^2).  The communication expert itself stays on the FP64 path.  Experts go
+    predict_shared (mean_g + V_l^T z_l, var_g - |V_l|^2).  The communication expert is predicted the same way (one triangular
+    product with L_g^-1, at no fewer than 6 planes in the FP64-grade modes); the factorisations stay FP64.  Experts go
     through in chunks of `chunk` (transient K*, X_l, digit planes and V_l^T; the digit planes of X_l are kept in
     ``st_l.plane_cache`` when that dict exists).  Same return value as predict_pair."""
     assert can_emulate(st_g, st_l)
@@ -784,17 +790,26 @@ def predict_shared_emulated(st_g: FitState, st_l: FitState, xs: torch.Tensor, sl
         return (mg[:, :m].contiguous(), vg[:, :m].contiguous()), (ml[:, :m].contiguous(), vl[:, :m].contiguous())
     ng, n, npad, B = st_g.n, st_l.n, st_l.npad, st_l.B
     nl = n - ng
-    # communication expert: FP64 GEMM form, as in predict_shared
+    ensure_inverse_factors(st_g, st_l)
+    slices_g = max(slices, 6) if slices >= 5 else slices     # the communication expert enters every expert's result: keep it FP64 grade
+    # communication expert, the same way: V_g^T = K*_g X_g^T (X_g = L_g^-1, lower triangular, digit planes cached on the state),
+    # mean_g = V_g^T z_g, var_g = prior - |V_g|^2.  (The local experts do not need V_g^T here, so it is not kept.)
     mg = torch.empty(1, m, dtype=F64, device=dev)
     vg = torch.empty(1, m, dtype=F64, device=dev)
-    vt = _work("predict_vt", m * st_g.npad * 8, dev)
-    Linv = tril_inverse(st_g)
-    scratch_g = _work("predict_gemm", int(lib.gpr_predict_gemm_scratch_bytes(1, st_g.npad, st_g.dpad, m)), dev)
-    _lib.call("gpr_predict_gemm", _p(Linv), _p(st_g.a), _p(st_g.nrm), _p(st_g.z), _p(st_g.hp), st_g.hp.shape[-1],
-              _p(st_g.prior), _p(xs), 1, st_g.n, st_g.npad, st_g.d, st_g.dpad, m, _p(mg), _p(vg), _p(vt), _p(scratch_g), _stream(),
-              0, None, None)
-    _count(3)
-    ensure_inverse_factors(st_g, st_l)
+    as_g, nrms_g = scale_inputs(xs, st_g.hp[:1], 1, m)
+    Ks_g = _f64_work("emu_ks_g", m * ng, dev).view(m, ng)
+    _lib.call("gpr_se_cross", _p(as_g), _p(nrms_g), m, _p(st_g.a), _p(st_g.nrm), st_g.npad, _p(st_g.hp), st_g.hp.shape[-1],
+              1, m, ng, st_g.dpad, _p(Ks_g), _stream())
+    _count(1)
+    pg = getattr(st_g, "inverse_planes", None)
+    if pg is None or pg.slices != slices_g:
+        pg = st_g.inverse_planes = ozaki_split(tril_inverse(st_g)[0], slices_g)
+    Vg = _f64_work("emu_v_g", m * ng, dev).view(m, ng)
+    ozaki_gemm_nt(ozaki_split(Ks_g, slices_g, bound=float(st_g.hp[0, 0]) ** 2), pg, out=Vg, b_lower=0)
+    zero = torch.zeros(m, dtype=F64, device=dev)
+    _lib.call("gpr_vt_reduce", _p(Vg), ng, _p(st_g.z), st_g.z.stride(0), _p(zero), _p(st_g.prior.expand(m).contiguous()), 1, m, ng,
+              _p(mg), _p(vg), _stream())
+    _count(1)
     ml = torch.empty(B, m, dtype=F64, device=dev)
     vl = torch.empty(B, m, dtype=F64, device=dev)
     cache = getattr(st_l, "plane_cache", None)
