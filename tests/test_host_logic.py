@@ -71,6 +71,19 @@ def test_shard_bounds_cover_all_experts():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
             assert max(hi - lo for lo, hi in parts) == -(-nc // ws)
     assert [hi - lo for lo, hi in (shard_bounds(255, 8, r) for r in range(8))] == [32] * 7 + [31]
+    assert [hi - lo for lo, hi in (shard_bounds(9, 8, r) for r in range(8))] == [2] + [1] * 7      # balanced: no empty rank while nc >= G
+    assert [hi - lo for lo, hi in (shard_bounds(3, 4, r) for r in range(4))] == [1, 1, 1, 0]
+
+
+def test_unsharded_model_enters_no_collective():
+    """Without a process group, and for a model that holds every expert, GRBCM.sharded is False whatever expert_offset / nc_total say
+    (the bench constructs its 1-GPU model with them)."""
+    import pygpr_b200 as P
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+    xl, yl, xg, yg = torch.rand(4, 20, 2), torch.rand(4, 20), torch.rand(10, 2), torch.rand(10)
+    assert not P.GRBCM(xl, yl, xg, yg, cov).sharded
+    assert not P.GRBCM(xl, yl, xg, yg, cov, expert_offset=0, nc_total=4).sharded
+    assert not P.GRBCM(xl, yl, xg, yg, cov, shard=True).sharded
 
 
 def _partial_cpu(mean_l, var_l, var_g, first):
@@ -105,6 +118,15 @@ def _worker(rank, ws, port, tmp):
     ok = torch.allclose(mu_a, mu_ref, rtol=1e-12, atol=1e-14) and torch.allclose(var_a, var_ref, rtol=1e-12, atol=1e-14)
     rows = gdist.all_gather_rows(mean_l[lo:hi].contiguous(), [gdist.shard_bounds(nc, ws, r)[1] - gdist.shard_bounds(nc, ws, r)[0] for r in range(ws)])
     ok = ok and torch.equal(rows, mean_l) and gdist.world() == (rank, ws)
+    # which models enter the collectives: only really sharded ones (a replicated GRBCM under an initialised process group must not
+    # sum its identical partial sums world-size times, nor wait for ranks that never call predict)
+    import pygpr_b200 as P
+    cov = P.Compose([P.Squared_exponential(), P.White_noise()])
+    xl, yl, xg, yg = torch.rand(4, 20, 2), torch.rand(4, 20), torch.rand(10, 2), torch.rand(10)
+    ok = ok and not P.GRBCM(xl, yl, xg, yg, cov).sharded
+    sh = P.GRBCM(xl, yl, xg, yg, cov, shard=True)
+    ok = ok and sh.sharded and sh.nc == 2 and sh.expert_offset == 2 * rank and sh.nc_total == 4
+    ok = ok and P.GRBCM(xl[:2], yl[:2], xg, yg, cov, expert_offset=2 * rank, nc_total=4).sharded
     open(os.path.join(tmp, "ok%d" % rank), "w").write("1" if ok else "0")
     dist.destroy_process_group()
 
