@@ -363,6 +363,9 @@ def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind:
     assert st.alpha is not None
     m = xs.shape[0]
     dev = xs.device
+    from .config import options
+    if want_var and options.emulate_slices > 0 and can_emulate_plain(st):
+        return predict_emulated(st, xs, options.emulate_slices, options.emulate_chunk, tag="_" + scratch_kind)
     mean = torch.empty(st.B, m, dtype=F64, device=dev)
     var = torch.empty(st.B, m, dtype=F64, device=dev) if want_var else None
     if want_var and allow_gemm and _use_gemm_form(st, m):
@@ -432,6 +435,7 @@ def tril_inverse(st: FitState) -> torch.Tensor:
         _lib.call("gpr_tril_inverse", _p(st.L), _p(st.invdiag), st.B, st.npad, _p(X), _p(scratch), _stream())
         _count(3)
         st.Linv = X
+        st.upper_is_inverse = True
     return st.Linv
 
 
@@ -742,107 +746,137 @@ def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = 
     return out
 
 
-def ensure_inverse_factors(st_g: FitState, st_l: FitState) -> None:
-    """L^-T of every local expert, in place in the strict block-upper part of its factor (once per fit): the emulated-FP64
-    prediction multiplies with rows of the explicit inverse.  The shared communication block's L_g^-T is copied, not recomputed."""
+def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
+    """L^-T of every expert of st_l, in place in the strict block-upper part of its factor (once per fit): the emulated-FP64
+    prediction multiplies with rows of the explicit inverse.  With a shared communication block (st_g) its L_g^-T is copied into
+    the leading block, not recomputed."""
     if getattr(st_l, "upper_is_inverse", False):
         return
-    assert st_l.shared_from is st_g and st_g.n % TILE == 0
-    tril_inverse(st_g)                                        # L_g^-T into the block-upper part of the communication factor
-    if not st_l.shared_upper:
-        _lib.call("gpr_copy_leading_block", _p(st_l.L), st_l.B, st_l.npad, _p(st_g.L), st_g.npad, st_g.n, 2, _stream())
-        _count(1)
-        st_l.shared_upper = True
-    scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(st_l.B, st_l.npad)), dtype=torch.uint8, device=st_l.L.device)
-    _lib.call("gpr_trtri_batched", _p(st_l.L), _p(st_l.invdiag), st_l.B, st_l.npad, _p(scratch), _stream(), st_g.n // TILE)
-    _count(2)
+    gt = 0
+    if st_g is not None:
+        assert st_l.shared_from is st_g and st_g.n % TILE == 0
+        if not getattr(st_g, "upper_is_inverse", False):
+            tril_inverse(st_g)                                # L_g^-T into the block-upper part of the communication factor
+        if not st_l.shared_upper:
+            _lib.call("gpr_copy_leading_block", _p(st_l.L), st_l.B, st_l.npad, _p(st_g.L), st_g.npad, st_g.n, 2, _stream())
+            _count(1)
+            st_l.shared_upper = True
+        gt = st_g.n // TILE
+    if st_l.npad > TILE:
+        scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(st_l.B, st_l.npad)), dtype=torch.uint8, device=st_l.L.device)
+        _lib.call("gpr_trtri_batched", _p(st_l.L), _p(st_l.invdiag), st_l.B, st_l.npad, _p(scratch), _stream(), gt)
+        _count(2)
     st_l.upper_is_inverse = True
-    # keep the digit planes of X_l across predictions when HBM allows (8 planes at most, + the transient chunk buffers)
+    # keep the digit planes of the inverse rows across predictions when HBM allows (8 planes at most, + the transient chunk buffers)
     free, _ = torch.cuda.mem_get_info(st_l.L.device)
-    nl = st_l.n - st_g.n
-    if free > st_l.B * nl * st_l.npad * 8 + (16 << 30):
+    rows = st_l.npad - (st_g.n if st_g is not None else 0)
+    if free > st_l.B * rows * st_l.npad * 8 + (16 << 30):
         st_l.plane_cache = {}
 
 
 def can_emulate(st_g: FitState, st_l: FitState) -> bool:
-    """Shapes the emulated-FP64 prediction handles: shared leading block, everything a whole number of 128-row blocks."""
+    """Shapes the emulated-FP64 prediction of a shared-block GRBCM handles: everything a whole number of 128-row blocks."""
     return (st_l.shared_from is st_g and st_g.B == 1 and st_g.n % TILE == 0 and st_l.n % TILE == 0 and st_l.n > st_g.n)
+
+
+def can_emulate_plain(st) -> bool:
+    """A fused fit (not the dense path) whose order is a whole number of 128-row blocks and whose experts stand alone."""
+    return isinstance(st, FitState) and st.n % TILE == 0 and st.alpha is not None
 
 
 def _f64_work(kind: str, numel: int, dev: torch.device) -> torch.Tensor:
     return _work(kind, numel * 8, dev)[: numel * 8].view(F64)
 
 
+def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Tensor, var0: torch.Tensor, slices: int, chunk: int,
+                      tag: str = ""):
+    """mean [B, m], var [B, m] of the experts of `st` from ONE emulated-FP64 GEMM per expert:
+        V^T = K* X^T,  X = rows row0.. of L^-1 (lower trapezoidal),  mean = mean0 + V^T z[row0:],  var = var0 - |V|^2
+    (gpr.py:79-85, 100-104; mean0 / var0 [m] carry the part of the sums that belongs to the rows before row0 — the communication
+    expert's prediction for a shared-block GRBCM, 0 and the prior variance otherwise).  All experts of `st` share one
+    hyper-parameter vector when row0 > 0; otherwise each expert's own amplitude bounds its K*.  xs: [m, d], m % 128 == 0."""
+    m, dev = xs.shape[0], xs.device
+    n, npad, B = st.n, st.npad, st.B
+    nl = n - row0
+    mean = torch.empty(B, m, dtype=F64, device=dev)
+    var = torch.empty(B, m, dtype=F64, device=dev)
+    cache = getattr(st, "plane_cache", None)
+    E = max(1, min(chunk, B))
+    if cache is not None and cache.get("layout") != (E, slices):
+        cache.clear()                                         # planes cached for another chunking / plane count: start over
+        cache["layout"] = (E, slices)
+    per_expert_var0 = var0.dim() == 2
+    sig2 = float((st.hp[:, 0] * st.hp[:, 0]).max())           # 0 < K* <= sig^2 (covar.py:149): the bound of the digit split
+    # transient staging, reused by every chunk (stream-ordered): K* and X in FP64, their digit planes, V^T.  (Preparing chunk c+1 on
+    # a side stream while the tensor cores work on chunk c was measured and dropped: the GEMM's 222 KB of shared memory per SM
+    # leaves no room for the kernel-matrix builder beside it, so the two only time-slice.)
+    Ks = _f64_work("emu_ks" + tag, E * m * n, dev).view(E, m, n)
+    X = _f64_work("emu_x" + tag, E * nl * npad, dev).view(E, nl, npad)
+    V = _f64_work("emu_v" + tag, E * m * nl, dev).view(E, m, nl)
+    bufa = DigitPlanes(E * m, n, slices, _work("emu_pa" + tag, slices * E * m * n, dev), _f64_work("emu_sa" + tag, E * m, dev))
+    bufb = (DigitPlanes(E * nl, npad, slices, _work("emu_pb" + tag, slices * E * nl * npad, dev), _f64_work("emu_sb" + tag, E * nl, dev))
+            if cache is None else None)
+    for e0 in range(0, B, E):
+        e1 = min(e0 + E, B)
+        ne = e1 - e0
+        # scaled test points of the chunk's experts (per-expert length scales), K* [ne, m, n] (covar.py:151-160), its digit planes
+        as_e, nrms_e = scale_inputs(xs, st.hp[e0:e1], ne, m)
+        _lib.call("gpr_se_cross", _p(as_e), _p(nrms_e), m, _p(st.a[e0:e1]), _p(st.nrm[e0:e1]), npad, _p(st.hp[e0:e1]),
+                  st.hp.shape[-1], ne, m, n, st.dpad, _p(Ks), _stream())
+        _count(1)
+        pa = ozaki_split(Ks[:ne].reshape(ne * m, n), slices, bound=sig2, out=bufa)
+        pb = cache.get((e0, e1)) if cache is not None else None
+        if pb is None:
+            _lib.call("gpr_tril_inverse_rows", _p(st.L[e0:e1]), _p(st.invdiag[e0:e1]), ne, npad, row0, _p(X), _stream())
+            _count(1)
+            pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices, out=bufb)
+            if cache is not None:
+                cache[(e0, e1)] = pb
+        ozaki_gemm_nt(pa, pb, out=V[:ne], b_lower=row0, batch=ne)
+        if per_expert_var0:                                   # independent experts: each has its own prior variance
+            for i in range(ne):
+                _lib.call("gpr_vt_reduce", _p(V[i]), nl, _p(st.z[e0 + i, row0:]), st.z.stride(0), _p(mean0), _p(var0[e0 + i]), 1, m, nl,
+                          _p(mean[e0 + i]), _p(var[e0 + i]), _stream())
+            _count(ne)
+        else:
+            _lib.call("gpr_vt_reduce", _p(V), nl, _p(st.z[e0:e1, row0:]), st.z.stride(0), _p(mean0), _p(var0), ne, m, nl, _p(mean[e0:e1]),
+                      _p(var[e0:e1]), _stream())
+            _count(1)
+    return mean, var
+
+
+def _pad_points(xs: torch.Tensor):
+    """Test points in whole 128-row tiles: the last one is repeated (and its results dropped again by the caller)."""
+    m = xs.shape[0]
+    pad = round_up(m, TILE) - m
+    return (torch.cat((xs, xs[-1:].expand(pad, -1))).contiguous() if pad else xs), m
+
+
+def predict_emulated(st: FitState, xs: torch.Tensor, slices: int = 6, chunk: int = 8, tag: str = ""):
+    """engine.predict (gpr.py:76-106) with the K* L^-T product of every expert on the INT8 tensor cores (opt-in):
+    `slices` digit planes per operand (6 = FP64 grade, 4 = FP32 grade); the factorisation stays FP64."""
+    assert can_emulate_plain(st)
+    xp, m = _pad_points(xs)
+    ensure_inverse_factors(None, st)
+    zero = torch.zeros(xp.shape[0], dtype=F64, device=xs.device)
+    prior = st.prior[:, None].expand(st.B, xp.shape[0]).contiguous()
+    mean, var = _emulated_experts(st, xp, 0, zero, prior, slices, chunk, tag)
+    return mean[:, :m].contiguous(), var[:, :m].contiguous()
+
+
 def predict_shared_emulated(st_g: FitState, st_l: FitState, xs: torch.Tensor, slices: int = 6, chunk: int = 8):
-    """predict_shared with the local experts' long product on the INT8 tensor cores (opt-in).
+    """predict_shared with the prediction products on the INT8 tensor cores (opt-in).
 
     For every local expert  V_l^T = K* X_l^T  with X_l = rows ng.. of L^-1 (lower trapezoidal) is ONE emulated-FP64 GEMM
     (gpr_ozaki_gemm_nt, `slices` digit planes per operand, exact int32 accumulation); mean and variance follow as in
     predict_shared (mean_g + V_l^T z_l, var_g - |V_l|^2).  The communication expert is predicted the same way (one triangular
     product with L_g^-1, at no fewer than 6 planes in the FP64-grade modes); the factorisations stay FP64.  Experts go
     through in chunks of `chunk` (transient K*, X_l, digit planes and V_l^T; the digit planes of X_l are kept in
-    ``st_l.plane_cache`` when that dict exists).  Same return value as predict_pair."""
+    ``st_l.plane_cache`` when HBM allows).  Same return value as predict_pair."""
     assert can_emulate(st_g, st_l)
-    m, dev, lib = xs.shape[0], xs.device, _lib.load()
-    if m % TILE:                                              # whole 128-row tiles of test points: repeat the last one, drop it again
-        pad = round_up(m, TILE) - m
-        (mg, vg), (ml, vl) = predict_shared_emulated(st_g, st_l, torch.cat((xs, xs[-1:].expand(pad, -1))).contiguous(), slices, chunk)
-        return (mg[:, :m].contiguous(), vg[:, :m].contiguous()), (ml[:, :m].contiguous(), vl[:, :m].contiguous())
-    ng, n, npad, B = st_g.n, st_l.n, st_l.npad, st_l.B
-    nl = n - ng
+    xp, m = _pad_points(xs)
+    slices_g = max(slices, 6) if slices >= 5 else slices     # the communication expert enters every expert's result
+    mg, vg = predict_emulated(st_g, xp, slices_g, 1, tag="_g")
     ensure_inverse_factors(st_g, st_l)
-    slices_g = max(slices, 6) if slices >= 5 else slices     # the communication expert enters every expert's result: keep it FP64 grade
-    # communication expert, the same way: V_g^T = K*_g X_g^T (X_g = L_g^-1, lower triangular, digit planes cached on the state),
-    # mean_g = V_g^T z_g, var_g = prior - |V_g|^2.  (The local experts do not need V_g^T here, so it is not kept.)
-    mg = torch.empty(1, m, dtype=F64, device=dev)
-    vg = torch.empty(1, m, dtype=F64, device=dev)
-    as_g, nrms_g = scale_inputs(xs, st_g.hp[:1], 1, m)
-    Ks_g = _f64_work("emu_ks_g", m * ng, dev).view(m, ng)
-    _lib.call("gpr_se_cross", _p(as_g), _p(nrms_g), m, _p(st_g.a), _p(st_g.nrm), st_g.npad, _p(st_g.hp), st_g.hp.shape[-1],
-              1, m, ng, st_g.dpad, _p(Ks_g), _stream())
-    _count(1)
-    pg = getattr(st_g, "inverse_planes", None)
-    if pg is None or pg.slices != slices_g:
-        pg = st_g.inverse_planes = ozaki_split(tril_inverse(st_g)[0], slices_g)
-    Vg = _f64_work("emu_v_g", m * ng, dev).view(m, ng)
-    ozaki_gemm_nt(ozaki_split(Ks_g, slices_g, bound=float(st_g.hp[0, 0]) ** 2), pg, out=Vg, b_lower=0)
-    zero = torch.zeros(m, dtype=F64, device=dev)
-    _lib.call("gpr_vt_reduce", _p(Vg), ng, _p(st_g.z), st_g.z.stride(0), _p(zero), _p(st_g.prior.expand(m).contiguous()), 1, m, ng,
-              _p(mg), _p(vg), _stream())
-    _count(1)
-    ml = torch.empty(B, m, dtype=F64, device=dev)
-    vl = torch.empty(B, m, dtype=F64, device=dev)
-    cache = getattr(st_l, "plane_cache", None)
-    E = max(1, min(chunk, B))
-    sig2 = float(st_l.hp[0, 0]) ** 2
-    as_, nrms = scale_inputs(xs, st_l.hp[:1], 1, m)          # one hyper-parameter vector: the scaled test points are shared
-    as_e = as_.expand(E, -1, -1).contiguous()
-    nrms_e = nrms.expand(E, -1).contiguous()
-    # transient staging, reused by every chunk (stream-ordered): K* and X_l in FP64, their digit planes, V_l^T.  (Preparing chunk
-    # c+1 on a side stream while the tensor cores work on chunk c was measured and dropped: the GEMM's 222 KB of shared memory per
-    # SM leaves no room for the kernel-matrix builder beside it, so the two only time-slice.)
-    Ks = _f64_work("emu_ks", E * m * n, dev).view(E, m, n)
-    X = _f64_work("emu_x", E * nl * npad, dev).view(E, nl, npad)
-    V = _f64_work("emu_v", E * m * nl, dev).view(E, m, nl)
-    bufa = DigitPlanes(E * m, n, slices, _work("emu_pa", slices * E * m * n, dev), _f64_work("emu_sa", E * m, dev))
-    bufb = DigitPlanes(E * nl, npad, slices, _work("emu_pb", slices * E * nl * npad, dev), _f64_work("emu_sb", E * nl, dev)) if cache is None else None
-    for e0 in range(0, B, E):
-        e1 = min(e0 + E, B)
-        ne = e1 - e0
-        # K* of the chunk's experts [ne, m, n] (covar.py:151-160), then its digit planes; 0 < K* <= sig^2 (covar.py:149)
-        _lib.call("gpr_se_cross", _p(as_e), _p(nrms_e), m, _p(st_l.a[e0:e1]), _p(st_l.nrm[e0:e1]), npad, _p(st_l.hp[e0:e1]),
-                  st_l.hp.shape[-1], ne, m, n, st_l.dpad, _p(Ks), _stream())
-        _count(1)
-        pa = ozaki_split(Ks[:ne].reshape(ne * m, n), slices, bound=sig2, out=bufa)
-        pb = cache.get(e0) if cache is not None else None
-        if pb is None or pb.slices != slices:
-            _lib.call("gpr_tril_inverse_rows", _p(st_l.L[e0:e1]), _p(st_l.invdiag[e0:e1]), ne, npad, ng, _p(X), _stream())
-            _count(1)
-            pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices, out=bufb)
-            if cache is not None:
-                cache[e0] = pb
-        ozaki_gemm_nt(pa, pb, out=V[:ne], b_lower=ng, batch=ne)
-        _lib.call("gpr_vt_reduce", _p(V), nl, _p(st_l.z[e0:e1, ng:]), st_l.z.stride(0), _p(mg), _p(vg), ne, m, nl, _p(ml[e0:e1]),
-                  _p(vl[e0:e1]), _stream())
-        _count(1)
-    return (mg, vg), (ml, vl)
+    ml, vl = _emulated_experts(st_l, xp, st_g.n, mg[0], vg[0], slices, chunk)
+    return (mg[:, :m].contiguous(), vg[:, :m].contiguous()), (ml[:, :m].contiguous(), vl[:, :m].contiguous())

@@ -191,6 +191,16 @@ def test_benchmarked_grbcm_path_against_oracle(monkeypatch):
     nl_o = torch.cat([orc.mle_loss(["se", "wn"], hp[i:i + 1], xa[i:i + 1], ya[i:i + 1]) for i in range(ns)])
     assert_close(st.nlml()[:ns].cpu().numpy(), nl_o.numpy(), TOL, "NLML of the local experts")
     assert_close(stg.nlml().cpu().numpy(), orc.mle_loss(["se", "wn"], hp[:1], xall[:1], yall[:1]).numpy(), TOL, "NLML of the communication expert")
+    # the opt-in emulated-FP64 prediction at the same sizes (6 digit planes on the INT8 tcgen05 tensor cores) against the oracle
+    monkeypatch.setattr(config.options, "emulate_slices", 6)
+    (mg_e, vg_e), (ml_e, vl_e) = eng.predict_pair(stg, st, xs.cuda())
+    monkeypatch.setattr(config.options, "emulate_slices", 0)
+    assert_close(mg_e[0].cpu().numpy(), parts["mean_g"].numpy(), TOL, "communication expert mean (emulated)")
+    assert_close(vg_e[0].cpu().numpy(), parts["var_g"].numpy(), TOL, "communication expert variance (emulated)")
+    assert_close(ml_e[:ns].cpu().numpy(), parts["mean_l"].numpy(), TOL, "local expert means (emulated)")
+    assert_close(vl_e[:ns].cpu().numpy(), parts["var_l"].numpy(), TOL, "local expert variances (emulated)")
+    assert_close(ml_e.cpu().numpy(), ml.cpu().numpy(), 1e-9, "emulated == FP64 path, all experts (mean)")
+    assert_close(vl_e.cpu().numpy(), vl.cpu().numpy(), 1e-9, "emulated == FP64 path, all experts (variance)")
     # all six experts: shared-block path == general path
     mdl0, mu0, var0 = run(False)
     assert_close(torch.as_tensor(mu).numpy(), torch.as_tensor(mu0).numpy(), 1e-10, "shared == general (mean)")
