@@ -143,6 +143,24 @@ def main():
         out["mu_full"] = _np(mu_f); out["cov_full"] = _np(cov_f)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
+    # ---- samplers / partitioning (sampler.py): UNIFORM, MATERN1.sample / cluster_samples / partition, euclidean_dist, cluster_samples ----
+    name = "sampler_seed3_seed5"
+    if not ONLY or any(o in name for o in ONLY):
+        mins, maxs = torch.zeros(2), torch.ones(2) * 2.0
+        xu = ref.UNIFORM(3).sample(500, mins, maxs)
+        mat = ref.MATERN1(5)
+        parts, centres = mat.partition(6, 20, mins, maxs)
+        dist = ref.euclidean_dist(xu, centres)
+        # cluster_samples needs equal-sized cells: a 2 x 2 grid of centres and 25 points per cell drawn around them
+        g = torch.Generator().manual_seed(9)
+        grid = torch.tensor([[0.5, 0.5], [0.5, 1.5], [1.5, 0.5], [1.5, 1.5]])
+        pts = (grid[:, None, :] + 0.4 * (torch.rand(4, 25, 2, generator=g, dtype=torch.float64) - 0.5)).reshape(100, 2)
+        pts = pts[torch.randperm(100, generator=g)]
+        cells = ref.cluster_samples(pts, grid)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), mins=_np(mins), maxs=_np(maxs), uniform=_np(xu), parts=_np(parts),
+                            centres=_np(centres), min_dist=np.float64(float(mat.min_dist)), dist=_np(dist), grid=_np(grid), pts=_np(pts),
+                            cells=_np(cells))
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

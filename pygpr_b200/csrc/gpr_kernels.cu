@@ -190,51 +190,128 @@ __global__ void __launch_bounds__(NTHREADS) se_tile_kernel(const double* __restr
     else gen_se_tile<false>(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig2, store);
 }
 
+// The same tile for WIDE inputs (dpad beyond what two [128 x dpad] feature tiles can occupy in shared memory, d >= 109): the
+// cross term is accumulated over slices of SE_SLICE features — load a slice of both feature tiles, 4 x 8 DMMA blocks per k4 step
+// into the thread's accumulators, next slice — and the epilogue is the one of se_tile_kernel.  The reference has no limit on d
+// (covar.py:102-127 is a plain matmul); neither has the kernel-level API now.
+constexpr int SE_SLICE = 64;
+__global__ void __launch_bounds__(NTHREADS) se_tile_wide_kernel(const double* __restrict__ aR, const double* __restrict__ nrmR,
+                                                                int rpad, const double* __restrict__ aC,
+                                                                const double* __restrict__ nrmC, int cpad,
+                                                                const double* __restrict__ hp, int hp_stride,
+                                                                const double* __restrict__ diag_add, int nrows, int ncols,
+                                                                int dpad, double* __restrict__ out, long long ld,
+                                                                long long out_bstride, int mode, int pad_identity,
+                                                                int lower_only) {
+    extern __shared__ double smem[];
+    const int tc = blockIdx.x, tr = blockIdx.y, b = blockIdx.z;
+    if (lower_only && tc > tr) return;
+    FeatSmem f = carve_feat(smem, SE_SLICE);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    if (threadIdx.x < TILE) {
+        f.nR[threadIdx.x] = nrmR[(long long)b * rpad + tr * TILE + threadIdx.x];
+        f.nC[threadIdx.x] = nrmC[(long long)b * cpad + tc * TILE + threadIdx.x];
+    }
+    double acc[4][8][2];
+    zero_acc(acc);
+    const double* gR = aR + ((long long)b * rpad + tr * TILE) * dpad;
+    const double* gC = aC + ((long long)b * cpad + tc * TILE) * dpad;
+    for (int k0 = 0; k0 < dpad; k0 += SE_SLICE) {
+        const int ds = (dpad - k0 < SE_SLICE) ? dpad - k0 : SE_SLICE;   // a multiple of 4 (dpad is)
+        __syncthreads();                                                 // the previous slice has been consumed
+        const int per_row = ds / 2;
+        for (int id = threadIdx.x; id < TILE * per_row; id += NTHREADS) {
+            const int row = id / per_row, cc = (id % per_row) * 2;
+            cp_async16(f.sR + row * f.sld + cc, gR + (long long)row * dpad + k0 + cc);
+            cp_async16(f.sC + row * f.sld + cc, gC + (long long)row * dpad + k0 + cc);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        const double* pa = f.sR + (wm * 32 + g) * f.sld + t;
+        const double* pb = f.sC + (wn * 64 + g) * f.sld + t;
+        for (int k = 0; k < ds; k += 4) {
+            double fa[4], fb[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) fa[mi] = pa[mi * 8 * f.sld + k];
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) fb[ni] = pb[ni * 8 * f.sld + k];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], fa[mi], fb[ni]);
+        }
+    }
+    const double sig = hp[(long long)b * hp_stride];
+    const double sig2 = sig * sig;
+    const double dadd = (mode == 0 && diag_add) ? diag_add[b] : 0.0;
+    double* ob = out + (long long)b * out_bstride;
+    const long long lim_r = (mode == 0 && pad_identity) ? ld : nrows;
+    const long long lim_c = (mode == 0 && pad_identity) ? ld : ncols;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const double nr = f.nR[wm * 32 + mi * 8 + g];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double d2 = -2.0 * acc[mi][ni][e] + (nr + f.nC[wn * 64 + ni * 8 + 2 * t + e]);
+                const double kv = (mode == 2) ? d2 : sig2 * exp_neg(d2);
+                const long long r = (long long)tr * TILE + acc_row(mi);
+                const long long c = (long long)tc * TILE + acc_col(ni, e);
+                if (r < nrows && c < ncols) ob[r * ld + c] = (mode == 0 && r == c) ? kv + dadd : kv;
+                else if (r < lim_r && c < lim_c) ob[r * ld + c] = (r == c) ? 1.0 : 0.0;
+            }
+    }
+}
+
+// launches the tile builder that fits: the whole feature tiles in shared memory, or slices of them for wide inputs
+static int launch_se_tile(dim3 grid, cudaStream_t st, const double* aR, const double* nrmR, int rpad, const double* aC,
+                          const double* nrmC, int cpad, const double* hp, int hp_stride, const double* diag_add, int nrows, int ncols,
+                          int dpad, double* out, long long ld, long long out_bstride, int mode, int pad_identity, int lower_only) {
+    const int smem = feat_smem_bytes(dpad);
+    if (smem <= 227 * 1024) {
+        CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
+        se_tile_kernel<<<grid, NTHREADS, smem, st>>>(aR, nrmR, rpad, aC, nrmC, cpad, hp, hp_stride, diag_add, nrows, ncols, dpad, out, ld,
+                                                     out_bstride, mode, pad_identity, lower_only);
+    } else {
+        const int smem_w = feat_smem_bytes(SE_SLICE);
+        CUDA_TRY(opt_in_smem(se_tile_wide_kernel, smem_w));
+        se_tile_wide_kernel<<<grid, NTHREADS, smem_w, st>>>(aR, nrmR, rpad, aC, nrmC, cpad, hp, hp_stride, diag_add, nrows, ncols, dpad, out,
+                                                            ld, out_bstride, mode, pad_identity, lower_only);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
 extern "C" int gpr_se_build(const double* a, const double* nrm, const double* hp, int hp_stride, const double* diag_add,
                             int B, int n, int npad, int dpad, double* K, int ldk, int pad_identity, int lower_only,
                             void* stream) {
     ARG_CHECK(a && nrm && hp && K);
     ARG_CHECK(B > 0 && n > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && ldk >= n);
     ARG_CHECK(!pad_identity || ldk <= npad);
-    const int smem = feat_smem_bytes(dpad);
-    if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused SE tile%s (dpad=%lld)", "", dpad);
-    CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
     const int nt = (pad_identity ? (ldk + TILE - 1) / TILE : (n + TILE - 1) / TILE);
-    dim3 grid(nt, nt, B);
-    se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a, nrm, npad, a, nrm, npad, hp, hp_stride, diag_add, n, n,
-                                                                   dpad, K, ldk, (long long)ldk * ldk, 0, pad_identity,
-                                                                   lower_only);
-    CUDA_TRY(cudaGetLastError());
-    return GPR_OK;
+    return launch_se_tile(dim3(nt, nt, B), (cudaStream_t)stream, a, nrm, npad, a, nrm, npad, hp, hp_stride, diag_add, n, n, dpad, K, ldk,
+                          (long long)ldk * ldk, 0, pad_identity, lower_only);
 }
 
 extern "C" int gpr_se_cross(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
                             const double* hp, int hp_stride, int B, int m, int n, int dpad, double* Ks, void* stream) {
     ARG_CHECK(as && nrms && a && nrm && hp && Ks);
     ARG_CHECK(B > 0 && m > 0 && n > 0 && mpad % TILE == 0 && npad % TILE == 0 && mpad >= m && npad >= n && dpad % 4 == 0);
-    const int smem = feat_smem_bytes(dpad);
-    if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused SE tile%s (dpad=%lld)", "", dpad);
-    CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
-    dim3 grid((n + TILE - 1) / TILE, (m + TILE - 1) / TILE, B);
-    se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(as, nrms, mpad, a, nrm, npad, hp, hp_stride, nullptr, m, n,
-                                                                   dpad, Ks, n, (long long)m * n, 1, 0, 0);
-    CUDA_TRY(cudaGetLastError());
-    return GPR_OK;
+    return launch_se_tile(dim3((n + TILE - 1) / TILE, (m + TILE - 1) / TILE, B), (cudaStream_t)stream, as, nrms, mpad, a, nrm, npad, hp,
+                          hp_stride, nullptr, m, n, dpad, Ks, n, (long long)m * n, 1, 0, 0);
 }
 
 // Squared Euclidean distances in GEMM form, D[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   (sampler.py:94-100, N3)
 extern "C" int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay, const double* ny, int npady, int nx_rows,
                            int ny_rows, int dpad, double* D, void* stream) {
     ARG_CHECK(ax && nx && ay && ny && D && nx_rows > 0 && ny_rows > 0 && npadx % TILE == 0 && npady % TILE == 0 && dpad % 4 == 0);
-    const int smem = feat_smem_bytes(dpad);
-    if (smem > 227 * 1024) return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the distance tile%s (dpad=%lld)", "", dpad);
-    CUDA_TRY(opt_in_smem(se_tile_kernel, smem));
-    dim3 grid((ny_rows + TILE - 1) / TILE, (nx_rows + TILE - 1) / TILE, 1);
     // hp is only read for sig (unused in raw mode); pass nx as a valid device pointer
-    se_tile_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(ax, nx, npadx, ay, ny, npady, nx, 0, nullptr, nx_rows, ny_rows, dpad,
-                                                                   D, ny_rows, 0, 2, 0, 0);
-    CUDA_TRY(cudaGetLastError());
-    return GPR_OK;
+    return launch_se_tile(dim3((ny_rows + TILE - 1) / TILE, (nx_rows + TILE - 1) / TILE, 1), (cudaStream_t)stream, ax, nx, npadx, ay, ny,
+                          npady, nx, 0, nullptr, nx_rows, ny_rows, dpad, D, ny_rows, 0, 2, 0, 0);
 }
 
 // dK materialisation for kernel_and_grad (API parity; small n only)                 covar.py:184-199

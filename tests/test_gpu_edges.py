@@ -122,17 +122,22 @@ def test_config2_shape_lml_grad_matches_oracle_at_reduced_n(P, orc):
     lo, go = orc.mle_loss_and_grad(["se", "wn"], _hp(1, d), x[None], y[None])
     assert_close(np.atleast_1d(loss), lo.numpy(), TOL, "nlml")
     assert_close(grad, go[0].numpy(), TOL, "grad")
+    D = P.euclidean_dist(x, xs)                               # sampler.py:94-100 on the same wide inputs
+    assert_close(D.numpy(), (x[:, None, :] - xs[None]).square().sum(-1).numpy(), 1e-12, "euclidean_dist")
     gamma = P.get_learn_rate(gp.params, mle, 1e-4)
     go_gamma = orc.learn_rate(["se", "wn"], _hp(1, d), x[None], y[None], 1e-4)
     assert_close(np.atleast_1d(gamma), go_gamma.numpy(), 1e-3, "gamma")
 
 
-def test_wide_inputs_take_the_dense_path(P, orc):
+@pytest.mark.parametrize("d", [64, 130, 301])
+def test_wide_inputs_take_the_dense_path(P, orc, d):
     """d = 64 is beyond what the on-chip tile generation holds in shared memory (d <= 44): the model falls back to materialised
-    kernel matrices instead of raising, with the reference's results."""
+    kernel matrices instead of raising, with the reference's results.  d = 130 / 301 are beyond what the stand-alone tile builder
+    holds at once (d <= 108): it accumulates the cross term over feature slices (se_tile_wide_kernel) — like the reference, the
+    kernel-level API has no limit on d."""
     from pygpr_b200 import engine
     g = torch.Generator().manual_seed(9)
-    n, d, m = 200, 64, 50
+    n, m = 200, 50
     x = torch.rand(n, d, generator=g, dtype=torch.float64)
     y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(n, generator=g, dtype=torch.float64)
     xs = torch.rand(m, d, generator=g, dtype=torch.float64)
