@@ -433,6 +433,17 @@ def main():
                        "the headline `value` is the FP64 DMMA path"}
         emu_last = dict(last)
         last.update(ml=ml_fp64, vl=vl_fp64, mg=mg_fp64, vg=vg_fp64)
+        if grad_ms is not None:
+            # the NLML gradient with K^-1 = L^-T L^-1 on the INT8 tensor cores (7 digit planes; L^-T stays the FP64 blocked trtri)
+            config.options.emulate_grad_slices = 7
+            eng.lml_grad(st); barrier()
+            barrier(); e0.record(); g_e = eng.lml_grad(st); e1.record(); barrier()
+            config.options.emulate_grad_slices = 0
+            eg_ms = max_over_ranks(e0.elapsed_time(e1))
+            emu["lml_grad"] = {"slices": 7, "ms": eg_ms, "speedup_vs_fp64_path": grad_ms / eg_ms,
+                               "grad_vs_fp64_path": float((g_e - g).abs().max() / g.abs().max()),
+                               "what": "engine.lml_grad with options.emulate_grad_slices: L^-T by the FP64 blocked trtri, K^-1 = U U^T as one "
+                                       "batched emulated-FP64 GEMM per chunk of experts, then the fused gradient reduction on K^-1"}
 
     # checksum of the aggregate, identical on every rank after the all-reduce: equal across N = 1/2/4/8 to ~1e-12 means the
     # sharded aggregation reproduces the single-GPU one (the driver-side multi-GPU parity check)

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 4
+#define GPR_ABI_VERSION 5
 
 typedef enum {
     GPR_OK = 0,
@@ -320,6 +320,9 @@ int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay,
  *                        k-blocks are skipped;  K * slices < 2^17 (int32 headroom).  batch > 1: `batch` independent products
  *                        in one launch — the plane arrays hold the operands of all batch entries stacked along the (padded)
  *                        row dimension (split the stacked matrices; rows must then be multiples of 128), C at c_batch_stride.
+ *                        a_upper = o >= 0: A[i, k] = 0 for k < i + o (rows of an upper-triangular factor; the leading zero
+ *                        k-blocks are skipped), -1: dense A.  c_lower != 0: only the 128 x 64 tiles that touch the lower
+ *                        triangle of C are computed and written (K^-1 = U U^T for the NLML gradient, loss.py:77,116).
  */
 long long gpr_ozaki_rows_padded(int rows);
 long long gpr_ozaki_k_padded(int k);
@@ -328,7 +331,7 @@ int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, 
                     void* stream);
 int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                       int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch, long long c_batch_stride,
-                      void* stream);
+                      int a_upper, int c_lower, void* stream);
 
 /* pieces of the emulated-FP64 prediction (opt-in): V_l^T = K* X_l^T with X_l = rows of the explicit inverse L^-1, the product on
  * the INT8 tensor cores (gpr_ozaki_gemm_nt).  Stands in for tc.cholesky_solve(K*^T, L) + the row sums of gpr.py:100-104 and the
@@ -343,6 +346,18 @@ int gpr_trtri_batched(double* L, const double* invdiag, int B, int npad, void* s
 int gpr_tril_inverse_rows(const double* L, const double* invdiag, int B, int npad, int row0, double* X, void* stream);
 int gpr_vt_reduce(const double* V, long long ldv, const double* z, long long z_stride, const double* mean_g, const double* var_g,
                   int E, int m, int nl, double* mean, double* var, void* stream);
+
+/* pieces of the emulated-FP64 NLML gradient (opt-in): K^-1 = U U^T (U = L^-T, tc.cholesky_solve(dK, L) + traces of loss.py:77-84,
+ * 116-121 reformulated as in gpr_lml_grad) with the product on the INT8 tensor cores.
+ *   gpr_triu_rows        Ud [B, npad, npad] = the rows of U as a dense upper-triangular matrix (zeros below the diagonal blocks),
+ *                        out of the in-place L^-T in the block-upper part of L and the diagonal-block inverses
+ *   gpr_grad_from_kinv   grad [B, P] from materialised K^-1 (lower 128 x 128 tiles of Kinv [B, ldk, ldk] read): the epilogue of
+ *                        gpr_lml_grad — M = (K^-1 - alpha alpha^T) o K_se with K_se generated on chip, reduced per hyper-parameter;
+ *                        scratch: gpr_lml_grad_scratch_bytes(B, npad, d)
+ */
+int gpr_triu_rows(const double* L, const double* invdiag, int B, int npad, double* Ud, void* stream);
+int gpr_grad_from_kinv(const double* Kinv, int ldk, const double* a, const double* nrm, const double* alpha, const double* hp,
+                       int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad, double* grad, void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@ Every knob takes its initial value from the environment ONCE, at import; afterwa
     PYGPR_PREDICT_FORM=...     options.predict_form   auto | subst | gemm  (engine.predict)
     PYGPR_EMULATE_FP64=s       options.emulate_slices  GRBCM predictions through the emulated-FP64 GEMM with s digit planes (0 = off)
     PYGPR_EMULATE_CHUNK=e      options.emulate_chunk   experts per batched emulated product
+    PYGPR_EMULATE_FP64_GRAD=s  options.emulate_grad_slices  K^-1 of the NLML gradient through the emulated-FP64 GEMM (0 = off)
     PYGPR_POTRF_MODE=...       set_potrf_mode()     auto | columns | columns1 | dataflow
     PYGPR_TRSV_MODE=...        set_trsv_mode()      auto | single
 """
@@ -30,6 +31,9 @@ class Options:
     # (0 = off, the FP64 DMMA path; 6 = FP64 grade, ~1e-11 on V; 3-4 = the FP32-grade mode).  engine.predict_shared_emulated
     emulate_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64", "0"))
     emulate_chunk: int = int(os.environ.get("PYGPR_EMULATE_CHUNK", "8"))
+    # opt-in: K^-1 = L^-T L^-1 of the NLML gradient on the INT8 tensor cores with this many digit planes (0 = off; 7 keeps the
+    # gradient at ~1e-10 of the FP64 path).  engine.lml_grad_emulated
+    emulate_grad_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_GRAD", "0"))
 
 
 options = Options()

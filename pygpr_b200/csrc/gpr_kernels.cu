@@ -2077,7 +2077,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdiagT, const double* __restrict__ a,
                   const double* __restrict__ nrm, const double* __restrict__ alpha, const double* __restrict__ hp, int hp_stride,
                   int n, int npad, int d, int dpad, double* __restrict__ partials, int P, int gt, const double* __restrict__ Kinv_g,
-                  int ldg) {
+                  int ldg, const double* __restrict__ Kinv_full = nullptr, int ldk = 0) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -2104,16 +2104,30 @@ lauum_grad_kernel(const double* __restrict__ L, const double* __restrict__ invdi
     Seg s0{Uii, TILE, (i == j) ? Uii : Uj + (long long)i * TILE, (i == j) ? (long long)TILE : (long long)npad, in_shared ? 0 : TILE / KC};
     const int k0 = in_shared ? gt : i + 1;
     Seg s1{Ui + (long long)k0 * TILE, npad, Uj + (long long)k0 * TILE, npad, (nt - k0) * (TILE / KC)};
-    mainloop<false, XPF_LAUUM>(acc, s0, s1, smem, nh, pipe);
-    if (in_shared) {
+    if (Kinv_full) {
+        // K^-1 comes materialised (gpr_grad_from_kinv: the emulated-FP64 product wrote it): the tile is read, not multiplied
+        const double* kb = Kinv_full + (long long)b * ldk * ldk;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni) {
-                const double2 v = *reinterpret_cast<const double2*>(Kinv_g + ((long long)i * TILE + acc_row(mi)) * ldg + j * TILE + acc_col(ni, 0));
-                acc[mi][ni][0] += v.x;
-                acc[mi][ni][1] += v.y;
+                const double2 v = *reinterpret_cast<const double2*>(kb + ((long long)i * TILE + acc_row(mi)) * ldk + j * TILE + acc_col(ni, 0));
+                acc[mi][ni][0] = v.x;
+                acc[mi][ni][1] = v.y;
             }
+    } else {
+        mainloop<false, XPF_LAUUM>(acc, s0, s1, smem, nh, pipe);
+        if (in_shared) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) {
+                    const double2 v = *reinterpret_cast<const double2*>(Kinv_g + ((long long)i * TILE + acc_row(mi)) * ldg + j * TILE + acc_col(ni, 0));
+                    acc[mi][ni][0] += v.x;
+                    acc[mi][ni][1] += v.y;
+                }
+        }
+        __syncthreads();                                         // the pipeline's shared memory becomes the epilogue's tile below
     }
 
     // epilogue: M = (K^-1 - alpha_i alpha_j^T) o K_se  -> smem tile
@@ -2235,6 +2249,58 @@ static int lml_grad_impl(double* L, const double* invdiag, const double* a, cons
     CUDA_TRY(opt_in_smem(lauum_grad_kernel, smem));
     lauum_grad_kernel<<<dim3(ntiles, B), NTHREADS, smem, st>>>(L, invdiagT, a, nrm, alpha, hp, hp_stride, n, npad, d, dpad,
                                                                partials, P, gt, Kinv_g, ldg);
+    grad_finalize_kernel<<<B, ((P + 31) / 32) * 32, 0, st>>>(partials, ntiles, P, hp, hp_stride, d, grad);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+// ---- emulated-FP64 gradient pieces (engine.lml_grad_emulated): K^-1 = U U^T comes from gpr_ozaki_gemm_nt ---------------------------
+__global__ void triu_rows_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad, double* __restrict__ Ud) {
+    // Ud[r][c] = U[r][c]: block column > block row from the strict block-upper part of L, diagonal blocks = inv(L_ii)^T, zeros below
+    __shared__ double t[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int br = r0 / TILE, bc = c0 / TILE, nt = npad / TILE;
+    const double* Lb = L + (long long)b * npad * npad;
+    double* Ub = Ud + (long long)b * npad * npad;
+    if (bc < br) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) Ub[(long long)(r0 + r) * npad + c0 + threadIdx.x] = 0.0;
+    } else if (bc > br) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y)
+            Ub[(long long)(r0 + r) * npad + c0 + threadIdx.x] = Lb[(long long)(r0 + r) * npad + c0 + threadIdx.x];
+    } else {
+        const double* inv = invdiag + ((long long)b * nt + br) * TILE * TILE;
+        const int rr = r0 - br * TILE, cc = c0 - bc * TILE;
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = inv[(cc + r) * TILE + rr + threadIdx.x];   // inv[c][r]
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) Ub[(long long)(r0 + r) * npad + c0 + threadIdx.x] = t[threadIdx.x][r];
+    }
+}
+
+extern "C" int gpr_triu_rows(const double* L, const double* invdiag, int B, int npad, double* Ud, void* stream) {
+    ARG_CHECK(L && invdiag && Ud && B > 0 && npad > 0 && npad % TILE == 0);
+    triu_rows_kernel<<<dim3(npad / 32, npad / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(L, invdiag, npad, Ud);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
+extern "C" int gpr_grad_from_kinv(const double* Kinv, int ldk, const double* a, const double* nrm, const double* alpha,
+                                  const double* hp, int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad,
+                                  double* grad, void* scratch, void* stream) {
+    ARG_CHECK(Kinv && a && nrm && alpha && hp && grad && scratch);
+    ARG_CHECK(B > 0 && n > 0 && d > 0 && npad % TILE == 0 && npad >= n && dpad % 4 == 0 && dpad >= d && ldk >= npad && ldk % 2 == 0);
+    const long long smem_l = lml_feat_bytes(dpad);
+    if (smem_l > 227 * 1024 || d + 2 > NTHREADS)
+        return fail(GPR_ERR_UNSUPPORTED, "input dimension too large for the fused gradient%s (dpad=%lld)", "", dpad);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = npad / TILE;
+    const int ntiles = nt * (nt + 1) / 2;
+    const int P = d + 1 + (has_noise ? 1 : 0);
+    double* partials = reinterpret_cast<double*>(scratch);
+    const int smem = (int)(smem_l > MAIN_SMEM_BYTES ? smem_l : MAIN_SMEM_BYTES);
+    CUDA_TRY(opt_in_smem(lauum_grad_kernel, smem));
+    lauum_grad_kernel<<<dim3(ntiles, B), NTHREADS, smem, st>>>(nullptr, nullptr, a, nrm, alpha, hp, hp_stride, n, npad, d, dpad,
+                                                               partials, P, 0, nullptr, 0, Kinv, ldk);
     grad_finalize_kernel<<<B, ((P + 31) / 32) * 32, 0, st>>>(partials, ntiles, P, hp, hp_stride, d, grad);
     CUDA_TRY(cudaGetLastError());
     return GPR_OK;

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ C, long long ldc,
             int M, int N, int kpad, int stages, int b_lower, double beta, int group_m, int tmem_cols,
-            int a_batch_rows, int b_batch_rows, long long c_batch_stride) {
+            int a_batch_rows, int b_batch_rows, long long c_batch_stride, int a_upper, int c_lower) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled tiles want (at least) 512 B alignment
@@ -240,8 +240,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int tm = first_m + in_group % gsz;
     int tn = in_group / gsz;
     if (b_lower >= 0) tn = tiles_n - 1 - tn;
+    if (c_lower && tn * BN > tm * BM + BM - 1) return;          // only tiles on / below the diagonal of C are wanted (whole CTA leaves)
     int nkb = kpad / BK;
     if (b_lower >= 0) nkb = min(nkb, (b_lower + (tn + 1) * BN + BK - 1) / BK);   // B[j, k] = 0 for k > j + b_lower
+    const int kb0 = a_upper >= 0 ? min(nkb - 1, (a_upper + tm * BM) / BK) : 0;  // A[i, k] = 0 for k < i + a_upper (rows of an upper factor)
     // batched product: batch entry blockIdx.y owns a_batch_rows / b_batch_rows consecutive (padded) rows of the plane arrays
     const int a_row0 = blockIdx.y * a_batch_rows + tm * BM, b_row0 = blockIdx.y * b_batch_rows + tn * BN;
     scaleA += (long long)blockIdx.y * a_batch_rows;
@@ -274,7 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < nkb; ++kb) {
             mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
             if (leader) {
                 const uint32_t full = bar_full + 8u * stage;
@@ -291,13 +293,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < nkb; ++kb) {
             mbar_wait(bar_full + 8u * stage, phase);
             tc_fence_after();
             const uint32_t a_lo = desc_lo(base + (uint32_t)(stage * sbytes));
             const uint32_t b_lo = a_lo + (uint32_t)((S * A_PLANE) >> 4);
             if (leader) {
-                if (kb == 0) issue_k_block<S, true>(tmem, a_lo, b_lo);
+                if (kb == kb0) issue_k_block<S, true>(tmem, a_lo, b_lo);
                 else issue_k_block<S, false>(tmem, a_lo, b_lo);
                 umma_commit(bar_empty + 8u * stage);       // ring slot free once these products have read it
             }
@@ -405,9 +407,9 @@ extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, i
 
 extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                                  int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch,
-                                 long long c_batch_stride, void* stream) {
+                                 long long c_batch_stride, int a_upper, int c_lower, void* stream) {
     if (!(planesA && planesB && scaleA && scaleB && C && M > 0 && N > 0 && K > 0 && ldc >= N && slices >= 1 && slices <= oz::MAX_SLICES &&
-          batch >= 1 && batch <= 65535 && b_lower >= -1))
+          batch >= 1 && batch <= 65535 && b_lower >= -1 && a_upper >= -1))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_gemm_nt%s (slices=%lld)", "", slices);
     // int32 headroom of a diagonal: (g+1) products of |q| <= 128 over K terms
     if ((long long)K * slices * 16384LL >= (1LL << 31))
@@ -435,7 +437,7 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
         if (e == cudaSuccess)                                                                                                  \
             oz::gemm_kernel<S><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                   \
                 mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA, rpadB,       \
-                c_batch_stride);                                                                                               \
+                c_batch_stride, a_upper, c_lower);                                                                             \
         break;
     switch (slices) {
         OZ_LAUNCH(1) OZ_LAUNCH(2) OZ_LAUNCH(3) OZ_LAUNCH(4) OZ_LAUNCH(5) OZ_LAUNCH(6) OZ_LAUNCH(7) OZ_LAUNCH(8)

@@ -483,9 +483,43 @@ def kinv(st: FitState) -> torch.Tensor:
     return st.Kinv
 
 
+def lml_grad_emulated(st: FitState, slices: int = 7, chunk: int = 8) -> torch.Tensor:
+    """lml_grad with K^-1 = U U^T (U = L^-T) on the INT8 tensor cores (opt-in): L^-T stays the FP64 blocked
+    trtri (in place), then per chunk of experts the rows of U go through gpr_triu_rows -> gpr_ozaki_split, ONE batched
+    gpr_ozaki_gemm_nt (a_upper: the zero k-blocks before the diagonal are skipped; c_lower: only the lower tiles) writes K^-1,
+    and gpr_grad_from_kinv runs gpr_lml_grad's fused reduction on it (dK never formed).  loss.py:59-128."""
+    assert st.alpha is not None and st.n % TILE == 0
+    ensure_inverse_factors(st.shared_from, st)               # L^-T of every expert, in place (the shared block's is copied)
+    dev, B, npad = st.L.device, st.B, st.npad
+    P = st.d + 1 + int(st.has_noise)
+    grad = torch.empty(B, P, dtype=F64, device=dev)
+    # experts per batched product: what the free HBM holds of the three staging buffers (rows of U, its digit planes, K^-1)
+    per = npad * npad * (16 + slices) + (1 << 20)
+    held = sum(b.numel() for k, b in _scratch_cache.items() if k[0] == dev.index and str(k[1]).startswith("emg_"))
+    free, _ = torch.cuda.mem_get_info(dev)
+    E = int(max(1, min(chunk, B, (free + held - (2 << 30)) // per)))
+    Ud = _f64_work("emg_u", E * npad * npad, dev).view(E, npad, npad)
+    Kinv = _f64_work("emg_kinv", E * npad * npad, dev).view(E, npad, npad)
+    buf = DigitPlanes(E * npad, npad, slices, _work("emg_p", slices * E * npad * npad, dev), _f64_work("emg_s", E * npad, dev))
+    scratch = _work("emg_scratch", int(_lib.load().gpr_lml_grad_scratch_bytes(E, npad, st.d)), dev)
+    for e0 in range(0, B, E):
+        e1 = min(e0 + E, B)
+        ne = e1 - e0
+        _lib.call("gpr_triu_rows", _p(st.L[e0:e1]), _p(st.invdiag[e0:e1]), ne, npad, _p(Ud), _stream())
+        pu = ozaki_split(Ud[:ne].reshape(ne * npad, npad), slices, out=buf)
+        ozaki_gemm_nt(pu, pu, out=Kinv[:ne], batch=ne, a_upper=0, c_lower=True)
+        _lib.call("gpr_grad_from_kinv", _p(Kinv), npad, _p(st.a[e0:e1]), _p(st.nrm[e0:e1]), _p(st.alpha[e0:e1]), _p(st.hp[e0:e1]),
+                  st.hp.shape[-1], int(st.has_noise), ne, st.n, npad, st.d, st.dpad, _p(grad[e0:e1]), _p(scratch), _stream())
+        _count(4)
+    return grad
+
+
 def lml_grad(st: FitState) -> torch.Tensor:
     """d NLML / d hp [B, P] from a finished fit (destroys the strict block-upper part of st.L)   loss.py:59-128."""
     assert st.alpha is not None
+    from .config import options
+    if options.emulate_grad_slices > 0 and st.n % TILE == 0 and st.npad > TILE and (st.shared_from is None or st.shared_from.n % TILE == 0):
+        return lml_grad_emulated(st, options.emulate_grad_slices, options.emulate_chunk)
     P = st.d + 1 + int(st.has_noise)
     grad = torch.empty(st.B, P, dtype=F64, device=st.L.device)
     nbytes = int(_lib.load().gpr_lml_grad_scratch_bytes(st.B, st.npad, st.d))
@@ -724,11 +758,12 @@ def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0, out: Optional[
 
 
 def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = None, beta: float = 0.0,
-                  b_lower: Optional[int] = None, batch: int = 1) -> torch.Tensor:
+                  b_lower: Optional[int] = None, batch: int = 1, a_upper: Optional[int] = None, c_lower: bool = False) -> torch.Tensor:
     """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt).
 
-    b_lower = o: B[j, k] = 0 for k > j + o (True means o = 0), the zero k-blocks are skipped.  batch > 1: A and B hold `batch`
-    operands stacked along the rows (rows % 128 == 0 each); the result is [batch, M, N]."""
+    b_lower = o: B[j, k] = 0 for k > j + o (True means o = 0), the zero k-blocks are skipped; a_upper = o: A[i, k] = 0 for
+    k < i + o (rows of an upper-triangular factor); c_lower: only the tiles touching the lower triangle of C are computed and
+    written.  batch > 1: A and B hold `batch` operands stacked along the rows (rows % 128 == 0 each); the result is [batch, M, N]."""
     assert A.k == B.k and A.slices == B.slices and A.rows % batch == 0 and B.rows % batch == 0
     M, N = A.rows // batch, B.rows // batch
     assert batch == 1 or (M % 128 == 0 and N % 128 == 0)
@@ -741,7 +776,8 @@ def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = 
     assert tuple(out.shape) == shape and out.stride(-1) == 1
     off = -1 if b_lower is None or b_lower is False else (0 if b_lower is True else int(b_lower))
     _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), M, _p(B.planes), _p(B.scale), N, A.k, A.slices,
-              off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0, _stream())
+              off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0,
+              -1 if a_upper is None else int(a_upper), int(c_lower), _stream())
     _count(1)
     return out
 

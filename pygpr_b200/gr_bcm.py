@@ -371,7 +371,10 @@ class GRBCM_MLE:
         per = npad * npad * 8 + 3 * npad * engine.TILE * 8
         free, _ = torch.cuda.mem_get_info(engine.device())
         held = self._part._L_buf.numel() * 8 if getattr(self, "_part", None) is not None and self._part._L_buf is not None else 0
-        return int(max(1, min(g.nc, (free + held - (6 << 30)) // per)))
+        reserve = 6 << 30
+        if options.emulate_grad_slices > 0:                  # staging of the emulated K^-1 products: two experts' worth
+            reserve += 2 * npad * npad * (16 + options.emulate_grad_slices)
+        return int(max(1, min(g.nc, (free + held - reserve) // per)))
 
     def loss(self, params):
         self.loss_value, _ = self._eval(params, False)

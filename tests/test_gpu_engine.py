@@ -286,6 +286,18 @@ def test_ozaki_gemm_accumulate_lower_and_batched(eng):
     ref = C0 + A @ Bm.T
     assert float((C - ref).abs().max() / ref.abs().max()) <= 1e-13
     assert torch.equal(eng.ozaki_gemm_nt(pa, pb, b_lower=off), eng.ozaki_gemm_nt(pa, pb))   # skipping zeros changes nothing
+    # rows of an upper-triangular factor times themselves, lower tiles of C only (K^-1 = U U^T of the emulated gradient)
+    n = 384
+    U = torch.triu(torch.randn(n, n, generator=g, dtype=torch.float64)).cuda()
+    pu = eng.ozaki_split(U, 7)
+    Cl = torch.full((n, n), float("nan"), dtype=torch.float64, device="cuda")
+    eng.ozaki_gemm_nt(pu, pu, out=Cl, a_upper=0, c_lower=True)
+    refu = U @ U.T
+    rows, cols = torch.arange(n, device="cuda")[:, None], torch.arange(n, device="cuda")[None, :]
+    computed = (cols // 64) * 64 <= (rows // 128) * 128 + 127            # the 128 x 64 tiles that touch the lower triangle
+    assert bool(torch.isnan(Cl[~computed]).all()) and not bool(torch.isnan(Cl[computed]).any())
+    assert float((Cl[computed] - refu[computed]).abs().max() / refu.abs().max()) <= 1e-13
+    assert torch.equal(Cl[computed], eng.ozaki_gemm_nt(pu, pu)[computed])   # skipping zero k-blocks changes nothing
     nb = 3
     Ab = torch.randn(nb, 128, 192, generator=g, dtype=torch.float64).cuda()
     Bb = torch.randn(nb, 256, 192, generator=g, dtype=torch.float64).cuda()
