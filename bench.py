@@ -221,6 +221,23 @@ def run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf):
     barrier(); e0.record(); f, grad = mle.loss_and_grad(theta.numpy()); e1.record(); barrier()
     lg_ms = max_over_ranks(e0.elapsed_time(e1))
     assert math.isfinite(f) and bool(torch.isfinite(torch.from_numpy(grad)).all()) and abs(f - f_loss) <= 1e-9 * abs(f)
+    from pygpr_b200 import config
+    del mle
+    torch.cuda.empty_cache()                                  # the FP64 evaluation's factor buffer goes back before the next one allocates
+    config.options.emulate_grad_slices = 7                    # the same evaluation with L^-T's off-segment blocks and K^-1 on the
+    config.options.emulate_inverse_slices = 7                 # INT8 tensor cores (opt-in); the Cholesky stays FP64
+    try:
+        mle_e = P.GRBCM_MLE(model)
+        mle_e.set_params(theta)
+        chunk_e = mle_e._auto_chunk()
+        barrier(); e0.record(); f_e, grad_e = mle_e.loss_and_grad(theta.numpy()); e1.record(); barrier()
+        lg_e_ms = max_over_ranks(e0.elapsed_time(e1))
+    finally:
+        config.options.emulate_grad_slices = 0
+        config.options.emulate_inverse_slices = 0
+    emulated = {"slices": 7, "loss_and_grad_ms": lg_e_ms, "speedup_vs_fp64_path": lg_ms / lg_e_ms, "chunk_experts": chunk_e,
+                "nlml_vs_fp64_path": abs(f_e - f) / abs(f), "grad_vs_fp64_path": float(np.abs(grad_e - grad).max() / np.abs(grad).max())}
+    del mle_e
     n_l, n_g = 2.0 * m0, float(m0)
     nc_total = per * world
     # executed flops: Cholesky (n^3 - ng^3)/3 + L^-T and K^-1/gradient 2 (n^3 - ng^3)/3 per local expert (shared leading block),
@@ -231,9 +248,10 @@ def run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf):
            "loss_and_grad_ms": lg_ms, "loss_ms": loss_ms, "tflops": flops / lg_ms * 1e-9, "frac_of_peak": flops / lg_ms * 1e-9 / (peak_tf * world),
            "unshared_count_tflops": flops_unshared / lg_ms * 1e-9, "nlml": f, "grad_norm": float((grad * grad).sum() ** 0.5),
            "collective": "all_reduce(sum, f64) of [1+P] = %d doubles per evaluation over %d rank(s)" % (1 + d + 2, world),
+           "emulated_fp64_grad": emulated,
            "what": "GRBCM_MLE.loss_and_grad at one shared hyper-parameter vector, wall time of the public call incl. host->device "
                    "staging of each expert chunk and the [1+P] read-back"}
-    del mle, model
+    del model
     torch.cuda.empty_cache()
     return out
 
@@ -404,6 +422,7 @@ def main():
     if args.emulate > 0 and shared and eng.can_emulate(model.gpg._state, st):
         from pygpr_b200 import config
         config.options.emulate_slices = args.emulate
+        config.options.emulate_inverse_slices = 7            # L^-T assembled from segment inverses by emulated products as well
         barrier(); e0.record(); eng.ensure_inverse_factors(model.gpg._state, st); e1.record(); barrier()
         prep_ms = max_over_ranks(e0.elapsed_time(e1))        # once per fit: L^-T of every expert (in place)
         for _ in range(2):
@@ -437,13 +456,19 @@ def main():
             # the NLML gradient with K^-1 = L^-T L^-1 on the INT8 tensor cores (7 digit planes; L^-T stays the FP64 blocked trtri)
             config.options.emulate_grad_slices = 7
             eng.lml_grad(st); barrier()
+            st.upper_is_inverse = False                         # like lml_grad of the FP64 path, the timed call recomputes L^-T
             barrier(); e0.record(); g_e = eng.lml_grad(st); e1.record(); barrier()
-            config.options.emulate_grad_slices = 0
             eg_ms = max_over_ranks(e0.elapsed_time(e1))
-            emu["lml_grad"] = {"slices": 7, "ms": eg_ms, "speedup_vs_fp64_path": grad_ms / eg_ms,
+            barrier(); e0.record(); eng.lml_grad(st); e1.record(); barrier()
+            eg2_ms = max_over_ranks(e0.elapsed_time(e1))       # L^-T already in place (e.g. after an emulated prediction of the same fit)
+            config.options.emulate_grad_slices = 0
+            config.options.emulate_inverse_slices = 0
+            emu["lml_grad"] = {"slices": 7, "ms": eg_ms, "speedup_vs_fp64_path": grad_ms / eg_ms, "ms_with_inverse_in_place": eg2_ms,
                                "grad_vs_fp64_path": float((g_e - g).abs().max() / g.abs().max()),
-                               "what": "engine.lml_grad with options.emulate_grad_slices: L^-T by the FP64 blocked trtri, K^-1 = U U^T as one "
-                                       "batched emulated-FP64 GEMM per chunk of experts, then the fused gradient reduction on K^-1"}
+                               "what": "engine.lml_grad with options.emulate_grad_slices / emulate_inverse_slices = 7: L^-T from FP64 inverses of "
+                                       "diagonal segments + emulated-FP64 products between them, K^-1 = U U^T as one batched emulated-FP64 "
+                                       "GEMM per chunk of experts, then the fused gradient reduction on K^-1"}
+        config.options.emulate_inverse_slices = 0
 
     # checksum of the aggregate, identical on every rank after the all-reduce: equal across N = 1/2/4/8 to ~1e-12 means the
     # sharded aggregation reproduces the single-GPU one (the driver-side multi-GPU parity check)

@@ -314,7 +314,9 @@ int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay,
  *                        (rpad = gpr_ozaki_rows_padded(rows), kpad = gpr_ozaki_k_padded(k); planes of
  *                        gpr_ozaki_planes_bytes bytes; padding rows/columns are zero).  bound > 0: the caller vouches that
  *                        |x| <= bound everywhere and every row is scaled by that bound (one pass instead of two);
- *                        bound <= 0: each row is scaled by its own maximum
+ *                        bound <= 0: each row is scaled by its own maximum.  batch > 1: `batch` matrices x_batch_stride
+ *                        doubles apart (e.g. the same window of every expert's factor), planes / scales stacked along the
+ *                        padded row dimension ([slices][batch * rpad][kpad], [batch * rpad]) as gpr_ozaki_gemm_nt's batch wants
  *   gpr_ozaki_gemm_nt    both operands split with the SAME slices and k;  b_lower = -1: dense B;  b_lower = o >= 0:
  *                        B[j, k] = 0 for k > j + o (a lower-triangular / lower-trapezoidal B, e.g. rows of L^-1) and the zero
  *                        k-blocks are skipped;  K * slices < 2^17 (int32 headroom).  batch > 1: `batch` independent products
@@ -323,26 +325,33 @@ int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay,
  *                        a_upper = o >= 0: A[i, k] = 0 for k < i + o (rows of an upper-triangular factor; the leading zero
  *                        k-blocks are skipped), -1: dense A.  c_lower != 0: only the 128 x 64 tiles that touch the lower
  *                        triangle of C are computed and written (K^-1 = U U^T for the NLML gradient, loss.py:77,116).
+ *                        C = beta*C + alpha * A B^T.
  */
 long long gpr_ozaki_rows_padded(int rows);
 long long gpr_ozaki_k_padded(int k);
 long long gpr_ozaki_planes_bytes(int rows, int k, int slices);
 int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, double bound, void* planes, double* scale,
-                    void* stream);
+                    int batch, long long x_batch_stride, void* stream);
 int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                       int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch, long long c_batch_stride,
-                      int a_upper, int c_lower, void* stream);
+                      int a_upper, int c_lower, double alpha, void* stream);
 
 /* pieces of the emulated-FP64 prediction (opt-in): V_l^T = K* X_l^T with X_l = rows of the explicit inverse L^-1, the product on
  * the INT8 tensor cores (gpr_ozaki_gemm_nt).  Stands in for tc.cholesky_solve(K*^T, L) + the row sums of gpr.py:100-104 and the
  * tc.bmm of gpr.py:80-83 for experts that extend the communication expert.
  *   gpr_trtri_batched      U = L^-T in place in the strict block-upper part of L [B, npad, npad]; block columns < gt must already
- *                          hold the shared L_g^-T (gpr_copy_leading_block mode 2); scratch: gpr_potri_scratch_bytes(B, npad)
+ *                          hold the shared L_g^-T (gpr_copy_leading_block mode 2); scratch: gpr_potri_scratch_bytes(B, npad).
+ *                          seg > 0: only the diagonal segments of seg block rows are inverted (the blocks between segments are
+ *                          products of segment inverses: U_AB = -U_AA L_BA^T U_BB, formed by gpr_ozaki_gemm_nt)
  *   gpr_tril_inverse_rows  X [B, npad - row0, npad] = rows row0.. of L^-1 (dense row-major, zeros right of the diagonal block)
  *   gpr_vt_reduce          mean[e, t] = mean_g[t] + sum_c V[e, t, c] z[e, c],  var[e, t] = var_g[t] - sum_c V[e, t, c]^2
  *                          (V [E, m, ldv] with nl used columns; z rows z_stride apart)
  */
-int gpr_trtri_batched(double* L, const double* invdiag, int B, int npad, void* scratch, void* stream, int gt);
+int gpr_trtri_batched(double* L, const double* invdiag, int B, int npad, void* scratch, void* stream, int gt, int seg);
+/* window [r0, r0+nr) x [c0, c0+nc) of U = L^-T (kind 0) or X = L^-1 (kind 1) as a dense block out [B, nr, nc] (multiples of 32),
+ * read out of the in-place L^-T and the diagonal-block inverses: operands of the products that assemble L^-T from diagonal segments */
+int gpr_factor_window(const double* L, const double* invdiag, int B, int npad, int kind, int r0, int nr, int c0, int nc, double* out,
+                      void* stream);
 int gpr_tril_inverse_rows(const double* L, const double* invdiag, int B, int npad, int row0, double* X, void* stream);
 int gpr_vt_reduce(const double* V, long long ldv, const double* z, long long z_stride, const double* mean_g, const double* var_g,
                   int E, int m, int nl, double* mean, double* var, void* stream);

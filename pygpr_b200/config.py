@@ -10,6 +10,7 @@ Every knob takes its initial value from the environment ONCE, at import; afterwa
     PYGPR_EMULATE_FP64=s       options.emulate_slices  GRBCM predictions through the emulated-FP64 GEMM with s digit planes (0 = off)
     PYGPR_EMULATE_CHUNK=e      options.emulate_chunk   experts per batched emulated product
     PYGPR_EMULATE_FP64_GRAD=s  options.emulate_grad_slices  K^-1 of the NLML gradient through the emulated-FP64 GEMM (0 = off)
+    PYGPR_EMULATE_FP64_INVERSE=s  options.emulate_inverse_slices  L^-T assembled from segment inverses by emulated-FP64 products (0 = off)
     PYGPR_POTRF_MODE=...       set_potrf_mode()     auto | columns | columns1 | dataflow
     PYGPR_TRSV_MODE=...        set_trsv_mode()      auto | single
 """
@@ -34,6 +35,9 @@ class Options:
     # opt-in: K^-1 = L^-T L^-1 of the NLML gradient on the INT8 tensor cores with this many digit planes (0 = off; 7 keeps the
     # gradient at ~1e-10 of the FP64 path).  engine.lml_grad_emulated
     emulate_grad_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_GRAD", "0"))
+    # opt-in: assemble L^-T (needed by the emulated prediction and gradient) from FP64 inverses of diagonal segments and
+    # emulated-FP64 products between them, with this many digit planes (0 = the plain FP64 blocked trtri).  engine._inverse_factors
+    emulate_inverse_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_INVERSE", "0"))
 
 
 options = Options()

@@ -1920,7 +1920,7 @@ __global__ void transpose_invdiag_kernel(const double* __restrict__ invdiag, dou
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const double* __restrict__ invdiagT, int B, int npad,
-             int* __restrict__ counter, int gt) {
+             int* __restrict__ counter, int gt, int seg) {
     extern __shared__ double smem[];
     __shared__ unsigned long long pipe_bars[2 * STAGES];
     Pipe pipe;
@@ -1940,8 +1940,11 @@ trtri_kernel(double* __restrict__ L, const double* __restrict__ invdiag, const d
         double* Lb = L + (long long)b * npad * npad;
         const double* Ujj = invdiagT + ((long long)b * nt + j) * TILE * TILE;
         double* Urow = Lb + ((long long)j * TILE) * npad;      // row tile j of U lives in the block-upper part
-        // gt > 0 (shared leading block): U[j, i] for i < gt is the communication expert's L_g^-T, already in place
-        for (int i = (j + 1 > gt ? j + 1 : gt); i < nt; ++i) {
+        // gt > 0 (shared leading block): U[j, i] for i < gt is the communication expert's L_g^-T, already in place.
+        // seg > 0: only the diagonal segments of `seg` block rows are inverted here (U[j, i] for i inside j's segment); the blocks
+        // between segments are products of the segment inverses and come from the emulated-FP64 GEMM (engine.inverse_factors).
+        const int iend = seg > 0 ? min(nt, (j / seg + 1) * seg) : nt;
+        for (int i = (j + 1 > gt ? j + 1 : gt); i < iend; ++i) {
             double acc[4][8][2];
             zero_acc(acc);
             __syncthreads();
@@ -2042,7 +2045,7 @@ static long long trtri_work_bytes(int B, int npad, int sms) {
     return 256 + align256((long long)B * nt * 4) + (task_mode ? 0 : (long long)B * trtri_slot_tiles(nt, sms) * TILE * TILE * 8);
 }
 static int launch_trtri(double* L, const double* invdiag, const double* invdiagT, int B, int npad, void* work, cudaStream_t st,
-                        int gt = 0) {
+                        int gt = 0, int seg = 0) {
     const int nt = npad / TILE;
     if (nt <= 1) return GPR_OK;
     int sms = gpr_device_sm_count();
@@ -2052,10 +2055,11 @@ static int launch_trtri(double* L, const double* invdiag, const double* invdiagT
     if (ntasks >= 2LL * sms) {
         CUDA_TRY(cudaMemsetAsync(task_counter, 0, 256, st));
         CUDA_TRY(opt_in_smem(trtri_kernel, MAIN_SMEM_BYTES));
-        trtri_kernel<<<sms, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, task_counter, gt);
+        trtri_kernel<<<sms, NTHREADS, MAIN_SMEM_BYTES, st>>>(L, invdiag, invdiagT, B, npad, task_counter, gt, seg);
         CUDA_TRY(cudaGetLastError());
         return GPR_OK;
     }
+    if (seg > 0) return fail(GPR_ERR_UNSUPPORTED, "segmented trtri needs the task schedule%s (B*(nt-1) = %lld tasks)", "", ntasks);
     int* counters = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + 256);
     double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(counters) + align256((long long)B * nt * 4));
     const int spe = (int)trtri_slot_tiles(nt, sms);
@@ -2381,15 +2385,61 @@ extern "C" int gpr_tril_inverse(double* L, const double* invdiag, int B, int npa
 //   gpr_vt_reduce          mean_i = mean_g + V_l^T z_l,  var_i = var_g - |V_l|^2 per test point   (gpr.py:80-85,100-104 for an
 //                          expert that extends the communication expert); fixed-order sums, no atomics
 // ---------------------------------------------------------------------------------------------
-extern "C" int gpr_trtri_batched(double* L, const double* invdiag, int B, int npad, void* scratch, void* stream, int gt) {
-    ARG_CHECK(L && invdiag && scratch && B > 0 && npad > 0 && npad % TILE == 0 && gt >= 0 && gt < npad / TILE);
+extern "C" int gpr_trtri_batched(double* L, const double* invdiag, int B, int npad, void* scratch, void* stream, int gt, int seg) {
+    ARG_CHECK(L && invdiag && scratch && B > 0 && npad > 0 && npad % TILE == 0 && gt >= 0 && gt < npad / TILE && seg >= 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int nt = npad / TILE;
     int sms = gpr_device_sm_count();
     if (sms <= 0) return fail(GPR_ERR_CUDA, "no CUDA device%s", "");
     double* invdiagT = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + trtri_work_bytes(B, npad, sms));
     transpose_invdiag_kernel<<<dim3(TILE / 32, TILE / 32, B * nt), dim3(32, 8), 0, st>>>(invdiag, invdiagT);
-    return launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st, gt);
+    return launch_trtri(L, invdiag, invdiagT, B, npad, scratch, st, gt, seg);
+}
+
+// A window [r0, r0+nr) x [c0, c0+nc) of a factor-derived matrix as a dense row-major block out[b][nr][nc] (all multiples of 32):
+//   kind 0: U = L^-T   (block column > block row: the strict block-upper part of L; diagonal blocks inv(L_ii)^T; zeros below)
+//   kind 1: X = L^-1   (X[r][c] = U[c][r])
+// — the operands of the products that assemble L^-T from its diagonal segments (engine.inverse_factors) and of K^-1 = U U^T.
+__global__ void factor_window_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad, int kind, int r0,
+                                     int nr, int c0, int nc, double* __restrict__ out) {
+    __shared__ double t[32][33];
+    const int b = blockIdx.z;
+    const int wr = blockIdx.y * 32, wc = blockIdx.x * 32;          // inside the window
+    const int gr = r0 + wr, gc = c0 + wc;                          // in the matrix
+    const int br = gr / TILE, bc = gc / TILE, nt = npad / TILE;
+    const double* Lb = L + (long long)b * npad * npad;
+    double* ob = out + (long long)b * nr * nc + (long long)wr * nc + wc;
+    const bool zero = kind == 0 ? bc < br : bc > br;
+    const bool diag = bc == br;
+    if (zero) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) ob[(long long)r * nc + threadIdx.x] = 0.0;
+    } else if (diag && kind == 1) {                                // X_ii = inv(L_ii)
+        const double* inv = invdiag + ((long long)b * nt + br) * TILE * TILE;
+        for (int r = threadIdx.y; r < 32; r += blockDim.y)
+            ob[(long long)r * nc + threadIdx.x] = inv[(gr - br * TILE + r) * TILE + (gc - bc * TILE + threadIdx.x)];
+    } else if (diag) {                                             // U_ii = inv(L_ii)^T
+        const double* inv = invdiag + ((long long)b * nt + br) * TILE * TILE;
+        const int rr = gr - br * TILE, cc = gc - bc * TILE;
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = inv[(cc + r) * TILE + rr + threadIdx.x];
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) ob[(long long)r * nc + threadIdx.x] = t[threadIdx.x][r];
+    } else if (kind == 0) {                                        // U above the diagonal: stored as is
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) ob[(long long)r * nc + threadIdx.x] = Lb[(long long)(gr + r) * npad + gc + threadIdx.x];
+    } else {                                                       // X below the diagonal: U transposed
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = Lb[(long long)(gc + r) * npad + gr + threadIdx.x];
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) ob[(long long)r * nc + threadIdx.x] = t[threadIdx.x][r];
+    }
+}
+
+extern "C" int gpr_factor_window(const double* L, const double* invdiag, int B, int npad, int kind, int r0, int nr, int c0, int nc,
+                                 double* out, void* stream) {
+    ARG_CHECK(L && invdiag && out && B > 0 && npad > 0 && npad % TILE == 0 && (kind == 0 || kind == 1));
+    ARG_CHECK(r0 >= 0 && c0 >= 0 && nr > 0 && nc > 0 && r0 % 32 == 0 && c0 % 32 == 0 && nr % 32 == 0 && nc % 32 == 0 &&
+              r0 + nr <= npad && c0 + nc <= npad);
+    factor_window_kernel<<<dim3(nc / 32, nr / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(L, invdiag, npad, kind, r0, nr, c0, nc, out);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
 }
 
 __global__ void tril_rows_from_upper_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad, int row0,

@@ -157,10 +157,14 @@ __device__ __forceinline__ void issue_k_block(uint32_t tmem, uint32_t a_lo, uint
 // digit planes:  X [rows, k] (FP64, leading dimension ld)  ->  planes [slices][rpad][kpad] int8, scale [rpad]
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_kernel(const double* __restrict__ X, long long ld, int rows, int k, int rpad, int kpad,
-                                                    int slices, double bound, int8_t* __restrict__ planes, double* __restrict__ scale) {
+                                                    int slices, double bound, int8_t* __restrict__ planes, double* __restrict__ scale,
+                                                    long long x_batch_stride) {
+    // batch entry blockIdx.y: its matrix starts x_batch_stride doubles further, its planes / scales rpad rows further
     const int r = blockIdx.x;
-    const long long plane_stride = (long long)rpad * kpad;
-    int8_t* out = planes + (long long)r * kpad;
+    X += (long long)blockIdx.y * x_batch_stride;
+    scale += (long long)blockIdx.y * rpad;
+    const long long plane_stride = (long long)gridDim.y * rpad * kpad;
+    int8_t* out = planes + ((long long)blockIdx.y * rpad + r) * kpad;
     __shared__ double red[8];
     __shared__ int e_sh;
     // row scale from the row maximum, or — when the caller knows a bound on |x| (bound > 0, e.g. sig^2 for an SE kernel matrix) —
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ C, long long ldc,
             int M, int N, int kpad, int stages, int b_lower, double beta, int group_m, int tmem_cols,
-            int a_batch_rows, int b_batch_rows, long long c_batch_stride, int a_upper, int c_lower) {
+            int a_batch_rows, int b_batch_rows, long long c_batch_stride, int a_upper, int c_lower, double alpha) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled tiles want (at least) 512 B alignment
@@ -312,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // ---- epilogue warps 2..5: warp w may touch TMEM lanes [32 (w % 4), +32) ------------------------------------------------
         const int q = warp & 3;
         const int row = tm * BM + q * 32 + lane;
-        const double sa = scaleA[row];                      // scale arrays are padded to whole tiles
+        const double sa = alpha * scaleA[row];              // scale arrays are padded to whole tiles
         mbar_wait(bar_tmem, 0);
         tc_fence_after();
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -395,11 +399,12 @@ extern "C" long long gpr_ozaki_planes_bytes(int rows, int k, int slices) {
 }
 
 extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, double bound, void* planes, double* scale,
-                               void* stream) {
-    if (!(X && planes && scale && rows > 0 && k > 0 && ld >= k && slices >= 1 && slices <= oz::MAX_SLICES))
+                               int batch, long long x_batch_stride, void* stream) {
+    if (!(X && planes && scale && rows > 0 && k > 0 && ld >= k && slices >= 1 && slices <= oz::MAX_SLICES && batch >= 1 && batch <= 65535))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_split%s (slices=%lld)", "", slices);
     const int rpad = oz::round_up(rows, oz::BM), kpad = oz::round_up(k, oz::BK);
-    oz::split_kernel<<<rpad, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, k, rpad, kpad, slices, bound, static_cast<int8_t*>(planes), scale);
+    oz::split_kernel<<<dim3(rpad, batch), 256, 0, (cudaStream_t)stream>>>(X, ld, rows, k, rpad, kpad, slices, bound,
+                                                                          static_cast<int8_t*>(planes), scale, x_batch_stride);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return gpr_internal_fail(GPR_ERR_CUDA, "%s (cuda error %lld)", cudaGetErrorString(e), (long long)e);
     return GPR_OK;
@@ -407,7 +412,7 @@ extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, i
 
 extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                                  int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch,
-                                 long long c_batch_stride, int a_upper, int c_lower, void* stream) {
+                                 long long c_batch_stride, int a_upper, int c_lower, double alpha, void* stream) {
     if (!(planesA && planesB && scaleA && scaleB && C && M > 0 && N > 0 && K > 0 && ldc >= N && slices >= 1 && slices <= oz::MAX_SLICES &&
           batch >= 1 && batch <= 65535 && b_lower >= -1 && a_upper >= -1))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_gemm_nt%s (slices=%lld)", "", slices);
@@ -437,7 +442,7 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
         if (e == cudaSuccess)                                                                                                  \
             oz::gemm_kernel<S><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                   \
                 mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA, rpadB,       \
-                c_batch_stride, a_upper, c_lower);                                                                             \
+                c_batch_stride, a_upper, c_lower, alpha);                                                                      \
         break;
     switch (slices) {
         OZ_LAUNCH(1) OZ_LAUNCH(2) OZ_LAUNCH(3) OZ_LAUNCH(4) OZ_LAUNCH(5) OZ_LAUNCH(6) OZ_LAUNCH(7) OZ_LAUNCH(8)

@@ -739,26 +739,32 @@ class DigitPlanes:
     scale: torch.Tensor
 
 
-def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0, out: Optional[DigitPlanes] = None) -> DigitPlanes:
+def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0, out: Optional[DigitPlanes] = None, batch: int = 1,
+                batch_stride: int = 0, rows: Optional[int] = None, k: Optional[int] = None) -> DigitPlanes:
     """Digit planes of a row-major FP64 matrix (last dimension contiguous).  bound > 0: |X| <= bound is known, every row is
-    scaled by it (one pass over X); otherwise each row by its own maximum.  out: planes / scale buffers to write into."""
+    scaled by it (one pass over X); otherwise each row by its own maximum.  out: planes / scale buffers to write into.
+    batch > 1: `batch` windows of `rows` x `k` elements starting at X's first element, batch_stride doubles apart, row stride
+    X.stride(0) (e.g. the same block of every expert's factor); the planes are stacked along the rows (rows % 128 == 0)."""
     assert X.dim() == 2 and X.stride(1) == 1 and X.dtype == F64
-    rows, k = X.shape
+    rows = X.shape[0] if rows is None else rows
+    k = X.shape[1] if k is None else k
+    assert batch == 1 or rows % 128 == 0
     lib = _lib.load()
     rpad, kpad = int(lib.gpr_ozaki_rows_padded(rows)), int(lib.gpr_ozaki_k_padded(k))
     if out is None:
-        planes = torch.empty(slices, rpad, kpad, dtype=torch.int8, device=X.device)
-        scale = torch.empty(rpad, dtype=F64, device=X.device)
+        planes = torch.empty(slices, batch * rpad, kpad, dtype=torch.int8, device=X.device)
+        scale = torch.empty(batch * rpad, dtype=F64, device=X.device)
     else:
-        planes = out.planes.view(-1)[: slices * rpad * kpad].view(slices, rpad, kpad)
-        scale = out.scale[:rpad]
-    _lib.call("gpr_ozaki_split", _p(X), X.stride(0), rows, k, slices, float(bound), _p(planes), _p(scale), _stream())
+        planes = out.planes.view(-1)[: slices * batch * rpad * kpad].view(slices, batch * rpad, kpad)
+        scale = out.scale[: batch * rpad]
+    _lib.call("gpr_ozaki_split", _p(X), X.stride(0), rows, k, slices, float(bound), _p(planes), _p(scale), batch, batch_stride, _stream())
     _count(1)
-    return DigitPlanes(rows, k, slices, planes, scale)
+    return DigitPlanes(batch * rows, k, slices, planes, scale)
 
 
 def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = None, beta: float = 0.0,
-                  b_lower: Optional[int] = None, batch: int = 1, a_upper: Optional[int] = None, c_lower: bool = False) -> torch.Tensor:
+                  b_lower: Optional[int] = None, batch: int = 1, a_upper: Optional[int] = None, c_lower: bool = False,
+                  alpha: float = 1.0) -> torch.Tensor:
     """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt).
 
     b_lower = o: B[j, k] = 0 for k > j + o (True means o = 0), the zero k-blocks are skipped; a_upper = o: A[i, k] = 0 for
@@ -773,13 +779,82 @@ def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = 
         beta = 0.0
     if batch == 1 and out.dim() == 3 and out.shape[0] == 1:
         out = out[0]
-    assert tuple(out.shape) == shape and out.stride(-1) == 1
+    assert tuple(out.shape) == shape and out.stride(-1) == 1 and (batch == 1 or out.stride(0) % 2 == 0)
     off = -1 if b_lower is None or b_lower is False else (0 if b_lower is True else int(b_lower))
     _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), M, _p(B.planes), _p(B.scale), N, A.k, A.slices,
               off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0,
-              -1 if a_upper is None else int(a_upper), int(c_lower), _stream())
+              -1 if a_upper is None else int(a_upper), int(c_lower), float(alpha), _stream())
     _count(1)
     return out
+
+
+def _inverse_plan(nt: int, gt: int, B: int, sms: int):
+    """Segment size (in 128-row blocks) for the assembled inverse, or 0 for the plain FP64 trtri: the part [gt, nt) is cut into
+    4 or 2 equal diagonal segments of at least 4 blocks (the FP64 chain then works inside segments only and the rest — 3/4 to
+    15/16 of the flops — are GEMMs), provided the persistent task schedule of trtri_kernel applies."""
+    from .config import options
+    if options.emulate_inverse_slices <= 0 or B * (nt - 1) < 2 * sms:
+        return 0
+    span = nt - gt
+    for parts in (4, 2):
+        if span % parts == 0 and span // parts >= 4 and (gt == 0 or gt % (span // parts) == 0):
+            return span // parts
+    return 0
+
+
+def _inverse_factors(st: FitState, gt: int) -> None:
+    """U = L^-T of every expert, in place in the strict block-upper part of st.L (block columns < gt already hold the shared L_g^-T).
+
+    Plain form: the FP64 blocked trtri (gpr_trtri_batched), a triangular-solve chain at the DMMA rate.  Assembled form (opt-in,
+    config.options.emulate_inverse_slices): trtri only inside diagonal segments; every block between two adjacent groups of
+    segments A (above) and B (below) is   U_AB = -U_AA L_BA^T U_BB   — two products on the INT8 tensor cores per merge
+    (gpr_ozaki_gemm_nt; T^T = U_AA L_BA^T, then U_AB = -T^T X_BB^T with X_BB = U_BB^T), merged pairwise up to the whole matrix."""
+    from .config import options
+    lib = _lib.load()
+    dev, B, npad = st.L.device, st.B, st.npad
+    nt = npad // TILE
+    if dev.index not in _sm_count:
+        _sm_count[dev.index] = torch.cuda.get_device_properties(dev.index).multi_processor_count
+    seg = _inverse_plan(nt, gt, B, _sm_count[dev.index])
+    scratch = torch.empty(int(lib.gpr_potri_scratch_bytes(B, npad)), dtype=torch.uint8, device=dev)
+    _lib.call("gpr_trtri_batched", _p(st.L), _p(st.invdiag), B, npad, _p(scratch), _stream(), gt, seg)
+    _count(2)
+    if seg == 0:
+        return
+    slices = options.emulate_inverse_slices
+    # merges, finest first: pairs of segments inside [gt, nt), then pairs of pairs, ..., finally the shared block against the rest
+    merges, width = [], seg
+    while width < nt - gt:
+        for a0 in range(gt, nt, 2 * width):
+            merges.append((a0, a0 + width, a0 + 2 * width))
+        width *= 2
+    if gt > 0:
+        merges.append((0, gt, nt))
+    hmax = max(max(a1 - a0, a2 - a1) for a0, a1, a2 in merges) * TILE
+    per = hmax * hmax * (24 + 4 * slices) + (1 << 20)          # three FP64 windows + four plane sets per expert of a chunk
+    free, _ = torch.cuda.mem_get_info(dev)
+    held = sum(b.numel() for k, b in _scratch_cache.items() if k[0] == dev.index and str(k[1]).startswith("inv_"))
+    E = int(max(1, min(options.emulate_chunk, B, (free + held - (2 << 30)) // per)))
+    for e0 in range(0, B, E):
+        ne = min(e0 + E, B) - e0
+        Lc, Ic = st.L[e0:e0 + ne], st.invdiag[e0:e0 + ne]
+        for a0, a1, a2 in merges:
+            hA, hB = (a1 - a0) * TILE, (a2 - a1) * TILE
+            UA = _f64_work("inv_ua", ne * hA * hA, dev).view(ne * hA, hA)
+            XB = _f64_work("inv_xb", ne * hB * hB, dev).view(ne * hB, hB)
+            Tt = _f64_work("inv_tt", ne * hA * hB, dev).view(ne, hA, hB)
+            _lib.call("gpr_factor_window", _p(Lc), _p(Ic), ne, npad, 0, a0 * TILE, hA, a0 * TILE, hA, _p(UA), _stream())   # U_AA
+            _lib.call("gpr_factor_window", _p(Lc), _p(Ic), ne, npad, 1, a1 * TILE, hB, a1 * TILE, hB, _p(XB), _stream())   # X_BB
+            pUA = ozaki_split(UA, slices)
+            pXB = ozaki_split(XB, slices)
+            # L_BA straight out of the factor: the same [hB x hA] window of every expert, npad^2 doubles apart
+            LBA = Lc[0, a1 * TILE:, a0 * TILE:]
+            pLBA = ozaki_split(LBA, slices, batch=ne, batch_stride=npad * npad, rows=hB, k=hA)
+            ozaki_gemm_nt(pUA, pLBA, out=Tt, batch=ne, a_upper=0)                      # T^T = U_AA L_BA^T   [hA, hB]
+            pTt = ozaki_split(Tt.view(ne * hA, hB), slices)
+            UAB = Lc[:, a0 * TILE:a1 * TILE, a1 * TILE:a2 * TILE]                       # written in place, row stride npad
+            ozaki_gemm_nt(pTt, pXB, out=UAB, batch=ne, b_lower=0, alpha=-1.0)          # U_AB = -T^T X_BB^T
+            _count(2)
 
 
 def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
@@ -799,9 +874,7 @@ def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
             st_l.shared_upper = True
         gt = st_g.n // TILE
     if st_l.npad > TILE:
-        scratch = torch.empty(int(_lib.load().gpr_potri_scratch_bytes(st_l.B, st_l.npad)), dtype=torch.uint8, device=st_l.L.device)
-        _lib.call("gpr_trtri_batched", _p(st_l.L), _p(st_l.invdiag), st_l.B, st_l.npad, _p(scratch), _stream(), gt)
-        _count(2)
+        _inverse_factors(st_l, gt)
     st_l.upper_is_inverse = True
     # keep the digit planes of the inverse rows across predictions when HBM allows (8 planes at most, + the transient chunk buffers)
     free, _ = torch.cuda.mem_get_info(st_l.L.device)

@@ -307,3 +307,43 @@ def test_ozaki_gemm_accumulate_lower_and_batched(eng):
     assert float((Cb - refb).abs().max() / refb.abs().max()) <= 1e-13
     for i in range(nb):   # a batch entry equals the same product launched alone, bit for bit
         assert torch.equal(Cb[i], eng.ozaki_gemm_nt(eng.ozaki_split(Ab[i], 7), eng.ozaki_split(Bb[i], 7)))
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_inverse_factors_assembled_from_segments(eng, orc, monkeypatch, shared):
+    """L^-T assembled from FP64 inverses of diagonal segments and emulated-FP64 products between them (engine._inverse_factors,
+    opt-in) equals the plain FP64 blocked trtri and the oracle's inverse; with and without a shared communication block."""
+    from pygpr_b200 import config
+    B, n, d = 20, 2048, 4                       # 20 x 15 row tasks: the persistent task schedule of trtri_kernel applies
+    x, y, xs, hp = _data(31, B, n, d, 128)
+    if shared:
+        x[:, :1024] = x[0, :1024]               # every expert starts with the same 1024 points (the communication set)
+        y[:, :1024] = y[0, :1024]
+
+    def inverse(slices):
+        monkeypatch.setattr(config.options, "emulate_inverse_slices", slices)
+        st_g = None
+        if shared:
+            st_g = eng.fit(x[:1, :1024].contiguous().cuda(), y[:1, :1024].contiguous().cuda(), hp[:1].cuda(), True)
+        st = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True, shared=st_g)
+        eng.ensure_inverse_factors(st_g, st)
+        U = torch.empty(B, n, n, dtype=torch.float64, device="cuda")
+        from pygpr_b200 import _lib
+        _lib.call("gpr_factor_window", eng._p(st.L), eng._p(st.invdiag), B, st.npad, 0, 0, n, 0, n, eng._p(U), eng._stream())
+        return st, U
+
+    st0, U0 = inverse(0)
+    st1, U1 = inverse(7)
+    assert eng._inverse_plan(st1.npad // 128, 8 if shared else 0, B, 148) > 0
+    torch.cuda.synchronize()
+    assert float((U1 - U0).abs().max() / U0.abs().max()) <= 1e-11
+    L_ref, _ = orc.gp_fit(SPEC, hp[:2], x[:2], y[:2])
+    Uref = torch.linalg.inv(L_ref).transpose(1, 2)
+    assert_close(U1[:2].cpu().numpy(), Uref.numpy(), 1e-9, "L^-T (assembled) vs the oracle's factor inverted")
+    # and the emulated prediction on top of it
+    monkeypatch.setattr(config.options, "emulate_inverse_slices", 0)
+    mean, var = eng.predict_emulated(st1, xs.cuda(), 7, 4) if not shared else (None, None)
+    if not shared:
+        mean_o, var_o = orc.gp_predict(SPEC, hp[:2], x[:2], y[:2], xs, "diag")
+        assert_close(mean[:2].cpu().numpy(), mean_o.numpy(), TOL, "mean")
+        assert_close(var[:2].cpu().numpy(), var_o.numpy(), TOL, "var")
