@@ -225,7 +225,8 @@ def run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf):
     del mle
     torch.cuda.empty_cache()                                  # the FP64 evaluation's factor buffer goes back before the next one allocates
     config.options.emulate_grad_slices = 7                    # the same evaluation with L^-T's off-segment blocks and K^-1 on the
-    config.options.emulate_inverse_slices = 7                 # INT8 tensor cores (opt-in); the Cholesky stays FP64
+    config.options.emulate_inverse_slices = 7                 # INT8 tensor cores (opt-in), and so are the Cholesky's panel solves and
+    config.options.emulate_fit_slices = 7                     # trailing updates (engine.fit_emulated)
     try:
         mle_e = P.GRBCM_MLE(model)
         mle_e.set_params(theta)
@@ -235,6 +236,7 @@ def run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf):
     finally:
         config.options.emulate_grad_slices = 0
         config.options.emulate_inverse_slices = 0
+        config.options.emulate_fit_slices = 0
     emulated = {"slices": 7, "loss_and_grad_ms": lg_e_ms, "speedup_vs_fp64_path": lg_ms / lg_e_ms, "chunk_experts": chunk_e,
                 "nlml_vs_fp64_path": abs(f_e - f) / abs(f), "grad_vs_fp64_path": float(np.abs(grad_e - grad).max() / np.abs(grad).max())}
     del mle_e
@@ -469,6 +471,21 @@ def main():
                                        "diagonal segments + emulated-FP64 products between them, K^-1 = U U^T as one batched emulated-FP64 "
                                        "GEMM per chunk of experts, then the fused gradient reduction on K^-1"}
         config.options.emulate_inverse_slices = 0
+        # the factorisation itself: right-looking blocked Cholesky with emulated-FP64 panel solves / trailing updates (7 planes)
+        config.options.emulate_fit_slices = 7
+        for _ in range(2):
+            model.gpl.need_upd = True; model.gpg.need_upd = True
+            barrier(); e0.record(); model.update(); e1.record(); barrier()
+        config.options.emulate_fit_slices = 0
+        ef_ms = max_over_ranks(e0.elapsed_time(e1))
+        st_e = model.gpl._state
+        emu["fit"] = {"slices": 7, "ms": ef_ms, "speedup_vs_fp64_path": fit_ms / ef_ms, "tflops_equiv": fit_flops / ef_ms * 1e-9,
+                      "nlml_vs_fp64_path": float((st_e.nlml() - st.nlml()).abs().max() / st.nlml().abs().max()),
+                      "alpha_vs_fp64_path": float((st_e.alpha - st.alpha).abs().max() / st.alpha.abs().max()),
+                      "what": "GRBCM.update with options.emulate_fit_slices: K built in place, diagonal blocks of 1024 rows by the FP64 "
+                              "Cholesky, panel solves and trailing updates as batched emulated-FP64 GEMMs (the shared communication block is "
+                              "one panel against the cached L_g^-1), forward solve fused panel by panel"}
+        del st_e
 
     # checksum of the aggregate, identical on every rank after the all-reduce: equal across N = 1/2/4/8 to ~1e-12 means the
     # sharded aggregation reproduces the single-GPU one (the driver-side multi-GPU parity check)

@@ -325,7 +325,8 @@ int gpr_sq_dist(const double* ax, const double* nx, int npadx, const double* ay,
  *                        a_upper = o >= 0: A[i, k] = 0 for k < i + o (rows of an upper-triangular factor; the leading zero
  *                        k-blocks are skipped), -1: dense A.  c_lower != 0: only the 128 x 64 tiles that touch the lower
  *                        triangle of C are computed and written (K^-1 = U U^T for the NLML gradient, loss.py:77,116).
- *                        C = beta*C + alpha * A B^T.
+ *                        C = beta*C + alpha * A B^T.  b_shared != 0 (with batch > 1): ONE B operand (planesB holds N rows) is
+ *                        used by every batch entry (e.g. the communication expert's L_g^-1 against every local expert's block).
  */
 long long gpr_ozaki_rows_padded(int rows);
 long long gpr_ozaki_k_padded(int k);
@@ -334,7 +335,7 @@ int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, 
                     int batch, long long x_batch_stride, void* stream);
 int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                       int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch, long long c_batch_stride,
-                      int a_upper, int c_lower, double alpha, void* stream);
+                      int a_upper, int c_lower, double alpha, int b_shared, void* stream);
 
 /* pieces of the emulated-FP64 prediction (opt-in): V_l^T = K* X_l^T with X_l = rows of the explicit inverse L^-1, the product on
  * the INT8 tensor cores (gpr_ozaki_gemm_nt).  Stands in for tc.cholesky_solve(K*^T, L) + the row sums of gpr.py:100-104 and the
@@ -367,6 +368,12 @@ int gpr_vt_reduce(const double* V, long long ldv, const double* z, long long z_s
 int gpr_triu_rows(const double* L, const double* invdiag, int B, int npad, double* Ud, void* stream);
 int gpr_grad_from_kinv(const double* Kinv, int ldk, const double* a, const double* nrm, const double* alpha, const double* hp,
                        int hp_stride, int has_noise, int B, int n, int npad, int d, int dpad, double* grad, void* scratch, void* stream);
+
+/* y[b, i] -= sum_k A[b, i, k] z[b, k]   for i < rows, k < kdim: A = a window of every expert's factor (row stride lda, experts
+ * a_batch_stride apart), y / z rows y_stride / z_stride apart.  The forward solve's update of the remaining right-hand side
+ * behind a finished block column (z = L^-1 y, gpr.py:70-72) in the panel-wise factorisation of engine.fit_emulated.  HBM bound. */
+int gpr_gemv_sub(const double* A, long long lda, long long a_batch_stride, int B, int rows, int kdim, const double* z,
+                 long long z_stride, double* y, long long y_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ Every knob takes its initial value from the environment ONCE, at import; afterwa
     PYGPR_EMULATE_CHUNK=e      options.emulate_chunk   experts per batched emulated product
     PYGPR_EMULATE_FP64_GRAD=s  options.emulate_grad_slices  K^-1 of the NLML gradient through the emulated-FP64 GEMM (0 = off)
     PYGPR_EMULATE_FP64_INVERSE=s  options.emulate_inverse_slices  L^-T assembled from segment inverses by emulated-FP64 products (0 = off)
+    PYGPR_EMULATE_FP64_FIT=s   options.emulate_fit_slices   blocked Cholesky with emulated-FP64 panel solves / trailing updates (0 = off)
     PYGPR_POTRF_MODE=...       set_potrf_mode()     auto | columns | columns1 | dataflow
     PYGPR_TRSV_MODE=...        set_trsv_mode()      auto | single
 """
@@ -38,6 +39,11 @@ class Options:
     # opt-in: assemble L^-T (needed by the emulated prediction and gradient) from FP64 inverses of diagonal segments and
     # emulated-FP64 products between them, with this many digit planes (0 = the plain FP64 blocked trtri).  engine._inverse_factors
     emulate_inverse_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_INVERSE", "0"))
+    # opt-in: the factorisation itself as a right-looking blocked Cholesky whose panel solves and trailing updates are emulated-FP64
+    # products (diagonal blocks of `emulate_fit_panel` rows stay FP64), this many digit planes (0 = the FP64 DMMA Cholesky)
+    emulate_fit_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_FIT", "0"))
+    emulate_fit_panel: int = int(os.environ.get("PYGPR_EMULATE_FIT_PANEL", "1024"))
+    emulate_fit_chunk: int = int(os.environ.get("PYGPR_EMULATE_FIT_CHUNK", "32"))
 
 
 options = Options()

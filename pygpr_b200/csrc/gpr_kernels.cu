@@ -2258,6 +2258,35 @@ static int lml_grad_impl(double* L, const double* invdiag, const double* a, cons
     return GPR_OK;
 }
 
+// y[b, i] -= A[b, i, :] . z[b, :]  — one warp per row, 8 rows per block; the right-hand-side update of the panel-wise forward solve
+__global__ void __launch_bounds__(256) gemv_sub_kernel(const double* __restrict__ A, long long lda, long long a_batch_stride, int rows,
+                                                       int kdim, const double* __restrict__ z, long long z_stride,
+                                                       double* __restrict__ y, long long y_stride) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= rows) return;
+    const double* a = A + (long long)b * a_batch_stride + (long long)i * lda;
+    const double* zb = z + (long long)b * z_stride;
+    double s = 0.0;
+    for (int k = lane * 2; k < kdim; k += 64) {
+        const double2 av = *reinterpret_cast<const double2*>(a + k);
+        const double2 zv = *reinterpret_cast<const double2*>(zb + k);
+        s = fma(av.x, zv.x, s);
+        s = fma(av.y, zv.y, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) y[(long long)b * y_stride + i] -= s;
+}
+
+extern "C" int gpr_gemv_sub(const double* A, long long lda, long long a_batch_stride, int B, int rows, int kdim, const double* z,
+                            long long z_stride, double* y, long long y_stride, void* stream) {
+    ARG_CHECK(A && z && y && B > 0 && rows > 0 && kdim > 0 && kdim % 2 == 0 && lda >= kdim && lda % 2 == 0 && a_batch_stride % 2 == 0 &&
+              z_stride % 2 == 0);
+    gemv_sub_kernel<<<dim3((rows + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(A, lda, a_batch_stride, rows, kdim, z, z_stride, y, y_stride);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
+}
+
 // ---- emulated-FP64 gradient pieces (engine.lml_grad_emulated): K^-1 = U U^T comes from gpr_ozaki_gemm_nt ---------------------------
 __global__ void triu_rows_kernel(const double* __restrict__ L, const double* __restrict__ invdiag, int npad, double* __restrict__ Ud) {
     // Ud[r][c] = U[r][c]: block column > block row from the strict block-upper part of L, diagonal blocks = inv(L_ii)^T, zeros below

@@ -412,7 +412,7 @@ extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, i
 
 extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                                  int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch,
-                                 long long c_batch_stride, int a_upper, int c_lower, double alpha, void* stream) {
+                                 long long c_batch_stride, int a_upper, int c_lower, double alpha, int b_shared, void* stream) {
     if (!(planesA && planesB && scaleA && scaleB && C && M > 0 && N > 0 && K > 0 && ldc >= N && slices >= 1 && slices <= oz::MAX_SLICES &&
           batch >= 1 && batch <= 65535 && b_lower >= -1 && a_upper >= -1))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_gemm_nt%s (slices=%lld)", "", slices);
@@ -424,7 +424,7 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
     CUtensorMap mapA, mapB;
     int rc = oz::make_map(&mapA, planesA, rpadA * batch, kpad, slices, oz::BM);
     if (rc != GPR_OK) return rc;
-    rc = oz::make_map(&mapB, planesB, rpadB * batch, kpad, slices, oz::BN);
+    rc = oz::make_map(&mapB, planesB, b_shared ? rpadB : rpadB * batch, kpad, slices, oz::BN);
     if (rc != GPR_OK) return rc;
     const int sbytes = oz::stage_bytes(slices);
     int stages = (oz::SMEM_LIMIT - 2048) / sbytes;
@@ -441,7 +441,8 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
         e = cudaFuncSetAttribute(oz::gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
         if (e == cudaSuccess)                                                                                                  \
             oz::gemm_kernel<S><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                   \
-                mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA, rpadB,       \
+                mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA,              \
+                b_shared ? 0 : rpadB,                                                                                          \
                 c_batch_stride, a_upper, c_lower, alpha);                                                                      \
         break;
     switch (slices) {

@@ -199,6 +199,10 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     """
     B, n, d = x.shape
     assert hp.shape == (B, d + 1 + int(has_noise)), (hp.shape, B, d, has_noise)
+    from .config import options
+    if options.emulate_fit_slices > 0 and can_fit_emulated(n, shared):
+        return fit_emulated(x, y, hp, has_noise, options.emulate_fit_slices, want_alpha, jitter, L_out, shared,
+                            options.emulate_fit_panel, options.emulate_fit_chunk)
     npad = round_up(n, TILE)
     nt = npad // TILE
     dev = x.device
@@ -249,6 +253,104 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     st = FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior, shared)
     st.shared_upper = shared is not None and shared_upper
     return st
+
+
+def can_fit_emulated(n: int, shared: Optional[FitState]) -> bool:
+    return n % TILE == 0 and n >= 4 * TILE and (shared is None or (shared.n % TILE == 0 and shared.B == 1 and shared.n < n))
+
+
+def fit_emulated(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, slices: int = 7, want_alpha: bool = True,
+                 jitter: float = JITTER, L_out: Optional[torch.Tensor] = None, shared: Optional[FitState] = None,
+                 panel: int = 1024, chunk: int = 32) -> FitState:
+    """engine.fit (Exact_GP.update, gpr.py:65-74) with the O(n^3) work on the INT8 tensor cores (opt-in): a
+    right-looking blocked Cholesky whose panel solves and trailing updates are emulated-FP64 GEMMs.
+
+    K is built in place (gpr_se_build, lower tiles).  Per panel of `panel` rows, for a chunk of experts at a time:
+      D    = the panel's diagonal block, factorised in FP64 by the library's own batched Cholesky (gpr_potrf_batched on a contiguous
+             copy; its fused forward solve gives z for these rows, its log-determinant / z.z parts are accumulated),
+      P    = K[below, panel] inv(L_DD)^T            one emulated GEMM against X = L_DD^-1 (gpr_tril_inverse), written in place,
+      K[below, below] -= P P^T                      one emulated GEMM (alpha = -1, beta = 1, lower tiles only),
+      y[below] -= P z_panel                         gpr_gemv_sub (the forward solve's right-hand side).
+    With a shared communication block (shared = its fitted state, tile aligned) the first "panel" is the whole shared block:
+    its factor is copied, P = K_lg L_g^-T against the communication expert's cached L_g^-1 (one B operand for all experts).
+    ~98 % of the flops run as GEMMs; the factor, z, log-determinant and info are those of engine.fit to ~1e-11."""
+    B, n, d = x.shape
+    assert hp.shape == (B, d + 1 + int(has_noise)) and can_fit_emulated(n, shared)
+    lib = _lib.load()
+    npad, dev = n, x.device
+    nt = npad // TILE
+    a, nrm = scale_inputs(x, hp, B, npad)
+    dpad = a.shape[2]
+    diag_add, prior = split_hp(hp, d, has_noise, jitter)
+    L = torch.empty(B, npad, npad, dtype=F64, device=dev) if L_out is None else L_out
+    invdiag = torch.empty(B, nt, TILE, TILE, dtype=F64, device=dev)
+    yrem = y.to(F64).clone().contiguous()                      # right-hand side, updated panel by panel
+    z = torch.empty(B, npad, dtype=F64, device=dev)
+    logdet_half = torch.zeros(B, dtype=F64, device=dev)
+    zz = torch.zeros(B, dtype=F64, device=dev)
+    info = torch.zeros(B, dtype=torch.int32, device=dev)
+    _lib.call("gpr_se_build", _p(a), _p(nrm), _p(hp), hp.shape[-1], _p(diag_add), B, n, npad, dpad, _p(L), npad, 1, 1, _stream())
+    _count(1)
+    r_start, pXg, shared_upper = 0, None, False
+    if shared is not None:
+        ng = shared.n
+        _lib.call("gpr_copy_leading_block", _p(L), B, npad, _p(shared.L), shared.npad, ng, 1, _stream())
+        invdiag[:, : ng // TILE] = shared.invdiag[0, : ng // TILE]
+        z[:, :ng] = shared.z[0, :ng]
+        logdet_half[:] = shared.logdet_half[0]
+        zz[:] = shared.zz[0]
+        info[:] = shared.info[0]
+        pXg = ozaki_split(tril_inverse(shared)[0, :ng, :ng].contiguous(), slices)
+        r_start = ng
+    nn = npad * npad
+
+    def panel_update(e0, ne, r0, r1, pX, zsrc, z_stride, b_shared):
+        """rows below [r0, r1): P = K[below, r0:r1] X^T, K[below, below] -= P P^T, y[below] -= P z[r0:r1]"""
+        h, hR = r1 - r0, npad - r1
+        win = L[e0, r1:, r0:]                                  # [hR, .] window of the first expert of the chunk; the others nn apart
+        pA = ozaki_split(win, slices, batch=ne, batch_stride=nn, rows=hR, k=h)
+        ozaki_gemm_nt(pA, pX, out=L[e0:e0 + ne, r1:, r0:r1], batch=ne, b_lower=0, b_shared=b_shared)
+        pP = ozaki_split(win, slices, batch=ne, batch_stride=nn, rows=hR, k=h)
+        ozaki_gemm_nt(pP, pP, out=L[e0:e0 + ne, r1:, r1:], batch=ne, beta=1.0, alpha=-1.0, c_lower=True)
+        _lib.call("gpr_gemv_sub", _p(win), npad, nn, ne, hR, h, _p(zsrc), z_stride, _p(yrem[e0:e0 + ne, r1:]), yrem.stride(0), _stream())
+        _count(1)
+
+    # experts per chunk: what the free HBM holds of the transient digit planes (two sets of the widest [below x panel] window)
+    widest = (npad - r_start) * max(r_start, min(panel, npad - r_start))      # elements of the widest [below x panel] window
+    hmax = max(r_start if shared is None else 0, min(panel, npad - r_start))  # diagonal blocks inverted per chunk (not the shared one)
+    per = 2 * slices * widest + hmax * hmax * (16 + slices) + (1 << 20)
+    free, _ = torch.cuda.mem_get_info(dev)
+    E = int(max(1, min(chunk, B, (free - (2 << 30)) // per)))
+    for e0 in range(0, B, E):
+        ne = min(e0 + E, B) - e0
+        if shared is not None:
+            panel_update(e0, ne, 0, r_start, pXg, z[e0:e0 + ne], z.stride(0), True)
+        for r0 in range(r_start, npad, panel):
+            r1 = min(r0 + panel, npad)
+            h = r1 - r0
+            D = L[e0:e0 + ne, r0:r1, r0:r1].contiguous()
+            yp = yrem[e0:e0 + ne, r0:r1].contiguous()
+            invd, zp, ld, zzp, inf = potrf_inplace(D, yp)      # FP64: the panel's diagonal block (+ its part of the forward solve)
+            L[e0:e0 + ne, r0:r1, r0:r1] = D
+            invdiag[e0:e0 + ne, r0 // TILE:r1 // TILE] = invd
+            z[e0:e0 + ne, r0:r1] = zp
+            logdet_half[e0:e0 + ne] += ld
+            zz[e0:e0 + ne] += zzp
+            cur = info[e0:e0 + ne]
+            info[e0:e0 + ne] = torch.where((cur == 0) & (inf > 0), inf + r0, cur)
+            if r1 < npad:
+                X = torch.empty(ne, h, h, dtype=F64, device=dev)
+                scratch = _work("emf_potri", int(lib.gpr_potri_scratch_bytes(ne, h)), dev)
+                _lib.call("gpr_tril_inverse", _p(D), _p(invd), ne, h, _p(X), _p(scratch), _stream())
+                _count(3)
+                panel_update(e0, ne, r0, r1, ozaki_split(X.view(ne * h, h), slices), zp, zp.stride(0), False)
+    alpha = None
+    if want_alpha:
+        alpha = torch.empty(B, npad, dtype=F64, device=dev)
+        twork = _work("trsv", int(lib.gpr_trsv_work_bytes(B)), dev)
+        _lib.call("gpr_trsv_backward", _p(L), _p(invdiag), B, npad, _p(z), _p(alpha), _p(twork), _stream())
+        _count(1)
+    return FitState(B, n, npad, d, dpad, has_noise, hp, a, nrm, L, invdiag, z, alpha, logdet_half, zz, info, prior, shared)
 
 
 def fit_grbcm(xg: torch.Tensor, yg: torch.Tensor, hp_g: torch.Tensor, x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor,
@@ -764,14 +866,14 @@ def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0, out: Optional[
 
 def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = None, beta: float = 0.0,
                   b_lower: Optional[int] = None, batch: int = 1, a_upper: Optional[int] = None, c_lower: bool = False,
-                  alpha: float = 1.0) -> torch.Tensor:
+                  alpha: float = 1.0, b_shared: bool = False) -> torch.Tensor:
     """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt).
 
     b_lower = o: B[j, k] = 0 for k > j + o (True means o = 0), the zero k-blocks are skipped; a_upper = o: A[i, k] = 0 for
     k < i + o (rows of an upper-triangular factor); c_lower: only the tiles touching the lower triangle of C are computed and
     written.  batch > 1: A and B hold `batch` operands stacked along the rows (rows % 128 == 0 each); the result is [batch, M, N]."""
-    assert A.k == B.k and A.slices == B.slices and A.rows % batch == 0 and B.rows % batch == 0
-    M, N = A.rows // batch, B.rows // batch
+    assert A.k == B.k and A.slices == B.slices and A.rows % batch == 0 and (b_shared or B.rows % batch == 0)
+    M, N = A.rows // batch, (B.rows if b_shared else B.rows // batch)
     assert batch == 1 or (M % 128 == 0 and N % 128 == 0)
     shape = (M, N) if batch == 1 else (batch, M, N)
     if out is None:
@@ -783,7 +885,7 @@ def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = 
     off = -1 if b_lower is None or b_lower is False else (0 if b_lower is True else int(b_lower))
     _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), M, _p(B.planes), _p(B.scale), N, A.k, A.slices,
               off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0,
-              -1 if a_upper is None else int(a_upper), int(c_lower), float(alpha), _stream())
+              -1 if a_upper is None else int(a_upper), int(c_lower), float(alpha), int(b_shared and batch > 1), _stream())
     _count(1)
     return out
 

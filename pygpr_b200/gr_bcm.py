@@ -127,7 +127,7 @@ class GRBCM(GPR):
         if self._shares_hyperparameters():
             # one hyper-parameter vector for the whole committee: the local experts' factors start with the communication
             # expert's (gr_bcm.py:19-26 puts its training set first in every expert), so it is fitted first and reused
-            if g.need_upd and options.fused_fit:
+            if g.need_upd and options.fused_fit and options.emulate_fit_slices <= 0:
                 self._fused_update()                         # both factorisations in one launch
             else:
                 if g.need_upd:
@@ -374,6 +374,8 @@ class GRBCM_MLE:
         reserve = 6 << 30
         if options.emulate_grad_slices > 0:                  # staging of the emulated K^-1 products: two experts' worth
             reserve += 2 * npad * npad * (16 + options.emulate_grad_slices)
+        if options.emulate_fit_slices > 0:                   # digit planes of the emulated factorisation's panels: four experts' worth
+            reserve += 4 * npad * npad * options.emulate_fit_slices
         return int(max(1, min(g.nc, (free + held - reserve) // per)))
 
     def loss(self, params):

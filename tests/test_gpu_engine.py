@@ -347,3 +347,41 @@ def test_inverse_factors_assembled_from_segments(eng, orc, monkeypatch, shared):
         mean_o, var_o = orc.gp_predict(SPEC, hp[:2], x[:2], y[:2], xs, "diag")
         assert_close(mean[:2].cpu().numpy(), mean_o.numpy(), TOL, "mean")
         assert_close(var[:2].cpu().numpy(), var_o.numpy(), TOL, "var")
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_fit_emulated_matches_fp64_fit(eng, orc, monkeypatch, shared):
+    """Opt-in factorisation with emulated-FP64 panel solves and trailing updates (engine.fit_emulated, 7 digit planes, several panels
+    and expert chunks) against the FP64 DMMA Cholesky and the oracle: factor, forward / backward solve, NLML; non-PD reporting."""
+    from pygpr_b200 import config
+    B, n, d = 5, 1024, 6
+    x, y, xs, hp = _data(37, B, n, d, 64)
+    hp = hp[:1].expand(B, -1).contiguous()
+    st_g0 = st_g1 = None
+    if shared:
+        x[:, :512] = x[0, :512]; y[:, :512] = y[0, :512]
+        st_g0 = eng.fit(x[:1, :512].contiguous().cuda(), y[:1, :512].contiguous().cuda(), hp[:1].cuda(), True)
+        st_g1 = eng.fit(x[:1, :512].contiguous().cuda(), y[:1, :512].contiguous().cuda(), hp[:1].cuda(), True)
+    st0 = eng.fit(x.cuda(), y.cuda(), hp.cuda(), True, shared=st_g0)
+    st1 = eng.fit_emulated(x.cuda(), y.cuda(), hp.cuda(), True, slices=7, shared=st_g1, panel=256, chunk=2)
+    torch.cuda.synchronize()
+    assert int(st1.info.abs().sum()) == 0
+    assert_close(torch.tril(st1.L[:, :n, :n]).cpu().numpy(), torch.tril(st0.L[:, :n, :n]).cpu().numpy(), 1e-10, "L: emulated == FP64")
+    assert_close(st1.z.cpu().numpy(), st0.z.cpu().numpy(), 1e-10, "z")
+    assert_close(st1.alpha.cpu().numpy(), st0.alpha.cpu().numpy(), 1e-9, "alpha")
+    assert_close(st1.nlml().cpu().numpy(), st0.nlml().cpu().numpy(), 1e-11, "nlml")
+    L_ref, alpha_ref = orc.gp_fit(SPEC, hp[:2], x[:2], y[:2])
+    assert_close(torch.tril(st1.L[:2]).cpu().numpy(), L_ref.numpy(), 1e-9, "L vs oracle")
+    assert_close(st1.alpha[:2].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha vs oracle")
+    assert_close(st1.nlml()[:2].cpu().numpy(), orc.mle_loss(SPEC, hp[:2], x[:2], y[:2]).numpy(), TOL, "nlml vs oracle")
+    mean, var = eng.predict(st1, xs.cuda(), True) if not shared else eng.predict_pair(st_g1, st1, xs.cuda())[1]
+    mean0, var0 = eng.predict(st0, xs.cuda(), True) if not shared else eng.predict_pair(st_g0, st0, xs.cuda())[1]
+    assert_close(mean.cpu().numpy(), mean0.cpu().numpy(), 1e-9, "prediction from the emulated factor (mean)")
+    assert_close(var.cpu().numpy(), var0.cpu().numpy(), 1e-9, "prediction from the emulated factor (variance)")
+    if not shared:   # a non-positive-definite expert: reported in info like the FP64 path, the others unaffected
+        xb = x.clone(); xb[3, 700] = xb[3, 100]                  # duplicate point + negative "noise": K loses definiteness
+        hpb = hp.clone(); hpb[3, d + 1] = 0.0
+        stb = eng.fit_emulated(xb.cuda(), y.cuda(), hpb.cuda(), True, slices=7, panel=256, chunk=2, jitter=-1e-3)
+        st_ref = eng.fit(xb.cuda(), y.cuda(), hpb.cuda(), True, jitter=-1e-3)
+        torch.cuda.synchronize()
+        assert int(stb.info[3]) > 0 and [int(v) for v in stb.info.cpu()] == [int(v) for v in st_ref.info.cpu()]
