@@ -55,3 +55,8 @@ def set_potrf_mode(mode: str) -> None:
 
 def set_trsv_mode(mode: str) -> None:
     _lib.call("gpr_set_option", b"trsv_mode", mode.encode())
+
+
+def set_ozaki_bk(bk: int) -> None:
+    """k-block of the emulated-FP64 GEMM: 0 = default (64 B swizzled rows), 32 / 64 = forced (the 32 B variant is an A/B knob)."""
+    _lib.call("gpr_set_option", b"ozaki_bk", str(int(bk)).encode())

@@ -54,12 +54,14 @@ static int parse_potrf_mode(const char* v) {
     return POTRF_AUTO;
 }
 static int parse_trsv_mode(const char* v) { return (v && !strcmp(v, "single")) ? TRSV_SINGLE : TRSV_AUTO; }
+extern int g_ozaki_bk;   // ozaki_gemm.cu
 static int g_potrf_mode = parse_potrf_mode(getenv("PYGPR_POTRF_MODE"));
 static int g_trsv_mode = parse_trsv_mode(getenv("PYGPR_TRSV_MODE"));
 
 extern "C" int gpr_set_option(const char* name, const char* value) {
     if (name && !strcmp(name, "potrf_mode")) { g_potrf_mode = parse_potrf_mode(value); return GPR_OK; }
     if (name && !strcmp(name, "trsv_mode")) { g_trsv_mode = parse_trsv_mode(value); return GPR_OK; }
+    if (name && !strcmp(name, "ozaki_bk")) { g_ozaki_bk = value ? atoi(value) : 0; return GPR_OK; }
     return fail(GPR_ERR_BAD_ARG, "unknown option %s", name ? name : "(null)");
 }
 

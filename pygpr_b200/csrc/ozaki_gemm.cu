@@ -17,8 +17,8 @@
 //            ([slices][rows][64 B], SWIZZLE_64B) into a multi-stage shared-memory ring (mbarrier full/empty);
 //   warp 1   allocates TMEM (slices x 64 columns of int32 accumulators, one per diagonal) and issues the UMMA stream;
 //            `tcgen05.commit` releases ring slots / signals the epilogue;
-//   warps 2-5 epilogue: `tcgen05.ld` 32x32b, Horner recombination of the diagonals in FP64, power-of-two row/column
-//            scales, store.
+//   warps 2-9 epilogue (two per TMEM lane quadrant, 32 columns each): `tcgen05.ld` 32x32b, Horner recombination of the
+//            diagonals in FP64, power-of-two row/column scales, store.
 #include <cuda.h>   // CUtensorMap + enums only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked
 #include <cuda_runtime.h>
 #include <math.h>
@@ -28,19 +28,20 @@
 #include "../../include/pygpr_b200.h"
 
 extern "C" int gpr_internal_fail(int code, const char* fmt, const char* a, long long v);   // gpr_kernels.cu
+int g_ozaki_bk = 0;   // developer A/B knob (gpr_set_option "ozaki_bk"): 0 = automatic, 32 / 64 = force the k-block
 
 namespace oz {
 
 constexpr int BM = 128;           // output rows per CTA  = TMEM lanes = UMMA M
 constexpr int BN = 64;            // output columns per CTA = UMMA N; slices * BN <= 512 TMEM columns
-constexpr int BK = 64;            // int8 per k-block = one SWIZZLE_64B row; two UMMA k-steps of 32
+constexpr int BK = 64;            // int8 per k-block = one SWIZZLE_64B row; two UMMA k-steps of 32 (planes are padded to this)
+constexpr int BK_SMALL = 32;      // alternative k-block (A/B knob "ozaki_bk"): one SWIZZLE_32B row, one UMMA k-step — half the stage,
+                                  // twice the ring depth; measured slower, see gpr_ozaki_gemm_nt
 constexpr int MAX_SLICES = 8;
-constexpr int A_PLANE = BM * BK;  // bytes of one digit plane of the A tile in a stage
-constexpr int B_PLANE = BN * BK;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;      // warp 0 TMA, warp 1 UMMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-__host__ __device__ inline int stage_bytes(int slices) { return slices * (A_PLANE + B_PLANE); }
+__host__ __device__ inline int stage_bytes(int slices, int bk) { return slices * (BM + BN) * bk; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -115,11 +116,21 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
                  : "memory");
 }
 
+// exact int32 -> double without the conversion pipe: the biased integer is dropped into the mantissa of 2^52 and the bias
+// (2^52 + 2^31) subtracted — one logic op and one DADD instead of I2F.F64
+__device__ __forceinline__ double i32_to_f64(uint32_t v) {
+    return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
 // K-major operand tile [rows][64 B] written by TMA with SWIZZLE_64B: 8-row groups 512 B apart; LBO unused for swizzled
 // K-major layouts (set to 1 like CUTLASS); descriptor version 1 (Blackwell); layout type 4 = SWIZZLE_64B.
-constexpr uint64_t DESC_HI = (1ull << 16) | ((512ull >> 4) << 32) | (1ull << 46) | (4ull << 61);
-constexpr uint32_t DESC_HI32 = (uint32_t)(DESC_HI >> 32);
-constexpr uint32_t DESC_LO_FIXED = (uint32_t)(DESC_HI & 0xFFFFFFFFull);      // LBO field
+// (SWIZZLE_32B rows are 32 B: groups 256 B apart, layout type 6.)
+template <int BKT>
+struct Desc {
+    static constexpr uint64_t HI = (1ull << 16) | (((uint64_t)(8 * BKT) >> 4) << 32) | (1ull << 46) | ((BKT == 64 ? 4ull : 6ull) << 61);
+    static constexpr uint32_t HI32 = (uint32_t)(HI >> 32);
+};
+constexpr uint32_t DESC_LO_FIXED = 1u << 16;                                  // LBO field
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return DESC_LO_FIXED | ((addr & 0x3FFFF) >> 4); }
 
 // instruction descriptor: D = S32 (2 @bit 4), A = B = signed 8 bit (1 @bit 7, 1 @bit 10), both K-major, N>>3 @bit 17, M>>4 @bit 24
@@ -134,11 +145,13 @@ __host__ __device__ constexpr uint32_t idesc_for(int n) {
 // planes.  A 128 x N x 32 i8 UMMA fed from shared memory costs max(N/2, (128+N)/4) clocks (tools/microbench/umma_i8_rate.cu:
 // N=64 48, N=128 64, N=256 128): fused, the A plane is read once per 256 columns instead of once per 64 and the stream runs at
 // ~95 % of the tensor pipe instead of 67 %.  Fully unrolled: every offset and descriptor field is an immediate.
-template <int S, bool FIRST>
+template <int S, bool FIRST, int BKT>
 __device__ __forceinline__ void issue_k_block(uint32_t tmem, uint32_t a_lo, uint32_t b_lo) {
     constexpr int PL = 256 / BN;                       // B planes per UMMA
+    constexpr int A_PLANE = BM * BKT, B_PLANE = BN * BKT;
+    constexpr uint32_t DESC_HI32 = Desc<BKT>::HI32;
 #pragma unroll
-    for (int kk = 0; kk < BK / 32; ++kk)
+    for (int kk = 0; kk < BKT / 32; ++kk)
 #pragma unroll
         for (int t = 0; t < S; ++t)
 #pragma unroll
@@ -216,7 +229,7 @@ __global__ void __launch_bounds__(256) split_kernel(const double* __restrict__ X
 // ---------------------------------------------------------------------------------------------
 // the GEMM
 // ---------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int BKT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ C, long long ldc,
@@ -225,7 +238,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled tiles want (at least) 512 B alignment
-    constexpr int sbytes = S * (A_PLANE + B_PLANE);
+    constexpr int A_PLANE = BM * BKT;
+    constexpr int sbytes = S * (BM + BN) * BKT;
     const uint32_t bar_full = base + (uint32_t)(stages * sbytes);
     const uint32_t bar_empty = bar_full + 8u * stages;
     const uint32_t bar_tmem = bar_empty + 8u * stages;
@@ -245,9 +259,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     int tn = in_group / gsz;
     if (b_lower >= 0) tn = tiles_n - 1 - tn;
     if (c_lower && tn * BN > tm * BM + BM - 1) return;          // only tiles on / below the diagonal of C are wanted (whole CTA leaves)
-    int nkb = kpad / BK;
-    if (b_lower >= 0) nkb = min(nkb, (b_lower + (tn + 1) * BN + BK - 1) / BK);   // B[j, k] = 0 for k > j + b_lower
-    const int kb0 = a_upper >= 0 ? min(nkb - 1, (a_upper + tm * BM) / BK) : 0;  // A[i, k] = 0 for k < i + a_upper (rows of an upper factor)
+    int nkb = kpad / BKT;
+    if (b_lower >= 0) nkb = min(nkb, (b_lower + (tn + 1) * BN + BKT - 1) / BKT);   // B[j, k] = 0 for k > j + b_lower
+    const int kb0 = a_upper >= 0 ? min(nkb - 1, (a_upper + tm * BM) / BKT) : 0;   // A[i, k] = 0 for k < i + a_upper (rows of an upper factor)
     // batched product: batch entry blockIdx.y owns a_batch_rows / b_batch_rows consecutive (padded) rows of the plane arrays
     const int a_row0 = blockIdx.y * a_batch_rows + tm * BM, b_row0 = blockIdx.y * b_batch_rows + tn * BN;
     scaleA += (long long)blockIdx.y * a_batch_rows;
@@ -286,8 +300,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 const uint32_t full = bar_full + 8u * stage;
                 const uint32_t dst = base + (uint32_t)(stage * sbytes);
                 mbar_expect_tx(full, (uint32_t)sbytes);
-                tma_load_3d(dst, &mapA, full, kb * BK, a_row0, 0);
-                tma_load_3d(dst + (uint32_t)(S * A_PLANE), &mapB, full, kb * BK, b_row0, 0);
+                tma_load_3d(dst, &mapA, full, kb * BKT, a_row0, 0);
+                tma_load_3d(dst + (uint32_t)(S * A_PLANE), &mapB, full, kb * BKT, b_row0, 0);
             }
             __syncwarp();
             if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -303,8 +317,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const uint32_t a_lo = desc_lo(base + (uint32_t)(stage * sbytes));
             const uint32_t b_lo = a_lo + (uint32_t)((S * A_PLANE) >> 4);
             if (leader) {
-                if (kb == kb0) issue_k_block<S, true>(tmem, a_lo, b_lo);
-                else issue_k_block<S, false>(tmem, a_lo, b_lo);
+                if (kb == kb0) issue_k_block<S, true, BKT>(tmem, a_lo, b_lo);
+                else issue_k_block<S, false, BKT>(tmem, a_lo, b_lo);
                 umma_commit(bar_empty + 8u * stage);       // ring slot free once these products have read it
             }
             __syncwarp();
@@ -313,14 +327,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         if (leader) umma_commit(bar_tmem);                  // accumulators complete
         __syncwarp();
     } else {
-        // ---- epilogue warps 2..5: warp w may touch TMEM lanes [32 (w % 4), +32) ------------------------------------------------
+        // ---- epilogue warps 2..9: warp w may touch TMEM lanes [32 (w % 4), +32); warps w and w + 4 split the columns --------------
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                   // which 32 of the tile's 64 columns this warp drains
         const int row = tm * BM + q * 32 + lane;
         const double sa = alpha * scaleA[row];              // scale arrays are padded to whole tiles
         mbar_wait(bar_tmem, 0);
         tc_fence_after();
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
             // all diagonals of these 16 columns in flight at once, ONE wait: S TMEM round trips overlap instead of serialising
             uint32_t v[S][16];
 #pragma unroll
@@ -333,7 +348,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
             for (int g = S - 1; g >= 0; --g)               // Horner in 1/256, smallest diagonal first
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], 0.00390625, (double)(int)v[g][i]);
+                for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], 0.00390625, i32_to_f64(v[g][i]));
             const int col0 = tn * BN + c0;
             if (row < M) {
                 double* crow = C + (long long)row * ldc + col0;
@@ -374,15 +389,16 @@ static encode_fn_t encoder() {
 }
 
 // planes [slices][rpad][kpad] int8 as a 3-D tensor (k fastest); box = all planes of a [box_rows x 64] tile
-static int make_map(CUtensorMap* map, const void* planes, int rpad, int kpad, int slices, int box_rows) {
+static int make_map(CUtensorMap* map, const void* planes, int rpad, int kpad, int slices, int box_rows, int bk) {
     encode_fn_t enc = encoder();
     if (!enc) return gpr_internal_fail(GPR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s", "", 0);
     cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)rpad, (cuuint64_t)slices};
     cuuint64_t strides[2] = {(cuuint64_t)kpad, (cuuint64_t)kpad * (cuuint64_t)rpad};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)slices};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, (cuuint32_t)slices};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(planes), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return gpr_internal_fail(GPR_ERR_CUDA, "cuTensorMapEncodeTiled failed%s (CUresult %lld)", "", (long long)r);
     return GPR_OK;
@@ -421,12 +437,17 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
         return gpr_internal_fail(GPR_ERR_UNSUPPORTED, "K too long for exact int32 accumulation%s (K=%lld): split the product", "", K);
     const int kpad = oz::round_up(K, oz::BK);
     const int rpadA = oz::round_up(M, oz::BM), rpadB = oz::round_up(N, oz::BM);
+    // k-block: 64 B rows.  The 32 B variant (twice the ring depth where 7-8 digit planes leave room for only two 64-wide stages)
+    // is kept as an A/B knob: measured slower at every plane count (4096^3, 7 planes: 92 vs 106 TFLOP/s-equivalent; 6 planes:
+    // 110 vs 142) — the per-stage handshake and the 32 B TMA rows cost more than the deeper ring hides.
+    int bk = oz::BK;
+    if (g_ozaki_bk == 32 || g_ozaki_bk == 64) bk = g_ozaki_bk;
     CUtensorMap mapA, mapB;
-    int rc = oz::make_map(&mapA, planesA, rpadA * batch, kpad, slices, oz::BM);
+    int rc = oz::make_map(&mapA, planesA, rpadA * batch, kpad, slices, oz::BM, bk);
     if (rc != GPR_OK) return rc;
-    rc = oz::make_map(&mapB, planesB, b_shared ? rpadB : rpadB * batch, kpad, slices, oz::BN);
+    rc = oz::make_map(&mapB, planesB, b_shared ? rpadB : rpadB * batch, kpad, slices, oz::BN, bk);
     if (rc != GPR_OK) return rc;
-    const int sbytes = oz::stage_bytes(slices);
+    const int sbytes = oz::stage_bytes(slices, bk);
     int stages = (oz::SMEM_LIMIT - 2048) / sbytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return gpr_internal_fail(GPR_ERR_UNSUPPORTED, "too many digit planes for a two-stage ring%s (%lld)", "", slices);
@@ -436,18 +457,20 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
     const int tiles_m = (M + oz::BM - 1) / oz::BM, tiles_n = (N + oz::BN - 1) / oz::BN;
     const int group_m = tiles_m < 16 ? tiles_m : 16;
     cudaError_t e = cudaSuccess;
+#define OZ_LAUNCH_BK(S, BKT)                                                                                                   \
+    e = cudaFuncSetAttribute(oz::gemm_kernel<S, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                      \
+    if (e == cudaSuccess)                                                                                                      \
+        oz::gemm_kernel<S, BKT><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                  \
+            mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA,                  \
+            b_shared ? 0 : rpadB, c_batch_stride, a_upper, c_lower, alpha);
 #define OZ_LAUNCH(S)                                                                                                           \
     case S:                                                                                                                    \
-        e = cudaFuncSetAttribute(oz::gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
-        if (e == cudaSuccess)                                                                                                  \
-            oz::gemm_kernel<S><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                   \
-                mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA,              \
-                b_shared ? 0 : rpadB,                                                                                          \
-                c_batch_stride, a_upper, c_lower, alpha);                                                                      \
+        if (bk == 64) { OZ_LAUNCH_BK(S, 64) } else { OZ_LAUNCH_BK(S, 32) }                                                     \
         break;
     switch (slices) {
         OZ_LAUNCH(1) OZ_LAUNCH(2) OZ_LAUNCH(3) OZ_LAUNCH(4) OZ_LAUNCH(5) OZ_LAUNCH(6) OZ_LAUNCH(7) OZ_LAUNCH(8)
     }
+#undef OZ_LAUNCH_BK
 #undef OZ_LAUNCH
     if (e != cudaSuccess) return gpr_internal_fail(GPR_ERR_CUDA, "%s (cuda error %lld)", cudaGetErrorString(e), (long long)e);
     e = cudaGetLastError();

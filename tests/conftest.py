@@ -36,3 +36,4 @@ def _restore_library_modes(request):
         from pygpr_b200 import config
         config.set_potrf_mode("auto")
         config.set_trsv_mode("auto")
+        config.set_ozaki_bk(0)

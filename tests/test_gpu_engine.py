@@ -251,11 +251,13 @@ def test_vt_forms_agree(eng, orc):
 
 # ---- emulated FP64 on the INT8 tcgen05 tensor cores (csrc/ozaki_gemm.cu): integer work is checked BIT-EXACT ----------------------
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 100, 130), (300, 257, 1000), (1, 1, 1)])
-@pytest.mark.parametrize("slices", [1, 3, 6, 8])
-def test_ozaki_digit_planes_and_product_bit_exact(eng, M, N, K, slices):
+@pytest.mark.parametrize("slices,bk", [(1, 0), (3, 32), (6, 0), (6, 32), (7, 64), (8, 0)])
+def test_ozaki_digit_planes_and_product_bit_exact(eng, M, N, K, slices, bk):
     """gpr_ozaki_split's digit planes / row scales equal the numpy restatement (oracle/ozaki_ref.py) bit for bit, and
     gpr_ozaki_gemm_nt's C equals the restatement's (exact integer diagonals, same FP64 recombination order) bit for bit."""
     from oracle import ozaki_ref
+    from pygpr_b200 import config
+    config.set_ozaki_bk(bk)                                  # both k-block variants (64 B / 32 B swizzled rows), and the automatic choice
     g = torch.Generator().manual_seed(3)
     A = torch.randn(M, K, generator=g, dtype=torch.float64) * torch.exp(2.0 * torch.randn(M, 1, generator=g, dtype=torch.float64))
     B = torch.randn(N, K, generator=g, dtype=torch.float64)

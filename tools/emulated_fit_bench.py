@@ -13,8 +13,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pygpr_b200 import engine as eng  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-S = int(sys.argv[2]) if len(sys.argv) > 2 else 7
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 32
+S = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 7
 m0, d = 4096, 16
 g = torch.Generator().manual_seed(0)
 xg = torch.rand(1, m0, d, generator=g, dtype=torch.float64)
@@ -45,7 +45,8 @@ flops = B * ((2.0 * m0) ** 3 - float(m0) ** 3) / 3.0
 t0, st0 = timed(lambda: eng.fit(x, y, hp, True, L_out=Lbuf, shared=st_g))
 ref = {"L": torch.tril(st0.L).clone(), "nlml": st0.nlml().clone(), "alpha": st0.alpha.clone()}
 print(json.dumps({"impl": "fp64_dmma", "experts": B, "ms": t0, "tflops": flops / t0 * 1e-9}), flush=True)
-for panel, chunk in ((1024, 32), (2048, 32), (1024, 16), (512, 32)):
+CONFIGS = ((1024, 32),) if "one" in sys.argv else ((1024, 32), (2048, 32), (1024, 16), (512, 32))
+for panel, chunk in CONFIGS:
     t1, st1 = timed(lambda: eng.fit_emulated(x, y, hp, True, slices=S, L_out=Lbuf, shared=st_g, panel=panel, chunk=chunk))
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
     print(json.dumps({"impl": "emulated", "slices": S, "panel": panel, "chunk": chunk, "ms": t1, "tflops_equiv": flops / t1 * 1e-9,

@@ -42,9 +42,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--bk", type=int, default=0, help="force the GEMM's k-block (32 / 64); 0 = automatic")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    from pygpr_b200 import config
+    config.set_ozaki_bk(args.bk)
     out = []
 
     def emit(rec):
