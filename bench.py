@@ -447,6 +447,13 @@ def main():
                "e2e": {"value": m / (emu_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": emu_e2e_ms, "h2d_bytes_per_step": m * d * 8,
                        "d2h_bytes_per_step": 2 * m * 8},
                "tflops_equiv": (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m / emu_ms * 1e-9,
+               # INT8 tensor work of a step (plane products x 2 MNK of every expert's product) over the WHOLE step — digit-plane
+               # preparation, reductions and aggregation included — against the INT8 UMMA rate measured on this pool
+               # (tools/microbench/umma_i8_rate.cu, profiles/r02_umma_i8_rate.jsonl: 4518 TOP/s at N >= 128)
+               "roofline": {"bound": "tensor (int8 tcgen05)", "unit": "TOP/s", "peak": 4518.0,
+                            "achieved": args.emulate * (args.emulate + 1) // 2 * (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m / emu_ms * 1e-9,
+                            "frac": args.emulate * (args.emulate + 1) // 2 * (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m / emu_ms * 1e-9 / 4518.0,
+                            "peak_source": "measured: 128 x N x 32 kind::i8 UMMA issue rate on all 148 SMs, N = 128 / 256 (profiles/r02_umma_i8_rate.jsonl)"},
                "aggregate_mean_vs_fp64_path": rel(mu_e, mu), "aggregate_var_vs_fp64_path": rel(var_e, var),
                "expert_mean_vs_fp64_path": rel(last["ml"], ml_fp64), "expert_var_vs_fp64_path": rel(last["vl"], vl_fp64),
                "what": "GRBCM.predict with options.emulate_slices: per expert V_l^T = K* X_l^T (X_l = rows of L^-1) as one Ozaki-split "
