@@ -227,7 +227,11 @@ __global__ void __launch_bounds__(256) split_kernel(const double* __restrict__ X
 }
 
 // ---------------------------------------------------------------------------------------------
-// the GEMM
+// the GEMM.  One CTA per output tile on purpose: a persistent variant (one CTA per SM looping over a static tile list, TMEM / barriers
+// set up once, the next tile's first TMA loads issued under the epilogue) was built and measured on the same box — +3-4 % on long
+// dense products, but every product of the path is triangular (b_lower / a_upper / c_lower: k-ranges differ from tile to tile) and
+// there the hardware's block scheduler balances better than a static list, while the restructured kernel cost the short-k panel
+// products of the factorisation 12 % (80 -> 91 ms per 32 experts).  Not kept.
 // ---------------------------------------------------------------------------------------------
 template <int S, int BKT>
 __global__ void __launch_bounds__(NTHREADS, 1)
