@@ -19,7 +19,14 @@ def timed(fn, reps=3):
     return best, out
 
 def main():
-    which = sys.argv[1:] or ["1", "2", "3"]
+    args = [a for a in sys.argv[1:] if a != "--emulate"]
+    which = args or ["1", "2", "3"]
+    mode = "fp64_dmma"
+    if "--emulate" in sys.argv:   # every opt-in emulated-FP64 form at once (INT8 tcgen05 tensor cores)
+        from pygpr_b200 import config
+        config.options.emulate_slices = 6
+        config.options.emulate_grad_slices = config.options.emulate_inverse_slices = config.options.emulate_fit_slices = 7
+        mode = "emulated (predict 6 planes; fit / L^-T / K^-1 7 planes)"
     cov = P.Compose([P.Squared_exponential(), P.White_noise()])
     torch.manual_seed(0)
     if "1" in which:  # exact GPR, 1-D sine, n=1000
@@ -30,7 +37,7 @@ def main():
         tp, _ = timed(lambda: gp.predict(xs, var="diag"))
         mle = P.MLE(gp); hp = gp.params.numpy()
         tl, _ = timed(lambda: mle.loss(hp)); tg, _ = timed(lambda: mle.loss_and_grad(hp))
-        print(json.dumps({"config": "1: exact GPR n=1000 d=1 m=1000", "fit_ms": tf * 1e3, "predict_ms": tp * 1e3,
+        print(json.dumps({"mode": mode, "config": "1: exact GPR n=1000 d=1 m=1000", "fit_ms": tf * 1e3, "predict_ms": tp * 1e3,
                           "pred_per_s": 1000 / tp, "loss_ms": tl * 1e3, "loss_and_grad_ms": tg * 1e3}), flush=True)
     if "2" in which:  # exact GPR ARD-SE n=16384, d=8, LML + gradient
         n, d = 16384, 8
@@ -42,7 +49,9 @@ def main():
         xs = torch.rand(1024, d)
         gp.update()
         tp, _ = timed(lambda: gp.predict(xs, var="diag"), 2)
-        print(json.dumps({"config": "2: exact GPR n=16384 d=8 LML+grad", "predict_1024_ms": tp * 1e3, "loss_ms": tl * 1e3, "loss_tflops": n ** 3 / 3 / tl * 1e-12,
+        mu2, var2 = gp.predict(xs, var="diag")
+        print(json.dumps({"mode": mode, "config": "2: exact GPR n=16384 d=8 LML+grad", "predict_1024_ms": tp * 1e3,
+                          "pred_checksum": [float(torch.as_tensor(mu2).sum()), float(torch.as_tensor(var2).sum())], "loss_ms": tl * 1e3, "loss_tflops": n ** 3 / 3 / tl * 1e-12,
                           "loss_and_grad_ms": tg * 1e3, "loss_and_grad_tflops": float(n) ** 3 / tg * 1e-12, "nlml": float(nl),
                           "grad_norm": float(np.linalg.norm(lg[1])), "get_learn_rate_ms": tr * 1e3, "gamma": float(gamma)}), flush=True)
     if "3" in which:  # GRBCM 64 x 2048 + comm, d=8
@@ -55,9 +64,11 @@ def main():
         tf, _ = timed(fit, 2)
         tp, _ = timed(lambda: model.predict(xs, var="diag"), 2)
         flops = (M - 1) * (2 * m0) ** 3 / 3 + m0 ** 3 / 3
-        print(json.dumps({"config": "3: GRBCM 64x2048 d=8 (63 experts of order 4096 + comm), m=4096", "fit_ms": tf * 1e3,
+        print(json.dumps({"mode": mode, "config": "3: GRBCM 64x2048 d=8 (63 experts of order 4096 + comm), m=4096", "fit_ms": tf * 1e3,
                           "fit_tflops_unshared_count": flops / tf * 1e-12, "predict_ms": tp * 1e3, "pred_per_s": m / tp,
-                          "shared_leading_block": model.gpl._state.shared_from is not None}), flush=True)
+                          "shared_leading_block": model.gpl._state.shared_from is not None,
+                          "agg_checksum": [float(torch.as_tensor(model.predict(xs, var="diag")[0]).sum()),
+                                           float(torch.as_tensor(model.predict(xs, var="diag")[1]).sum())]}), flush=True)
     if "5" in which:  # one GPU's slice of config 5: GRBCM training, experts of order 16384 (8192 comm + 8192 local), d=32
         nc, m0, d = 16, 8192, 32
         x = torch.rand(nc + 1, m0, d); y = torch.sin(x.sum(-1)) + 0.1 * torch.randn(nc + 1, m0)
