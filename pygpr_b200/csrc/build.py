@@ -8,7 +8,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libpygpr_b200.so")
 SOURCES = [os.path.join(HERE, "gpr_kernels.cu"), os.path.join(HERE, "ozaki_gemm.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "gpr_core.cuh"), os.path.join(ROOT, "include", "pygpr_b200.h")]
+DEPS = SOURCES + [os.path.join(HERE, "gpr_core.cuh"), os.path.join(HERE, "gpr_diag_tile.cuh"), os.path.join(ROOT, "include", "pygpr_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -10,6 +10,7 @@
 
 #include "../../include/pygpr_b200.h"
 #include "gpr_core.cuh"
+#include "gpr_diag_tile.cuh"
 
 using namespace gpr;
 
@@ -499,11 +500,8 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             }
     }
     __syncthreads();
-    DiagBlock blk;
-    diag_block_coords(blk);
-    __shared__ double invblk[(TILE / 8) * 64];
-    double* Bm = smem + TILE * XLD;  // block-major exchange buffer, behind the tile (the GEN feature tiles there are spent)
-    potf2_blk(T, Bm, invblk, s_fail, blk);
+    double* Bm = smem + TILE * XLD;  // scratch of the tile routines, behind the tile (the GEN feature tiles there are spent)
+    potf2_tile(T, Bm, s_fail);
 
     // write L_jj (strict upper zeroed) and accumulate sum log L_ii
     for (int id = tid; id < TILE * TILE; id += NTHREADS) {
@@ -527,7 +525,7 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             }
         }
     }
-    trtri_blk(T, Bm, invblk, blk);
+    trtri_tile(T, Bm);
     double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
     for (int id = tid; id < TILE * TILE; id += NTHREADS) inv[id] = T[(id >> 7) * XLD + (id & 127)];
     if (y) {
