@@ -18,14 +18,6 @@
 
 namespace gpr {
 
-// developer build (tools/microbench/diag_tile.cu): clock stamps of the phases of potf2_tile, thread 0
-#ifdef DT_PROFILE
-__device__ long long g_dt_stamps[4][5];
-#define DT_STAMP(i) do { if (threadIdx.x == 0) g_dt_stamps[p][i] = clock64(); } while (0)
-#else
-#define DT_STAMP(i) do { } while (0)
-#endif
-
 constexpr int DT_NB = 32;                                  // panel width
 constexpr int XD_LD = 36;                                  // row stride of the scratch blocks (36 mod 16 = 4: conflict-free fragments)
 // scratch (doubles) behind the tile: 4 diagonal inverses [32][XD_LD], the columns of the current L_pp [32][32], 1/L_kk [128],
@@ -160,15 +152,12 @@ __device__ __forceinline__ void potf2_tile(double* T, double* S, int* fail) {
     for (int p = 0; p < TILE / DT_NB; ++p) {
         const int r0 = p * DT_NB;
         double* Xp = S + DT_XD + p * DT_NB * XD_LD;
-        DT_STAMP(0);
         if (warp == 0) {
             const int f = chol32_warp(T, r0, LT, dinv + r0);
             if (f && lane == 0) atomicMin(fail, r0 + f);
-            DT_STAMP(1);
             inv32_warp(LT, dinv + r0, Xp);
         }
         __syncthreads();
-        DT_STAMP(2);
         const int t0 = r0 + DT_NB, nb = TILE - t0;        // rows below the diagonal block
         if (nb == 0) break;
         // panel: P = A inv(L_pp)^T, in place; a warp owns whole rows, so only its own reads precede its writes
@@ -183,7 +172,6 @@ __device__ __forceinline__ void potf2_tile(double* T, double* S, int* fail) {
             for (int n = 0; n < 4; ++n) *reinterpret_cast<double2*>(Arow + g * XLD + 8 * n + 2 * t) = make_double2(c[n][0], c[n][1]);
         }
         __syncthreads();
-        DT_STAMP(3);
         // trailing update of the lower blocks: unit (i, J) = rows t0 + 8 i .., columns t0 + 32 J .. (J <= i / 4)
         int u = 0;
         for (int i = 0; i < nb / 8; ++i)
@@ -204,7 +192,6 @@ __device__ __forceinline__ void potf2_tile(double* T, double* S, int* fail) {
                     if (n < nmax) *reinterpret_cast<double2*>(Crow + g * XLD + 8 * n + 2 * t) = make_double2(c[n][0], c[n][1]);
             }
         __syncthreads();
-        DT_STAMP(4);
     }
 }
 

@@ -444,6 +444,15 @@ struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-war
 // potf2 + trti2 in registers -> L_jj, inv(L_jj), log-determinant / info, forward-solve block z_j.
 // Scalars that several CTAs update in turn (logdet_half, zz, info) and z go through L2 (__ldcg/__stcg): in the dataflow
 // kernel consecutive block columns of one expert run on different SMs and L1 is not coherent.
+// developer build (-DGPR_DIAG_STAMPS, tools/diag_phases.py): clock stamps of the phases of a diagonal-tile task, expert 0
+#ifdef GPR_DIAG_STAMPS
+__device__ long long g_diag_stamps[16];
+#define DIAG_STAMP(i) do { if (threadIdx.x == 0 && b == 0) g_diag_stamps[i] = clock64(); } while (0)
+extern "C" int gpr_debug_diag_stamps(long long* out) { return cudaMemcpyFromSymbol(out, g_diag_stamps, sizeof(g_diag_stamps)) == cudaSuccess ? 0 : 1; }
+#else
+#define DIAG_STAMP(i) do { } while (0)
+#endif
+
 template <bool GEN>
 __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem, double* pub, double* svec, int* s_fail, double* Lb,
                                             int b, int j, int n, int npad, const double* __restrict__ a,
@@ -464,6 +473,21 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
     double* Ljj = Lb + ((long long)j * TILE) * npad + j * TILE;
     if (tid == 0) *s_fail = 1 << 30;
     double* T = smem;  // full tile overlays the (drained) pipeline stages
+    // the look-ahead partial product parked by the previous column joins the accumulators first: eight independent 16-byte loads
+    // per batch (inside the element-wise epilogues below every load sat behind the previous store: ~400 clocks each, serial)
+    if (dpart != nullptr) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            double2 p2[8];
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) p2[ni] = *reinterpret_cast<const double2*>(dpart + (long long)acc_row(mi) * npad + acc_col(ni, 0));
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+                acc[mi][ni][0] += p2[ni].x;
+                acc[mi][ni][1] += p2[ni].y;
+            }
+        }
+    }
     if (GEN) {
         double* fbase = smem + TILE * XLD;
         FeatSmem f = carve_feat(fbase, dpad);
@@ -480,28 +504,25 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             double v;
             if (gr < n && gc < n) v = (r == c) ? kv + dadd : kv;
             else v = (r == c) ? 1.0 : 0.0;
-            if ((dpart != nullptr)) v -= dpart[(long long)r * npad + c];
             T[r * XLD + c] = v - acc[mi][ni][e];
         });
     } else {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi) {
+            const int r = acc_row(mi);
+            double2 k2[8];
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
-                const int r = acc_row(mi), c = acc_col(ni, 0);
-                double2 k2 = *reinterpret_cast<const double2*>(Ljj + (long long)r * npad + c);
-                if ((dpart != nullptr)) {
-                    const double2 p2 = *reinterpret_cast<const double2*>(dpart + (long long)r * npad + c);
-                    k2.x -= p2.x;
-                    k2.y -= p2.y;
-                }
-                T[r * XLD + c] = k2.x - acc[mi][ni][0];
-                T[r * XLD + c + 1] = k2.y - acc[mi][ni][1];
-            }
+            for (int ni = 0; ni < 8; ++ni) k2[ni] = *reinterpret_cast<const double2*>(Ljj + (long long)r * npad + acc_col(ni, 0));
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+                *reinterpret_cast<double2*>(T + r * XLD + acc_col(ni, 0)) = make_double2(k2[ni].x - acc[mi][ni][0], k2[ni].y - acc[mi][ni][1]);
+        }
     }
     __syncthreads();
+    DIAG_STAMP(3);
     double* Bm = smem + TILE * XLD;  // scratch of the tile routines, behind the tile (the GEN feature tiles there are spent)
     potf2_tile(T, Bm, s_fail);
+    DIAG_STAMP(4);
 
     // write L_jj (strict upper zeroed) and accumulate sum log L_ii
     for (int id = tid; id < TILE * TILE; id += NTHREADS) {
@@ -525,21 +546,43 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             }
         }
     }
+    DIAG_STAMP(5);
     trtri_tile(T, Bm);
+    DIAG_STAMP(6);
     double* inv = invdiag + ((long long)b * nt + j) * TILE * TILE;
     for (int id = tid; id < TILE * TILE; id += NTHREADS) inv[id] = T[(id >> 7) * XLD + (id & 127)];
+    DIAG_STAMP(7);
     if (y) {
         // z_j = inv(L_jj) (y_j - L[j,0:j] z[0:j]); warp per row, lanes along k, fixed-order reduction
         if (tid < TILE) pub[tid] = y[(long long)b * npad + j * TILE + tid] - svec[tid];
         __syncthreads();
         const int lane = tid & 31, warp = tid >> 5;
-        for (int r = warp; r < TILE; r += NTHREADS / 32) {
-            double s = 0.0;
-            for (int k = lane; k <= r; k += 32) s += T[r * XLD + k] * pub[k];
-            s = warp_sum(s);
+        // four rows of a warp in flight: their shuffle reductions overlap (one at a time the 16 rows of a warp cost 16 x 10 dependent
+        // shuffles, ~12 k clocks of the chain)
+        const double pk0 = pub[lane], pk1 = pub[lane + 32], pk2 = pub[lane + 64], pk3 = pub[lane + 96];
+#pragma unroll
+        for (int rr = 0; rr < TILE / (NTHREADS / 32); rr += 4) {
+            double s[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = warp + (rr + q) * (NTHREADS / 32);
+                const double* Tr = T + r * XLD + lane;     // X is lower triangular with zeros above: whole rows can be summed
+                s[q] = Tr[0] * pk0;
+                if (r >= 32) s[q] += Tr[32] * pk1;
+                if (r >= 64) s[q] += Tr[64] * pk2;
+                if (r >= 96) s[q] += Tr[96] * pk3;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
             if (lane == 0) {
-                zb[j * TILE + r] = s;
-                svec[r] = s * s;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = warp + (rr + q) * (NTHREADS / 32);
+                    zb[j * TILE + r] = s[q];
+                    svec[r] = s[q] * s[q];
+                }
             }
         }
         __syncthreads();
@@ -555,6 +598,7 @@ __device__ __forceinline__ void diag_finish(double (&acc)[4][8][2], double* smem
             }
         }
     }
+    DIAG_STAMP(8);
 }
 
 template <bool GEN>
@@ -571,6 +615,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     __shared__ double svec[TILE];
     __shared__ int s_fail;
     const int b = blockIdx.x;
+    DIAG_STAMP(0);
     double* Lb = L + (long long)b * npad * npad;
     double* zb = y ? z + (long long)b * npad : nullptr;
 
@@ -583,6 +628,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
     Seg s0{Arow, npad, Arow, npad, j > 0 ? TILE / KC : 0};
     Seg s1{nullptr, 0, nullptr, 0, 0};
     mainloop<true, XPF_POTRF>(acc, s0, s1, smem, hook, pipe);
+    DIAG_STAMP(1);
     const bool have_part = j >= 2;
     const double* dpart = Lb + ((long long)(j - 1) * TILE) * npad + (long long)j * TILE;  // upper block (j-1, j)
     hook.reduce_to(svec, (have_part && zb) ? zb + (long long)j * TILE : nullptr);
@@ -594,6 +640,7 @@ potrf_diag_kernel(double* __restrict__ L, int npad, int n, int j, const double* 
         __syncthreads();
         if (threadIdx.x == 0) st_release_gpu(done_flag + b, j + 1);
     }
+    DIAG_STAMP(9);
 }
 
 // grid.x = (nt-1-j) row tiles, plus one look-ahead CTA per expert when lookahead != 0 (j >= 1, j+1 < nt):

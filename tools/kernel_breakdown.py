@@ -3,6 +3,7 @@ ones launched through the C-ABI).  Shares, not benchmark numbers: the profiler a
 
     python tools/kernel_breakdown.py fit1 [n=16384] [panel=1024] [slices=7]     one matrix, emulated factorisation vs FP64
     python tools/kernel_breakdown.py predict [experts=16] [slices=6]            shared-block GRBCM prediction, emulated
+    python tools/kernel_breakdown.py timeline [n=4096] [first=1500] [count=40]  start / duration of consecutive kernels of engine.fit, B=1
 """
 import json
 import math
@@ -46,6 +47,24 @@ def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "fit1"
     nums = [int(a) for a in sys.argv[2:]]
     g = torch.Generator().manual_seed(0)
+    if what == "timeline":
+        n = nums[0] if nums else 4096
+        first = nums[1] if len(nums) > 1 else 1500
+        count = nums[2] if len(nums) > 2 else 40
+        d = 8
+        x = torch.rand(1, n, d, generator=g, dtype=torch.float64).cuda()
+        y = (torch.sin(x.sum(-1)) + 0.1 * torch.randn(1, n, generator=g, dtype=torch.float64).cuda())
+        hp = hp_well(1, d)
+        eng.fit(x, y, hp, True); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            eng.fit(x, y, hp, True); torch.cuda.synchronize()
+        evs = sorted((ev for ev in prof.events() if ev.device_type.name == "CUDA"), key=lambda ev: ev.time_range.start)
+        t0 = evs[0].time_range.start
+        sel = [ev for ev in evs if ev.time_range.start - t0 >= first][:count]
+        for ev in sel:
+            print("%9.1f us  +%7.1f us  %s" % (ev.time_range.start - t0, ev.time_range.end - ev.time_range.start,
+                                              ev.name.split("(")[0].replace("void ", "")[:60]), flush=True)
+        return
     if what == "fit1":
         n = nums[0] if nums else 16384
         panel = nums[1] if len(nums) > 1 else 1024

@@ -9,7 +9,6 @@
 
 #include <vector>
 
-#define DT_PROFILE 1
 #include "gpr_core.cuh"
 #include "gpr_diag_tile.cuh"
 
@@ -52,6 +51,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tile_kernel(const double* __restr
         cyc[0] = t1 - t0;
         cyc[1] = t2 - t1;
         *fail_out = s_fail;
+    }
+}
+
+// the two single-warp phases in isolation (4 panels back to back, no updates in between: timing only)
+__global__ void __launch_bounds__(NTHREADS, 1) phase_kernel(const double* __restrict__ A, long long* __restrict__ cyc) {
+    extern __shared__ double smem[];
+    double* T = smem;
+    double* S = smem + TILE * XLD;
+    for (int id = threadIdx.x; id < TILE * TILE; id += NTHREADS) T[(id >> 7) * XLD + (id & 127)] = A[id];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int f = 0;
+        const long long t0 = clock64();
+        for (int p = 0; p < 4; ++p) f += chol32_warp(T, 32 * p, S + DT_LT, S + DT_DINV + 32 * p);
+        const long long t1 = clock64();
+        for (int p = 0; p < 4; ++p) inv32_warp(S + DT_LT, S + DT_DINV + 32 * p, S + DT_XD + p * DT_NB * XD_LD);
+        const long long t2 = clock64();
+        if (threadIdx.x == 0) {
+            cyc[0] = t1 - t0;
+            cyc[1] = t2 - t1;
+            cyc[2] = f;
+        }
     }
 }
 
@@ -112,13 +133,6 @@ static void run(const char* name, const std::vector<double>& A, const std::vecto
     printf("{\"variant\": \"%s\", \"potf2_clocks\": %lld, \"trtri_clocks\": %lld, \"kernel_us\": %.2f, \"rel_err_L\": %.3e, \"rel_err_X\": %.3e, "
            "\"max_upper_X\": %.1e, \"fail\": %d, \"status\": \"%s\"}\n",
            name, c[0], c[1], ms * 1e3, eL / mL, eX / mX, upper, fail == (1 << 30) ? 0 : fail, cudaGetErrorString(e));
-    if (VARIANT == 1) {
-        long long st[4][5];
-        cudaMemcpyFromSymbol(st, g_dt_stamps, sizeof(st));
-        for (int p = 0; p < 4; ++p)
-            printf("{\"panel\": %d, \"chol32\": %lld, \"inv32\": %lld, \"panel_solve\": %lld, \"trailing\": %lld}\n", p, st[p][1] - st[p][0],
-                   st[p][2] - st[p][1], p < 3 ? st[p][3] - st[p][2] : 0, p < 3 ? st[p][4] - st[p][3] : 0);
-    }
     cudaFree(dA); cudaFree(dL); cudaFree(dX); cudaFree(dc); cudaFree(df);
 }
 
@@ -138,6 +152,19 @@ int main() {
             A[i * n + j] = exp(-s) + (i == j ? 0.09 + 1e-7 : 0.0);
         }
     host_chol(A, Lh, Xh);
+    {
+        double* dA;
+        long long* dc;
+        cudaMalloc(&dA, TILE * TILE * 8); cudaMalloc(&dc, 24);
+        cudaMemcpy(dA, A.data(), TILE * TILE * 8, cudaMemcpyHostToDevice);
+        const int smem = (TILE * XLD + BM_DOUBLES) * 8;
+        cudaFuncSetAttribute(phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int it = 0; it < 2; ++it) phase_kernel<<<1, NTHREADS, smem>>>(dA, dc);
+        long long c[3];
+        cudaMemcpy(c, dc, 24, cudaMemcpyDeviceToHost);
+        printf("{\"phase\": \"single-warp phases, 4 panels\", \"chol32_x4_clocks\": %lld, \"inv32_x4_clocks\": %lld}\n", c[0], c[1]);
+        cudaFree(dA); cudaFree(dc);
+    }
     run<0>("blocks8 (old)", A, Lh, Xh);
     run<1>("warp32 + dmma (new)", A, Lh, Xh);
     // a non-positive-definite tile: the first bad pivot must be reported by both
