@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 5
+#define GPR_ABI_VERSION 6
 
 typedef enum {
     GPR_OK = 0,
@@ -83,6 +83,22 @@ int gpr_se_build(const double* a, const double* nrm, const double* hp, int hp_st
  */
 int gpr_se_cross(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
                  const double* hp, int hp_stride, int B, int m, int n, int dpad, double* Ks, void* stream);
+/* The same with an explicit leading dimension / batch stride of Ks (ld >= n, bstride >= m * ld): the emulated prediction writes
+ * K* with rows padded to whole k-blocks of the digit-plane split (the padding columns are the caller's, kept zero). */
+int gpr_se_cross_ld(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
+                    const double* hp, int hp_stride, int B, int m, int n, int dpad, double* Ks, long long ld, long long bstride,
+                    void* stream);
+/*
+ * K* written straight as the digit planes of gpr_ozaki_split(Ks, bound = sig^2) — bit for bit the planes / scales that
+ * gpr_se_cross_ld followed by gpr_ozaki_split(bound) produce, without the FP64 round trip through HBM (covar.py:151-160 feeding
+ * gpr.py:100 on the emulated path).  Every row tile whole: the test points come padded to mpad rows.
+ *   planes [slices][B * mpad][npad] int8 (columns n .. npad zero), scale [B * mpad];  bound >= max |K*| (sig^2 of the experts)
+ * gpr_se_cross_planes_ok: 1 when the shared-memory staging fits for this input width / plane count.
+ */
+int gpr_se_cross_planes_ok(int dpad, int slices);
+int gpr_se_cross_planes(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
+                        const double* hp, int hp_stride, int B, int n, int dpad, int slices, double bound, void* planes,
+                        double* scale, void* stream);
 
 /*
  * dK[b,0] = 2 K_se/sig ; dK[b,1+k] = -2 ls_k (x_ik - x_jk)^2 K_se      (covar.py:169-206)

@@ -33,6 +33,9 @@ class Options:
     # (0 = off, the FP64 DMMA path; 6 = FP64 grade, ~1e-11 on V; 3-4 = the FP32-grade mode).  engine.predict_shared_emulated
     emulate_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64", "0"))
     emulate_chunk: int = int(os.environ.get("PYGPR_EMULATE_CHUNK", "8"))
+    # below this (padded) order the emulated prediction stays off even when opted in: at n = 1000 its staging costs more than the
+    # product it replaces (config 1: 0.38 vs 0.28 ms); from 2048 up it wins.  Tests set 0 to exercise it on small shapes.
+    emulate_min_order: int = int(os.environ.get("PYGPR_EMULATE_MIN_ORDER", "2048"))
     # opt-in: K^-1 = L^-T L^-1 of the NLML gradient on the INT8 tensor cores with this many digit planes (0 = off; 7 keeps the
     # gradient at ~1e-10 of the FP64 path).  engine.lml_grad_emulated
     emulate_grad_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_GRAD", "0"))
@@ -40,9 +43,10 @@ class Options:
     # emulated-FP64 products between them, with this many digit planes (0 = the plain FP64 blocked trtri).  engine._inverse_factors
     emulate_inverse_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_INVERSE", "0"))
     # opt-in: the factorisation itself as a right-looking blocked Cholesky whose panel solves and trailing updates are emulated-FP64
-    # products (diagonal blocks of `emulate_fit_panel` rows stay FP64), this many digit planes (0 = the FP64 DMMA Cholesky)
+    # products (diagonal blocks of `emulate_fit_panel` rows stay FP64; 0 = 2048 for up to 8 matrices, 1024 beyond), this many digit
+    # planes (0 = the FP64 DMMA Cholesky)
     emulate_fit_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_FIT", "0"))
-    emulate_fit_panel: int = int(os.environ.get("PYGPR_EMULATE_FIT_PANEL", "1024"))
+    emulate_fit_panel: int = int(os.environ.get("PYGPR_EMULATE_FIT_PANEL", "0"))
     emulate_fit_chunk: int = int(os.environ.get("PYGPR_EMULATE_FIT_CHUNK", "32"))
 
 

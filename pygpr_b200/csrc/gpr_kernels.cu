@@ -140,7 +140,7 @@ __device__ __forceinline__ FeatSmem carve_feat(double* base, int dpad) {
     f.nC = f.nR + TILE;
     return f;
 }
-static inline int feat_smem_bytes(int dpad) { return (2 * TILE * feat_sld(dpad) + 2 * TILE) * 8; }
+__host__ __device__ static inline int feat_smem_bytes(int dpad) { return (2 * TILE * feat_sld(dpad) + 2 * TILE) * 8; }
 // dynamic shared memory of a kernel that factorises diagonal tiles: the pipeline stages, overlaid by the 128x128 tile, and
 // behind the tile the larger of the feature tiles (GEN) and the block-major exchange buffer of potf2_blk / trtri_blk
 static inline int diag_smem_bytes(int gen, int dpad) {
@@ -306,6 +306,114 @@ extern "C" int gpr_se_cross(const double* as, const double* nrms, int mpad, cons
     ARG_CHECK(B > 0 && m > 0 && n > 0 && mpad % TILE == 0 && npad % TILE == 0 && mpad >= m && npad >= n && dpad % 4 == 0);
     return launch_se_tile(dim3((n + TILE - 1) / TILE, (m + TILE - 1) / TILE, B), (cudaStream_t)stream, as, nrms, mpad, a, nrm, npad, hp,
                           hp_stride, nullptr, m, n, dpad, Ks, n, (long long)m * n, 1, 0, 0);
+}
+
+extern "C" int gpr_se_cross_ld(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
+                               const double* hp, int hp_stride, int B, int m, int n, int dpad, double* Ks, long long ld, long long bstride,
+                               void* stream) {
+    ARG_CHECK(as && nrms && a && nrm && hp && Ks);
+    ARG_CHECK(B > 0 && m > 0 && n > 0 && mpad % TILE == 0 && npad % TILE == 0 && mpad >= m && npad >= n && dpad % 4 == 0);
+    ARG_CHECK(ld >= n && bstride >= (long long)m * ld);
+    return launch_se_tile(dim3((n + TILE - 1) / TILE, (m + TILE - 1) / TILE, B), (cudaStream_t)stream, as, nrms, mpad, a, nrm, npad, hp,
+                          hp_stride, nullptr, m, n, dpad, Ks, ld, bstride, 1, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K* straight into the digit planes of the emulated-FP64 product (ozaki_gemm.cu): the tile of gpr_se_cross is never written in
+// FP64 and read back by gpr_ozaki_split — every entry is bounded by `bound` (sig^2 for an SE kernel matrix), so the row scale is
+// known before the tile exists and the balanced radix-256 digits (the arithmetic of oz::split_kernel, bit for bit) come out of the
+// epilogue and leave as whole 32-byte sectors.  Columns n .. npad of the planes are written as zeros (padded k-range).
+//   planes [slices][B * mpad][npad] int8, scale [B * mpad]
+// ---------------------------------------------------------------------------------------------
+constexpr int SEP_LD = 48;   // row stride (bytes) of the per-warp transposition buffer: 32 B of digits + pad (rows 12 banks apart)
+__global__ void __launch_bounds__(NTHREADS) se_cross_planes_kernel(const double* __restrict__ aR, const double* __restrict__ nrmR, int mpad,
+                                                                   const double* __restrict__ aC, const double* __restrict__ nrmC, int npad,
+                                                                   const double* __restrict__ hp, int hp_stride, int n, int dpad,
+                                                                   int slices, double mult, double row_scale,
+                                                                   signed char* __restrict__ planes, double* __restrict__ scale) {
+    extern __shared__ double smem[];
+    const int tc = blockIdx.x, tr = blockIdx.y, b = blockIdx.z;
+    FeatSmem f = carve_feat(smem, dpad);
+    load_feat_tile(f.sR, f.sld, aR + ((long long)b * mpad + tr * TILE) * dpad, dpad);
+    load_feat_tile(f.sC, f.sld, aC + ((long long)b * npad + tc * TILE) * dpad, dpad);
+    cp_async_commit();
+    if (threadIdx.x < TILE) {
+        f.nR[threadIdx.x] = nrmR[(long long)b * mpad + tr * TILE + threadIdx.x];
+        f.nC[threadIdx.x] = nrmC[(long long)b * npad + tc * TILE + threadIdx.x];
+        if (tc == 0) scale[(long long)b * mpad + tr * TILE + threadIdx.x] = row_scale;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const double sig = hp[(long long)b * hp_stride];
+    const long long plane_stride = (long long)gridDim.z * mpad * npad;
+    signed char* out = planes + ((long long)b * mpad + tr * TILE) * npad + tc * TILE;
+    // Balanced radix-256 digits without the digit-by-digit carry loop: with J = I + sum_t 128 * 256^t the bytes of J are d_t + 128,
+    // so the digits are the bytes of J ^ 0x80..80 (the representation with d_t in [-128, 127] is unique: the same bytes as
+    // oz::split_kernel's loop).  Byte k (least significant first) belongs to plane slices-1-k.
+    unsigned long long bias = 0ull;
+    for (int t = 0; t < slices; ++t) bias |= 0x80ull << (8 * t);
+    // A warp's fragment covers 32 rows x 64 columns, 8 columns (one ni) at a time.  The digit words of four ni (32 columns = one
+    // 32-byte sector per row and plane) are collected in registers, then plane by plane transposed through a per-warp buffer
+    // [32 rows][48 B] and written as whole sectors (16-bit stores straight from the fragments ran the L2 at four partial-sector
+    // writes per sector: 2.1 ms per 8 experts instead of 0.75 + 1.13 ms for the FP64 tile + gpr_ozaki_split).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+    signed char* wbuf = reinterpret_cast<signed char*>(smem) + ((feat_smem_bytes(dpad) + 15) & ~15) + warp * (32 * SEP_LD);
+    unsigned long long Wb[4][4][2];
+    gen_se_tile<false>(f.sR, f.sC, f.sld, f.nR, f.nC, dpad, sig * sig, [&](int mi, int ni, int e, double kv) {
+        const int c = acc_col(ni, e);
+        const long long I = (tc * TILE + c < n) ? __double2ll_rn(kv * mult) : 0LL;
+        Wb[ni & 3][mi][e] = ((unsigned long long)I + bias) ^ bias;
+        if ((ni & 3) == 3 && mi == 3 && e == 1) {
+            const int row0 = (warp & 3) * 32, col0 = (warp >> 2) * 64 + (ni >> 2) * 32;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                   // byte k of every collected word -> plane slices-1-k
+                if (k < slices) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int m2 = 0; m2 < 4; ++m2) {
+                            const unsigned long long w0 = Wb[q][m2][0], w1 = Wb[q][m2][1];
+                            const unsigned pair = k < 4 ? __byte_perm((unsigned)w0, (unsigned)w1, 0x0040 + 0x11 * k)
+                                                        : __byte_perm((unsigned)(w0 >> 32), (unsigned)(w1 >> 32), 0x0040 + 0x11 * (k - 4));
+                            *reinterpret_cast<unsigned short*>(wbuf + (m2 * 8 + g) * SEP_LD + q * 8 + 2 * t4) = (unsigned short)pair;
+                        }
+                    __syncwarp();
+                    signed char* dst = out + (long long)(slices - 1 - k) * plane_stride + col0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int idx = lane + 32 * h, rr = idx >> 1, half = idx & 1;
+                        *reinterpret_cast<int4*>(dst + (long long)(row0 + rr) * npad + 16 * half) =
+                            *reinterpret_cast<const int4*>(wbuf + rr * SEP_LD + 16 * half);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    });
+}
+
+static inline int se_cross_planes_smem(int dpad, int slices) { (void)slices; return ((feat_smem_bytes(dpad) + 15) & ~15) + (NTHREADS / 32) * 32 * SEP_LD; }
+
+// 1 when the fused builder can run for this input width / plane count (shared memory), else the caller takes gpr_se_cross_ld + gpr_ozaki_split
+extern "C" int gpr_se_cross_planes_ok(int dpad, int slices) {
+    return dpad % 4 == 0 && dpad <= 108 && slices >= 1 && slices <= 8 && se_cross_planes_smem(dpad, slices) <= 226 * 1024;
+}
+
+extern "C" int gpr_se_cross_planes(const double* as, const double* nrms, int mpad, const double* a, const double* nrm, int npad,
+                                   const double* hp, int hp_stride, int B, int n, int dpad, int slices, double bound, void* planes,
+                                   double* scale, void* stream) {
+    ARG_CHECK(as && nrms && a && nrm && hp && planes && scale);
+    ARG_CHECK(B > 0 && n > 0 && mpad % TILE == 0 && npad % TILE == 0 && npad >= n && bound > 0.0 && isfinite(bound));
+    if (!gpr_se_cross_planes_ok(dpad, slices)) return fail(GPR_ERR_UNSUPPORTED, "fused K* digit planes: input width / plane count too large%s (dpad=%lld)", "", dpad);
+    // the row scale of oz::split_kernel for a known bound: |x| 2^-e < 1/4, scale = 2^(e-8), digits of rint(x 2^(8 slices - e))
+    const int e = ilogb(bound) + 3;
+    const int smem_bytes = se_cross_planes_smem(dpad, slices);
+    CUDA_TRY(opt_in_smem(se_cross_planes_kernel, smem_bytes));
+    se_cross_planes_kernel<<<dim3(npad / TILE, mpad / TILE, B), NTHREADS, smem_bytes, (cudaStream_t)stream>>>(
+        as, nrms, mpad, a, nrm, npad, hp, hp_stride, n, dpad, slices, ldexp(1.0, 8 * slices - e), ldexp(1.0, e - 8),
+        static_cast<signed char*>(planes), scale);
+    CUDA_TRY(cudaGetLastError());
+    return GPR_OK;
 }
 
 // Squared Euclidean distances in GEMM form, D[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   (sampler.py:94-100, N3)

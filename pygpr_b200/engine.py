@@ -200,7 +200,7 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     B, n, d = x.shape
     assert hp.shape == (B, d + 1 + int(has_noise)), (hp.shape, B, d, has_noise)
     from .config import options
-    if options.emulate_fit_slices > 0 and can_fit_emulated(n, shared):
+    if options.emulate_fit_slices > 0 and can_fit_emulated(n, shared) and fit_emulated_pays(B, n):
         return fit_emulated(x, y, hp, has_noise, options.emulate_fit_slices, want_alpha, jitter, L_out, shared,
                             options.emulate_fit_panel, options.emulate_fit_chunk)
     npad = round_up(n, TILE)
@@ -256,12 +256,21 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
 
 
 def can_fit_emulated(n: int, shared: Optional[FitState]) -> bool:
-    return n % TILE == 0 and n >= 4 * TILE and (shared is None or (shared.n % TILE == 0 and shared.B == 1 and shared.n < n))
+    """Shapes fit_emulated handles: any order from 512 up (padded to whole 128-row blocks like engine.fit); a shared communication
+    block must itself be a whole number of blocks."""
+    return n >= 4 * TILE and (shared is None or (shared.n % TILE == 0 and shared.B == 1 and shared.n < n))
+
+
+def fit_emulated_pays(B: int, n: int) -> bool:
+    """Where the emulated factorisation beats the FP64 DMMA one (tools/fit_panel_sweep.py, profiles/r02_fit_panel_sweep.jsonl): one
+    matrix from order 8192 up (order 4096: 4.8 vs 4.3 ms — the FP64 chain of diagonal tiles is the bound either way), several
+    matrices from order 4096 up."""
+    return n >= 8192 or (B >= 4 and n >= 4096)
 
 
 def fit_emulated(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, slices: int = 7, want_alpha: bool = True,
                  jitter: float = JITTER, L_out: Optional[torch.Tensor] = None, shared: Optional[FitState] = None,
-                 panel: int = 1024, chunk: int = 32) -> FitState:
+                 panel: int = 0, chunk: int = 32) -> FitState:
     """engine.fit (Exact_GP.update, gpr.py:65-74) with the O(n^3) work on the INT8 tensor cores (opt-in): a
     right-looking blocked Cholesky whose panel solves and trailing updates are emulated-FP64 GEMMs.
 
@@ -277,14 +286,17 @@ def fit_emulated(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: 
     B, n, d = x.shape
     assert hp.shape == (B, d + 1 + int(has_noise)) and can_fit_emulated(n, shared)
     lib = _lib.load()
-    npad, dev = n, x.device
+    npad, dev = round_up(n, TILE), x.device
     nt = npad // TILE
+    if panel <= 0:
+        panel = 2048 if B <= 8 else 1024                   # few matrices: fewer, larger FP64 diagonal blocks (measured, see fit_emulated_pays)
     a, nrm = scale_inputs(x, hp, B, npad)
     dpad = a.shape[2]
     diag_add, prior = split_hp(hp, d, has_noise, jitter)
     L = torch.empty(B, npad, npad, dtype=F64, device=dev) if L_out is None else L_out
     invdiag = torch.empty(B, nt, TILE, TILE, dtype=F64, device=dev)
-    yrem = y.to(F64).clone().contiguous()                      # right-hand side, updated panel by panel
+    yrem = torch.zeros(B, npad, dtype=F64, device=dev)         # right-hand side, updated panel by panel (zero on the identity padding)
+    yrem[:, :n] = y
     z = torch.empty(B, npad, dtype=F64, device=dev)
     logdet_half = torch.zeros(B, dtype=F64, device=dev)
     zz = torch.zeros(B, dtype=F64, device=dev)
@@ -466,7 +478,7 @@ def predict(st: FitState, xs: torch.Tensor, want_var: bool = True, scratch_kind:
     m = xs.shape[0]
     dev = xs.device
     from .config import options
-    if want_var and options.emulate_slices > 0 and can_emulate_plain(st):
+    if want_var and options.emulate_slices > 0 and can_emulate_plain(st) and st.npad >= options.emulate_min_order:
         return predict_emulated(st, xs, options.emulate_slices, options.emulate_chunk, tag="_" + scratch_kind)
     mean = torch.empty(st.B, m, dtype=F64, device=dev)
     var = torch.empty(st.B, m, dtype=F64, device=dev) if want_var else None
@@ -514,7 +526,7 @@ def predict_pair(st_g: FitState, st_l: FitState, xs: torch.Tensor):
     dev = xs.device
     if st_l.shared_from is st_g:
         from .config import options
-        if options.emulate_slices > 0 and can_emulate(st_g, st_l):
+        if options.emulate_slices > 0 and can_emulate(st_g, st_l) and st_l.npad >= options.emulate_min_order:
             return predict_shared_emulated(st_g, st_l, xs, options.emulate_slices, options.emulate_chunk)
         return predict_shared(st_g, st_l, xs)
     main = torch.cuda.current_stream(dev)
@@ -590,7 +602,7 @@ def lml_grad_emulated(st: FitState, slices: int = 7, chunk: int = 8) -> torch.Te
     trtri (in place), then per chunk of experts the rows of U go through gpr_triu_rows -> gpr_ozaki_split, ONE batched
     gpr_ozaki_gemm_nt (a_upper: the zero k-blocks before the diagonal are skipped; c_lower: only the lower tiles) writes K^-1,
     and gpr_grad_from_kinv runs gpr_lml_grad's fused reduction on it (dK never formed).  loss.py:59-128."""
-    assert st.alpha is not None and st.n % TILE == 0
+    assert st.alpha is not None
     ensure_inverse_factors(st.shared_from, st)               # L^-T of every expert, in place (the shared block's is copied)
     dev, B, npad = st.L.device, st.B, st.npad
     P = st.d + 1 + int(st.has_noise)
@@ -620,7 +632,7 @@ def lml_grad(st: FitState) -> torch.Tensor:
     """d NLML / d hp [B, P] from a finished fit (destroys the strict block-upper part of st.L)   loss.py:59-128."""
     assert st.alpha is not None
     from .config import options
-    if options.emulate_grad_slices > 0 and st.n % TILE == 0 and st.npad > TILE and (st.shared_from is None or st.shared_from.n % TILE == 0):
+    if options.emulate_grad_slices > 0 and st.npad > TILE and (st.shared_from is None or st.shared_from.n % TILE == 0):
         return lml_grad_emulated(st, options.emulate_grad_slices, options.emulate_chunk)
     P = st.d + 1 + int(st.has_noise)
     grad = torch.empty(st.B, P, dtype=F64, device=st.L.device)
@@ -986,13 +998,14 @@ def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
 
 
 def can_emulate(st_g: FitState, st_l: FitState) -> bool:
-    """Shapes the emulated-FP64 prediction of a shared-block GRBCM handles: everything a whole number of 128-row blocks."""
-    return (st_l.shared_from is st_g and st_g.B == 1 and st_g.n % TILE == 0 and st_l.n % TILE == 0 and st_l.n > st_g.n)
+    """Shapes the emulated-FP64 prediction of a shared-block GRBCM handles: the shared block a whole number of 128-row blocks (the
+    experts' own rows may be ragged: they are padded like the factor)."""
+    return (st_l.shared_from is st_g and st_g.B == 1 and st_g.n % TILE == 0 and st_l.n > st_g.n)
 
 
 def can_emulate_plain(st) -> bool:
-    """A fused fit (not the dense path) whose order is a whole number of 128-row blocks and whose experts stand alone."""
-    return isinstance(st, FitState) and st.n % TILE == 0 and st.alpha is not None
+    """A fused fit (not the dense path) whose experts stand alone; any order (padded to whole 128-row blocks like the factor)."""
+    return isinstance(st, FitState) and st.alpha is not None
 
 
 def _f64_work(kind: str, numel: int, dev: torch.device) -> torch.Tensor:
@@ -1008,7 +1021,7 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
     hyper-parameter vector when row0 > 0; otherwise each expert's own amplitude bounds its K*.  xs: [m, d], m % 128 == 0."""
     m, dev = xs.shape[0], xs.device
     n, npad, B = st.n, st.npad, st.B
-    nl = n - row0
+    nl = npad - row0                                          # rows of L^-1 used, identity padding included (its K* columns are zero)
     mean = torch.empty(B, m, dtype=F64, device=dev)
     var = torch.empty(B, m, dtype=F64, device=dev)
     cache = getattr(st, "plane_cache", None)
@@ -1021,10 +1034,16 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
     # transient staging, reused by every chunk (stream-ordered): K* and X in FP64, their digit planes, V^T.  (Preparing chunk c+1 on
     # a side stream while the tensor cores work on chunk c was measured and dropped: the GEMM's 222 KB of shared memory per SM
     # leaves no room for the kernel-matrix builder beside it, so the two only time-slice.)
-    Ks = _f64_work("emu_ks" + tag, E * m * n, dev).view(E, m, n)
+    # K* goes straight into its digit planes when the fused builder's staging fits (gpr_se_cross_planes); else FP64 K*, then split
+    fused = bool(_lib.load().gpr_se_cross_planes_ok(st.dpad, slices))
+    Ks = None
+    if not fused:
+        Ks = _f64_work("emu_ks" + tag, E * m * npad, dev).view(E, m, npad)
+        if npad > n:
+            Ks[:, :, n:].zero_()                              # columns of the padding: gpr_se_cross_ld writes the first n of every row
     X = _f64_work("emu_x" + tag, E * nl * npad, dev).view(E, nl, npad)
     V = _f64_work("emu_v" + tag, E * m * nl, dev).view(E, m, nl)
-    bufa = DigitPlanes(E * m, n, slices, _work("emu_pa" + tag, slices * E * m * n, dev), _f64_work("emu_sa" + tag, E * m, dev))
+    bufa = DigitPlanes(E * m, npad, slices, _work("emu_pa" + tag, slices * E * m * npad, dev), _f64_work("emu_sa" + tag, E * m, dev))
     bufb = (DigitPlanes(E * nl, npad, slices, _work("emu_pb" + tag, slices * E * nl * npad, dev), _f64_work("emu_sb" + tag, E * nl, dev))
             if cache is None else None)
     for e0 in range(0, B, E):
@@ -1032,10 +1051,17 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
         ne = e1 - e0
         # scaled test points of the chunk's experts (per-expert length scales), K* [ne, m, n] (covar.py:151-160), its digit planes
         as_e, nrms_e = scale_inputs(xs, st.hp[e0:e1], ne, m)
-        _lib.call("gpr_se_cross", _p(as_e), _p(nrms_e), m, _p(st.a[e0:e1]), _p(st.nrm[e0:e1]), npad, _p(st.hp[e0:e1]),
-                  st.hp.shape[-1], ne, m, n, st.dpad, _p(Ks), _stream())
-        _count(1)
-        pa = ozaki_split(Ks[:ne].reshape(ne * m, n), slices, bound=sig2, out=bufa)
+        if fused:
+            pa = DigitPlanes(ne * m, npad, slices, bufa.planes.view(-1)[: slices * ne * m * npad].view(slices, ne * m, npad),
+                             bufa.scale[: ne * m])
+            _lib.call("gpr_se_cross_planes", _p(as_e), _p(nrms_e), m, _p(st.a[e0:e1]), _p(st.nrm[e0:e1]), npad, _p(st.hp[e0:e1]),
+                      st.hp.shape[-1], ne, n, st.dpad, slices, sig2, _p(pa.planes), _p(pa.scale), _stream())
+            _count(1)
+        else:
+            _lib.call("gpr_se_cross_ld", _p(as_e), _p(nrms_e), m, _p(st.a[e0:e1]), _p(st.nrm[e0:e1]), npad, _p(st.hp[e0:e1]),
+                      st.hp.shape[-1], ne, m, n, st.dpad, _p(Ks), npad, m * npad, _stream())
+            _count(1)
+            pa = ozaki_split(Ks[:ne].reshape(ne * m, npad), slices, bound=sig2, out=bufa)
         pb = cache.get((e0, e1)) if cache is not None else None
         if pb is None:
             _lib.call("gpr_tril_inverse_rows", _p(st.L[e0:e1]), _p(st.invdiag[e0:e1]), ne, npad, row0, _p(X), _stream())

@@ -127,7 +127,8 @@ class GRBCM(GPR):
         if self._shares_hyperparameters():
             # one hyper-parameter vector for the whole committee: the local experts' factors start with the communication
             # expert's (gr_bcm.py:19-26 puts its training set first in every expert), so it is fitted first and reused
-            if g.need_upd and options.fused_fit and options.emulate_fit_slices <= 0:
+            emulated = options.emulate_fit_slices > 0 and engine.fit_emulated_pays(l.x.shape[0] if l.x.dim() == 3 else 1, l.x.shape[-2])
+            if g.need_upd and options.fused_fit and not emulated:
                 self._fused_update()                         # both factorisations in one launch
             else:
                 if g.need_upd:

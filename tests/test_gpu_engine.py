@@ -351,12 +351,12 @@ def test_inverse_factors_assembled_from_segments(eng, orc, monkeypatch, shared):
         assert_close(var[:2].cpu().numpy(), var_o.numpy(), TOL, "var")
 
 
-@pytest.mark.parametrize("shared", [False, True])
-def test_fit_emulated_matches_fp64_fit(eng, orc, monkeypatch, shared):
+@pytest.mark.parametrize("shared,n", [(False, 1024), (True, 1024), (False, 1100), (True, 900)])
+def test_fit_emulated_matches_fp64_fit(eng, orc, monkeypatch, shared, n):
     """Opt-in factorisation with emulated-FP64 panel solves and trailing updates (engine.fit_emulated, 7 digit planes, several panels
     and expert chunks) against the FP64 DMMA Cholesky and the oracle: factor, forward / backward solve, NLML; non-PD reporting."""
     from pygpr_b200 import config
-    B, n, d = 5, 1024, 6
+    B, d = 5, 6
     x, y, xs, hp = _data(37, B, n, d, 64)
     hp = hp[:1].expand(B, -1).contiguous()
     st_g0 = st_g1 = None
@@ -369,12 +369,13 @@ def test_fit_emulated_matches_fp64_fit(eng, orc, monkeypatch, shared):
     torch.cuda.synchronize()
     assert int(st1.info.abs().sum()) == 0
     assert_close(torch.tril(st1.L[:, :n, :n]).cpu().numpy(), torch.tril(st0.L[:, :n, :n]).cpu().numpy(), 1e-10, "L: emulated == FP64")
-    assert_close(st1.z.cpu().numpy(), st0.z.cpu().numpy(), 1e-10, "z")
-    assert_close(st1.alpha.cpu().numpy(), st0.alpha.cpu().numpy(), 1e-9, "alpha")
+    assert_close(st1.z[:, :n].cpu().numpy(), st0.z[:, :n].cpu().numpy(), 1e-10, "z")
+    assert float(st1.z[:, n:].abs().sum()) == 0.0 and st1.npad == st0.npad
+    assert_close(st1.alpha[:, :n].cpu().numpy(), st0.alpha[:, :n].cpu().numpy(), 1e-9, "alpha")
     assert_close(st1.nlml().cpu().numpy(), st0.nlml().cpu().numpy(), 1e-11, "nlml")
     L_ref, alpha_ref = orc.gp_fit(SPEC, hp[:2], x[:2], y[:2])
-    assert_close(torch.tril(st1.L[:2]).cpu().numpy(), L_ref.numpy(), 1e-9, "L vs oracle")
-    assert_close(st1.alpha[:2].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha vs oracle")
+    assert_close(torch.tril(st1.L[:2, :n, :n]).cpu().numpy(), L_ref.numpy(), 1e-9, "L vs oracle")
+    assert_close(st1.alpha[:2, :n].cpu().numpy(), alpha_ref.numpy(), TOL, "alpha vs oracle")
     assert_close(st1.nlml()[:2].cpu().numpy(), orc.mle_loss(SPEC, hp[:2], x[:2], y[:2]).numpy(), TOL, "nlml vs oracle")
     mean, var = eng.predict(st1, xs.cuda(), True) if not shared else eng.predict_pair(st_g1, st1, xs.cuda())[1]
     mean0, var0 = eng.predict(st0, xs.cuda(), True) if not shared else eng.predict_pair(st_g0, st0, xs.cuda())[1]
@@ -387,3 +388,30 @@ def test_fit_emulated_matches_fp64_fit(eng, orc, monkeypatch, shared):
         st_ref = eng.fit(xb.cuda(), y.cuda(), hpb.cuda(), True, jitter=-1e-3)
         torch.cuda.synchronize()
         assert int(stb.info[3]) > 0 and [int(v) for v in stb.info.cpu()] == [int(v) for v in st_ref.info.cpu()]
+
+
+@pytest.mark.parametrize("B,n,d,m,slices", [(2, 300, 5, 256, 6), (1, 512, 16, 128, 7), (3, 200, 30, 128, 4)])
+def test_fused_cross_kernel_digit_planes_bit_exact(eng, B, n, d, m, slices):
+    """gpr_se_cross_planes (K* generated straight into its digit planes) gives bit for bit the planes and scales of the two-step
+    form gpr_se_cross_ld -> gpr_ozaki_split(bound = sig^2), zeros in the padded k-range included (covar.py:151-160 on the emulated
+    prediction path)."""
+    from pygpr_b200 import _lib
+    x, y, xs, hp = _data(53, B, n, d, m, per_expert=True)
+    npad = eng.round_up(n, 128)
+    hp_d = hp.cuda()
+    a, nrm = eng.scale_inputs(x.cuda(), hp_d, B, npad)
+    as_, nrms = eng.scale_inputs(xs.cuda(), hp_d, B, m)
+    dpad = a.shape[2]
+    assert _lib.load().gpr_se_cross_planes_ok(dpad, slices) == 1
+    bound = float((hp[:, 0] * hp[:, 0]).max())
+    Ks = torch.zeros(B, m, npad, dtype=torch.float64, device="cuda")
+    _lib.call("gpr_se_cross_ld", eng._p(as_), eng._p(nrms), m, eng._p(a), eng._p(nrm), npad, eng._p(hp_d), hp_d.shape[-1], B, m, n, dpad,
+              eng._p(Ks), npad, m * npad, eng._stream())
+    two = eng.ozaki_split(Ks.view(B * m, npad), slices, bound=bound)
+    planes = torch.full((slices, B * m, npad), 77, dtype=torch.int8, device="cuda")
+    scale = torch.full((B * m,), -1.0, dtype=torch.float64, device="cuda")
+    _lib.call("gpr_se_cross_planes", eng._p(as_), eng._p(nrms), m, eng._p(a), eng._p(nrm), npad, eng._p(hp_d), hp_d.shape[-1], B, n, dpad,
+              slices, bound, eng._p(planes), eng._p(scale), eng._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(planes, two.planes) and torch.equal(scale, two.scale)
+    assert int(planes[:, :, n:].abs().sum()) == 0 and int(planes.abs().sum()) > 0

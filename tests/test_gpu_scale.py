@@ -193,6 +193,7 @@ def test_benchmarked_grbcm_path_against_oracle(monkeypatch):
     assert_close(stg.nlml().cpu().numpy(), orc.mle_loss(["se", "wn"], hp[:1], xall[:1], yall[:1]).numpy(), TOL, "NLML of the communication expert")
     # the opt-in emulated-FP64 prediction at the same sizes (6 digit planes on the INT8 tcgen05 tensor cores) against the oracle
     monkeypatch.setattr(config.options, "emulate_slices", 6)
+    monkeypatch.setattr(config.options, "emulate_min_order", 0)
     (mg_e, vg_e), (ml_e, vl_e) = eng.predict_pair(stg, st, xs.cuda())
     monkeypatch.setattr(config.options, "emulate_slices", 0)
     assert_close(mg_e[0].cpu().numpy(), parts["mean_g"].numpy(), TOL, "communication expert mean (emulated)")

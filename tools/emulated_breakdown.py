@@ -56,12 +56,16 @@ out = {"experts_per_chunk": E, "slices": S}
 out["se_cross_ms"] = timed(lambda: _lib.call("gpr_se_cross", _p(as_e), _p(nrms_e), m, _p(st_l.a[:E]), _p(st_l.nrm[:E]), npad, _p(st_l.hp[:E]),
                                               st_l.hp.shape[-1], E, m, n, st_l.dpad, _p(Ks), _s()))
 out["split_Ks_ms"] = timed(lambda: eng.ozaki_split(Ks.reshape(E * m, n), S))
+pf = torch.empty(S, E * m, npad, dtype=torch.int8, device="cuda"); sf = torch.empty(E * m, dtype=torch.float64, device="cuda")
+out["fused_cross_planes_ms (replaces the two above)"] = timed(lambda: _lib.call(
+    "gpr_se_cross_planes", _p(as_e), _p(nrms_e), m, _p(st_l.a[:E]), _p(st_l.nrm[:E]), npad, _p(st_l.hp[:E]), st_l.hp.shape[-1], E, n,
+    st_l.dpad, S, 1.0, _p(pf), _p(sf), _s()))
 out["inverse_rows_ms"] = timed(lambda: _lib.call("gpr_tril_inverse_rows", _p(st_l.L[:E]), _p(st_l.invdiag[:E]), E, npad, ng, _p(X), _s()))
 out["split_X_ms"] = timed(lambda: eng.ozaki_split(X.reshape(E * nl, npad), S))
 pa, pb = eng.ozaki_split(Ks.reshape(E * m, n), S), eng.ozaki_split(X.reshape(E * nl, npad), S)
 out["gemm_ms"] = timed(lambda: eng.ozaki_gemm_nt(pa, pb, out=V, b_lower=ng, batch=E))
 out["reduce_ms"] = timed(lambda: _lib.call("gpr_vt_reduce", _p(V), nl, _p(st_l.z[:E, ng:]), st_l.z.stride(0), _p(mg), _p(vg), E, m, nl, _p(ml), _p(vl), _s()))
-out["sum_ms"] = sum(v for k, v in out.items() if k.endswith("_ms"))
+out["sum_ms"] = sum(v for k, v in out.items() if k.endswith("_ms") and k not in ("se_cross_ms", "split_Ks_ms"))
 out["per_expert_ms"] = out["sum_ms"] / E
 flops = E * (float(n) ** 2 - float(ng) ** 2) * m
 out["gemm_tflops_equiv"] = flops / out["gemm_ms"] * 1e-9
