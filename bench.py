@@ -21,6 +21,7 @@ collective is the all-reduce of the [3, M] partial sums (strong scaling: the tot
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -223,6 +224,7 @@ def run_train(args, P, eng, world, rank, dev, barrier, max_over_ranks, peak_tf):
     assert math.isfinite(f) and bool(torch.isfinite(torch.from_numpy(grad)).all()) and abs(f - f_loss) <= 1e-9 * abs(f)
     from pygpr_b200 import config
     del mle
+    gc.collect()
     torch.cuda.empty_cache()                                  # the FP64 evaluation's factor buffer goes back before the next one allocates
     config.options.emulate_grad_slices = 7                    # the same evaluation with L^-T's off-segment blocks and K^-1 on the
     config.options.emulate_inverse_slices = 7                 # INT8 tensor cores (opt-in), and so are the Cholesky's panel solves and
@@ -445,6 +447,9 @@ def main():
         rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
         emu = {"slices": args.emulate, "plane_products": args.emulate * (args.emulate + 1) // 2, "value": m / (emu_ms * 1e-3), "unit": UNIT,
                "ms_per_step": emu_ms, "speedup_vs_fp64_path": step_ms / emu_ms, "prepare_ms_once_per_fit": prep_ms,
+               "inverse_row_planes_cached_chunks": [len([k for k in (getattr(st, "plane_cache", None) or {}) if isinstance(k, tuple)]),
+                                                    -(-nc_loc // config.options.emulate_chunk)],
+               "hbm_free_gb": torch.cuda.mem_get_info(dev)[0] / 1e9,
                "e2e": {"value": m / (emu_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": emu_e2e_ms, "h2d_bytes_per_step": m * d * 8,
                        "d2h_bytes_per_step": 2 * m * 8},
                "tflops_equiv": (nc_loc * (float(n_l) ** 2 - float(n_g) ** 2) + float(n_g) ** 2) * m / emu_ms * 1e-9,

@@ -612,6 +612,13 @@ def lml_grad_emulated(st: FitState, slices: int = 7, chunk: int = 8) -> torch.Te
     held = sum(b.numel() for k, b in _scratch_cache.items() if k[0] == dev.index and str(k[1]).startswith("emg_"))
     free, _ = torch.cuda.mem_get_info(dev)
     E = int(max(1, min(chunk, B, (free + held - (2 << 30)) // per)))
+    cache = getattr(st, "plane_cache", None)
+    if E < min(chunk, B) and cache and len(cache) > 2:
+        # the prediction's cached digit planes (kept while HBM is idle) are in the way of a full chunk: give them back
+        cache.clear()
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info(dev)
+        E = int(max(1, min(chunk, B, (free + held - (2 << 30)) // per)))
     Ud = _f64_work("emg_u", E * npad * npad, dev).view(E, npad, npad)
     Kinv = _f64_work("emg_kinv", E * npad * npad, dev).view(E, npad, npad)
     buf = DigitPlanes(E * npad, npad, slices, _work("emg_p", slices * E * npad * npad, dev), _f64_work("emg_s", E * npad, dev))
@@ -990,11 +997,12 @@ def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
     if st_l.npad > TILE:
         _inverse_factors(st_l, gt)
     st_l.upper_is_inverse = True
-    # keep the digit planes of the inverse rows across predictions when HBM allows (8 planes at most, + the transient chunk buffers)
-    free, _ = torch.cuda.mem_get_info(st_l.L.device)
-    rows = st_l.npad - (st_g.n if st_g is not None else 0)
-    if free > st_l.B * rows * st_l.npad * 8 + (16 << 30):
-        st_l.plane_cache = {}
+    # the digit planes of the inverse rows are kept across predictions for as many expert chunks as the free HBM holds beside the
+    # transient chunk buffers (config 4 on ONE GPU: 137 GB of factors leave room for about a third of the 51 GB of planes)
+    st_l.plane_cache = {}
+
+
+PLANE_CACHE_RESERVE = 12 << 30   # HBM left alone by the plane cache: the transient buffers of later calls (other plane counts, the gradient)
 
 
 def can_emulate(st_g: FitState, st_l: FitState) -> bool:
@@ -1029,6 +1037,7 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
     if cache is not None and cache.get("layout") != (E, slices):
         cache.clear()                                         # planes cached for another chunking / plane count: start over
         cache["layout"] = (E, slices)
+        cache["full"] = False                                 # set once a chunk did not fit: later chunks stay transient
     per_expert_var0 = var0.dim() == 2
     sig2 = float((st.hp[:, 0] * st.hp[:, 0]).max())           # 0 < K* <= sig^2 (covar.py:149): the bound of the digit split
     # transient staging, reused by every chunk (stream-ordered): K* and X in FP64, their digit planes, V^T.  (Preparing chunk c+1 on
@@ -1044,8 +1053,7 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
     X = _f64_work("emu_x" + tag, E * nl * npad, dev).view(E, nl, npad)
     V = _f64_work("emu_v" + tag, E * m * nl, dev).view(E, m, nl)
     bufa = DigitPlanes(E * m, npad, slices, _work("emu_pa" + tag, slices * E * m * npad, dev), _f64_work("emu_sa" + tag, E * m, dev))
-    bufb = (DigitPlanes(E * nl, npad, slices, _work("emu_pb" + tag, slices * E * nl * npad, dev), _f64_work("emu_sb" + tag, E * nl, dev))
-            if cache is None else None)
+    bufb = None                                               # transient planes of X, allocated when a chunk is not (or cannot be) cached
     for e0 in range(0, B, E):
         e1 = min(e0 + E, B)
         ne = e1 - e0
@@ -1066,9 +1074,17 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
         if pb is None:
             _lib.call("gpr_tril_inverse_rows", _p(st.L[e0:e1]), _p(st.invdiag[e0:e1]), ne, npad, row0, _p(X), _stream())
             _count(1)
-            pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices, out=bufb)
-            if cache is not None:
-                cache[(e0, e1)] = pb
+            keep = False
+            if cache is not None and not cache["full"]:
+                free, _ = torch.cuda.mem_get_info(dev)
+                keep = free > 2 * slices * E * nl * npad + (PLANE_CACHE_RESERVE if bufb is None else PLANE_CACHE_RESERVE // 2)
+                cache["full"] = not keep
+            if keep:
+                pb = cache[(e0, e1)] = ozaki_split(X[:ne].reshape(ne * nl, npad), slices)
+            else:
+                if bufb is None:
+                    bufb = DigitPlanes(E * nl, npad, slices, _work("emu_pb" + tag, slices * E * nl * npad, dev), _f64_work("emu_sb" + tag, E * nl, dev))
+                pb = ozaki_split(X[:ne].reshape(ne * nl, npad), slices, out=bufb)
         ozaki_gemm_nt(pa, pb, out=V[:ne], b_lower=row0, batch=ne)
         if per_expert_var0:                                   # independent experts: each has its own prior variance
             for i in range(ne):

@@ -306,11 +306,16 @@ class GRBCM_MLE:
 
     def __init__(self, model: "GRBCM", chunk: int = 0) -> None:
         self.grbcm = model
-        self.model = self                     # optimisers call loss.model.params / set_params
         self.chunk = chunk
         self.loss_value = NotImplemented
         self.grad_value = NotImplemented
         self.params = torch.clone(model.gpg.params)
+
+    @property
+    def model(self):
+        """Optimisers call ``loss.model.params / set_params``: the loss is its own model.  (A property, not ``self.model = self``:
+        the reference cycle kept a dropped instance — and its HBM-sized factor buffer — alive until the next cyclic GC pass.)"""
+        return self
 
     def set_params(self, params) -> None:
         """Write the shared vector into every expert and mark the factorisations stale."""
@@ -326,7 +331,14 @@ class GRBCM_MLE:
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         P = theta.shape[-1]
         acc = np.zeros(1 + P)
-        step = self.chunk if self.chunk > 0 else self._auto_chunk()
+        step = self.chunk
+        if step <= 0:
+            # sized once per instance and mode: a later evaluation sees less free memory (the staging buffers of the first one are
+            # cached) and would pick a different, smaller batch
+            key = (options.emulate_grad_slices > 0, options.emulate_fit_slices > 0)
+            if getattr(self, "_auto", (None, 0))[0] != key:
+                self._auto = (key, self._auto_chunk())
+            step = self._auto[1]
         # the communication expert at theta: its NLML/gradient is added once below, and (one shared vector, tile-aligned
         # communication set) its factor is the leading block of every local expert's factor (engine.fit(shared=...))
         glob = getattr(self, "_glob", None)
@@ -373,11 +385,20 @@ class GRBCM_MLE:
         free, _ = torch.cuda.mem_get_info(engine.device())
         held = self._part._L_buf.numel() * 8 if getattr(self, "_part", None) is not None and self._part._L_buf is not None else 0
         reserve = 6 << 30
-        if options.emulate_grad_slices > 0:                  # staging of the emulated K^-1 products: two experts' worth
-            reserve += 2 * npad * npad * (16 + options.emulate_grad_slices)
-        if options.emulate_fit_slices > 0:                   # digit planes of the emulated factorisation's panels: four experts' worth
-            reserve += 4 * npad * npad * options.emulate_fit_slices
-        return int(max(1, min(g.nc, (free + held - reserve) // per)))
+        # the emulated forms stage FP64 windows and digit planes for a chunk of experts at a time (engine.lml_grad_emulated: rows of
+        # U, their planes, K^-1; engine.fit_emulated: two sets of planes of the widest [below x panel] window): leave room for full
+        # chunks — measured at config 5, 64 experts in one batch with 5-expert staging 3.87 s, 10 per batch 3.48 s
+        if options.emulate_grad_slices > 0:
+            reserve += options.emulate_chunk * npad * npad * (16 + options.emulate_grad_slices)
+        if options.emulate_fit_slices > 0:
+            ngt = (g.ng // engine.TILE) * engine.TILE if options.share else 0
+            reserve += min(options.emulate_fit_chunk, g.nc) * 2 * options.emulate_fit_slices * (npad - ngt) * max(ngt, 1024)
+        fit = int(max(1, min(g.nc, (free + held - reserve) // per)))
+        if options.emulate_grad_slices > 0 or options.emulate_fit_slices > 0:
+            # tools/train_chunk_sweep.py (config 5's share, 64 experts of order 16384): 8 / 12 / 16 / 24 / 32 / 48 experts per batch take
+            # 3.71 / 3.55 / 3.47 / 3.54 / 3.91 / 3.88 s — beyond ~24 the staging of the emulated products no longer gets whole chunks
+            fit = min(fit, 2 * max(options.emulate_chunk, 4))
+        return fit
 
     def loss(self, params):
         self.loss_value, _ = self._eval(params, False)
