@@ -1039,7 +1039,9 @@ def _emulated_experts(st: FitState, xs: torch.Tensor, row0: int, mean0: torch.Te
         cache["layout"] = (E, slices)
         cache["full"] = False                                 # set once a chunk did not fit: later chunks stay transient
     per_expert_var0 = var0.dim() == 2
-    sig2 = float((st.hp[:, 0] * st.hp[:, 0]).max())           # 0 < K* <= sig^2 (covar.py:149): the bound of the digit split
+    sig2 = getattr(st, "sig2_max", None)                      # 0 < K* <= sig^2 (covar.py:149): the bound of the digit split
+    if sig2 is None:                                          # read back once per fit: a device->host sync per prediction would
+        sig2 = st.sig2_max = float((st.hp[:, 0] * st.hp[:, 0]).max())   # keep the host from queueing ahead of the device
     # transient staging, reused by every chunk (stream-ordered): K* and X in FP64, their digit planes, V^T.  (Preparing chunk c+1 on
     # a side stream while the tensor cores work on chunk c was measured and dropped: the GEMM's 222 KB of shared memory per SM
     # leaves no room for the kernel-matrix builder beside it, so the two only time-slice.)
