@@ -252,30 +252,39 @@ class GRBCM(GPR):
 
     def train_batched(self, steps: int = 10, eps: float = 1e-4):
         """B200-native training loop: ALL local experts (and the communication expert) take a quadratic-fit gradient
-        step per iteration, ``theta <- theta - gamma J`` with ``gamma`` from ``get_learn_rate`` (hp_update.py:6-28), i.e. one
-        batched ``loss_and_grad`` + two batched ``loss`` evaluations per step for the whole committee.  Per-expert
-        hyper-parameters need no collective; returns the NLML history [steps, nc]."""
+        step per iteration, ``theta <- theta - gamma J`` with ``gamma`` from the parabola of ``get_learn_rate`` (hp_update.py:14-22),
+        i.e. one batched NLML + gradient and two batched NLML evaluations per step for the whole committee.
+
+        The line search runs on the device: the iterates, the three NLML vectors, slope / curvature / gamma and the masked update
+        are device tensors, the factorisations report failure through their ``info`` vector (no ``check()`` read-back), and nothing
+        crosses PCIe inside the loop — the NLML history comes back once at the end.  Experts whose parabola is not convex
+        (gamma <= 0 or not finite) or whose kernel matrix is not positive definite at a trial point stay where they are.
+        Per-expert hyper-parameters need no collective; returns the NLML history [steps, nc] (numpy)."""
         import numpy as np
         from .loss import MLE
         hist = []
         for model in (self.gpl, self.gpg):
             loss = MLE(model)
+            shape = tuple(model.params.shape)
+            hp = engine._dev(model.params.detach()).to(torch.float64).reshape(-1, shape[-1]).clone()
             for _ in range(steps):
-                theta = model.params.detach().cpu().numpy()
-                f0, J = loss.loss_and_grad(theta)                       # the three evaluations of hp_update.py:14-17
-                f_minus = loss.loss(theta - eps * J)
-                f_plus = loss.loss(theta + eps * J)
-                slope = (f_minus - f_plus) / (2.0 * eps)
-                curv = (f_minus + f_plus - 2 * f0) / (2.0 * eps ** 2)
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    gamma = np.asarray(-0.5 * (slope / curv))           # hp_update.py:22
-                step = gamma[..., None] * J
-                # a non-convex parabola (gamma <= 0 or not finite) gives no usable step: leave that expert where it is
-                ok = np.isfinite(step).all(-1, keepdims=True) & (gamma[..., None] > 0)
-                model.set_params(torch.from_numpy(theta - np.where(ok, step, 0.0)))
+                st = loss._fit(hp, True, check=False)                  # the three evaluations of hp_update.py:14-17
+                f0, good = st.nlml(), st.info == 0
+                J = loss._grad(st)
+                stm = loss._fit(hp - eps * J, False, check=False)
+                f_minus, good = stm.nlml(), good & (stm.info == 0)
+                stp = loss._fit(hp + eps * J, False, check=False)
+                f_plus, good = stp.nlml(), good & (stp.info == 0)
+                slope = (f_minus - f_plus) / (2.0 * eps)               # C1, hp_update.py:19
+                curv = (f_minus + f_plus - 2.0 * f0) / (2.0 * eps ** 2)  # C2, hp_update.py:20
+                gamma = -0.5 * (slope / curv)                          # hp_update.py:22
+                step = gamma[:, None] * J
+                ok = good & torch.isfinite(step).all(-1) & (gamma > 0)
+                hp = hp - torch.where(ok[:, None], step, torch.zeros_like(step))
                 if model is self.gpl:
-                    hist.append(np.array(f0, copy=True))
-        return np.stack(hist) if hist else np.zeros((0, self.nc))
+                    hist.append(f0)
+            model.set_params(_back(hp.reshape(shape), model.params))
+        return torch.stack(hist).cpu().numpy() if hist else np.zeros((0, self.nc))
 
     def gather_weights(self):
         """(beta, prec) for ALL experts [nc_total+1, m] when sharded (all-gather of the local rows)."""

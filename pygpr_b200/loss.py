@@ -63,12 +63,17 @@ class MLE(Loss):
             return st.L
         return None
 
-    def _fit(self, params: ndarray, want_alpha: bool):
+    def _fit(self, params, want_alpha: bool, check: bool = True):
+        """One factorisation at `params` (numpy like the reference's API, or a device tensor: the batched training loop keeps its
+        iterates in HBM).  check=False leaves `info` on the device (no host synchronisation; the caller masks failed experts)."""
         xs, ys = self.model.x, self.model.y
         spec = fused_spec(self.model.cov, xs.shape[-1])
         x = engine._dev(xs).reshape(-1, xs.shape[-2], xs.shape[-1])
         y = engine._dev(ys).reshape(-1, ys.shape[-1])
-        hp = engine._dev(torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)))
+        if isinstance(params, torch.Tensor):
+            hp = engine._dev(params.detach()).to(torch.float64).contiguous()
+        else:
+            hp = engine._dev(torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)))
         self._batched = hp.dim() > 1 or xs.dim() > 2
         hp = hp.reshape(-1, hp.shape[-1])
         B = max(hp.shape[0], x.shape[0])
@@ -89,7 +94,8 @@ class MLE(Loss):
             K = K.reshape(B, n, n).clone()
             K.diagonal(dim1=-2, dim2=-1).add_(engine.JITTER)           # loss.py:38,63,96
             st = engine.fit_dense(K, y, want_alpha=want_alpha)
-            st.check()
+            if check:
+                st.check()
             return st
         shared = getattr(self, "shared_state", None)        # set by GRBCM_MLE: the communication expert fitted at these params
         if shared is not None and not engine.can_share(shared, x.shape[1], x.shape[2], spec[0]):
@@ -98,7 +104,8 @@ class MLE(Loss):
         st = engine.fit(x, y, hp, spec[0], want_alpha=want_alpha, shared=shared, L_out=self._factor_buffer(B, npad, x.device))
         if self._L_buf is None or st.L.numel() > self._L_buf.numel():
             self._L_buf = st.L
-        st.check()                                           # tc.cholesky raises on a non-PD matrix, loss.py:39
+        if check:
+            st.check()                                       # tc.cholesky raises on a non-PD matrix, loss.py:39
         return st
 
     def _grad(self, st) -> torch.Tensor:
