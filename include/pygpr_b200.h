@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 6
+#define GPR_ABI_VERSION 7
 
 typedef enum {
     GPR_OK = 0,
@@ -390,6 +390,21 @@ int gpr_grad_from_kinv(const double* Kinv, int ldk, const double* a, const doubl
  * behind a finished block column (z = L^-1 y, gpr.py:70-72) in the panel-wise factorisation of engine.fit_emulated.  HBM bound. */
 int gpr_gemv_sub(const double* A, long long lda, long long a_batch_stride, int B, int rows, int kdim, const double* z,
                  long long z_stride, double* y, long long y_stride, void* stream);
+
+/*
+ * Communicator — for consumers without torch.distributed: the two collectives of the path, all-reduce(sum, f64) of the
+ * [3, m] partial sums of GRBCM.aggregate (gr_bcm.py:133,143-144; grbcm_partial -> HERE -> grbcm_finalize) and of the [1+P] NLML /
+ * gradient scalars of a shared-vector training step.  Thin wrappers over NCCL, bound at run time (dlopen "libnccl.so.2"):
+ * GPR_ERR_UNSUPPORTED where NCCL is absent, every other entry point is unaffected.
+ *   gpr_comm_unique_id        rank 0 fills id[gpr_comm_unique_id_bytes()] (128) and hands it to the other ranks by its own means
+ *   gpr_comm_init             collective; each rank on its own current CUDA device
+ *   gpr_comm_allreduce_f64    in place on a device buffer, ordered on `stream`
+ */
+int gpr_comm_unique_id_bytes(void);
+int gpr_comm_unique_id(void* id);
+int gpr_comm_init(void** comm, int world, int rank, const void* id);
+int gpr_comm_allreduce_f64(void* comm, double* buf, long long count, void* stream);
+int gpr_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

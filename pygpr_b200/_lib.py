@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygpr_b200.so")
 
 TILE = 128
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # name -> (restype, argtypes).  Pointers are passed as integers (tensor.data_ptr()).
 _P, _I, _LL = c_void_p, c_int, c_longlong
@@ -36,6 +36,11 @@ SIGNATURES = {
     "gpr_se_cross": (c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "gpr_se_cross_ld": (c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _LL, _LL, _P]),
     "gpr_se_cross_planes_ok": (c_int, [_I, _I]),
+    "gpr_comm_unique_id_bytes": (c_int, []),
+    "gpr_comm_unique_id": (c_int, [_P]),
+    "gpr_comm_init": (c_int, [_P, _I, _I, _P]),
+    "gpr_comm_allreduce_f64": (c_int, [_P, _P, _LL, _P]),
+    "gpr_comm_destroy": (c_int, [_P]),
     "gpr_se_cross_planes": (c_int, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, c_double, _P, _P, _P]),
     "gpr_se_kernel_grad": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gpr_potrf_batched": (c_int, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -29,6 +29,8 @@ class Options:
     fused_fit: bool = os.environ.get("PYGPR_GRBCM_FUSED_FIT", "1") != "0"
     predict_chunk: int = int(os.environ.get("PYGPR_PREDICT_CHUNK", "16384"))
     predict_form: str = os.environ.get("PYGPR_PREDICT_FORM", "auto")
+    # the data-path all-reduces: "torch" = torch.distributed (NCCL), "cabi" = the library's own NCCL wrapper (gpr_comm_*)
+    comm: str = os.environ.get("PYGPR_COMM", "torch")
     # opt-in: the local experts' prediction products on the INT8 tensor cores with this many digit planes per operand
     # (0 = off, the FP64 DMMA path; 6 = FP64 grade, ~1e-11 on V; 3-4 = the FP32-grade mode).  engine.predict_shared_emulated
     emulate_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64", "0"))

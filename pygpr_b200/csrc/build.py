@@ -7,12 +7,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libpygpr_b200.so")
-SOURCES = [os.path.join(HERE, "gpr_kernels.cu"), os.path.join(HERE, "ozaki_gemm.cu")]
+SOURCES = [os.path.join(HERE, "gpr_kernels.cu"), os.path.join(HERE, "ozaki_gemm.cu"), os.path.join(HERE, "gpr_comm.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "gpr_core.cuh"), os.path.join(HERE, "gpr_diag_tile.cuh"), os.path.join(ROOT, "include", "pygpr_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+    "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-ldl",
 ]
 
 

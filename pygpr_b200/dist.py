@@ -33,10 +33,49 @@ def shard_bounds(nc: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+_cabi_comm = None   # (handle, world) of the library's own NCCL communicator, created on first use when options.comm == "cabi"
+
+
+def cabi_comm():
+    """The C ABI's communicator over the default process group (gpr_comm_init): rank 0's NCCL id travels through torch.distributed
+    once, after that the all-reduces go through gpr_comm_allreduce_f64 — the path a consumer without torch would use."""
+    global _cabi_comm
+    if _cabi_comm is None:
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        rank, ws = dist.get_rank(), dist.get_world_size()
+        nbytes = int(lib.gpr_comm_unique_id_bytes())
+        buf = (ctypes.c_char * nbytes)()
+        if rank == 0:
+            _lib.call("gpr_comm_unique_id", ctypes.cast(buf, ctypes.c_void_p))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=0)
+        buf = (ctypes.c_char * nbytes).from_buffer_copy(box[0])
+        handle = ctypes.c_void_p()
+        _lib.call("gpr_comm_init", ctypes.cast(ctypes.byref(handle), ctypes.c_void_p), ws, rank, ctypes.cast(buf, ctypes.c_void_p))
+        _cabi_comm = (handle, ws)
+    return _cabi_comm[0]
+
+
+def cabi_comm_destroy() -> None:
+    global _cabi_comm
+    if _cabi_comm is not None:
+        from . import _lib
+        _lib.call("gpr_comm_destroy", _cabi_comm[0])
+        _cabi_comm = None
+
+
 def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place sum over ranks (no-op for a single process)."""
+    """In-place sum over ranks (no-op for a single process).  options.comm == "cabi" routes float64 CUDA tensors on the default
+    group through the library's own NCCL wrapper (gpr_comm_allreduce_f64) instead of torch.distributed."""
     if is_dist() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        from .config import options
+        if options.comm == "cabi" and group is None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous():
+            from . import _lib
+            _lib.call("gpr_comm_allreduce_f64", cabi_comm(), t.data_ptr(), t.numel(), torch.cuda.current_stream(t.device).cuda_stream)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
 

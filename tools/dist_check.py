@@ -54,6 +54,21 @@ def main():
         worst = max(worst, max(errs.values()))
         print("rank %d/%d nc=%d experts [%d,%d) shared_block=%s: %s" % (rank, world, nc, lo, hi,
               sharded.gpl._state.shared_from is not None, {k: "%.1e" % v for k, v in errs.items()}), flush=True)
+    # the C ABI's own communicator (gpr_comm_*): same sums as torch.distributed, and a sharded prediction routed through it
+    from pygpr_b200 import config, dist as gdist
+    a = torch.rand(3, 1000, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(rank))
+    b = a.clone()
+    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    config.options.comm = "cabi"
+    gdist.all_reduce_sum_(a)
+    torch.cuda.synchronize()
+    errs = {"cabi_allreduce": float((a - b).abs().max())}
+    mu_c, var_c = sharded.predict(xs, var="diag")                  # last case above, [3, m] sums through gpr_comm_allreduce_f64
+    errs["cabi_predict"] = max(float((mu_c - mu).abs().max()), float((var_c - var).abs().max()))
+    config.options.comm = "torch"
+    gdist.cabi_comm_destroy()
+    worst = max(worst, max(errs.values()))
+    print("rank %d/%d C-ABI communicator: %s" % (rank, world, {k: "%.1e" % v for k, v in errs.items()}), flush=True)
     t = torch.tensor([worst], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = float(t[0]) < 1e-10
