@@ -60,3 +60,18 @@ def test_engine_refuses_without_gpu():
     from pygpr_b200 import engine
     with pytest.raises(RuntimeError):
         engine.device()
+
+
+def test_comm_entry_points_without_a_gpu():
+    """gpr_comm_*: exported, argument errors are reported before NCCL is touched (no compute, no GPU)."""
+    import pytest
+    from pygpr_b200 import _lib
+    lib = _lib.load()
+    assert lib.gpr_comm_unique_id_bytes() == 128
+    with pytest.raises(_lib.GprError):
+        _lib.call("gpr_comm_unique_id", None)
+    with pytest.raises(_lib.GprError):
+        _lib.call("gpr_comm_init", None, 2, 0, None)
+    with pytest.raises(_lib.GprError):
+        _lib.call("gpr_comm_allreduce_f64", None, None, 0, None)
+    _lib.call("gpr_comm_destroy", None)           # destroying nothing is not an error
