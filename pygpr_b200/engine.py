@@ -1002,7 +1002,7 @@ def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
     st_l.plane_cache = {}
 
 
-PLANE_CACHE_RESERVE = 12 << 30   # HBM left alone by the plane cache: the transient buffers of later calls (other plane counts, the gradient)
+PLANE_CACHE_RESERVE = 6 << 30    # HBM left alone by the plane cache: transient buffers of later calls (lml_grad_emulated takes the cache back if it needs more)
 
 
 def can_emulate(st_g: FitState, st_l: FitState) -> bool:
