@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define GPR_TILE 128
-#define GPR_ABI_VERSION 7
+#define GPR_ABI_VERSION 8
 
 typedef enum {
     GPR_OK = 0,
@@ -352,6 +352,14 @@ int gpr_ozaki_split(const double* X, long long ld, int rows, int k, int slices, 
 int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                       int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch, long long c_batch_stride,
                       int a_upper, int c_lower, double alpha, int b_shared, void* stream);
+/* The same on a WINDOW of rows of each operand: every batch entry of A occupies a_rows_total (padded) rows of planesA / scaleA and the
+ * product uses the M rows starting a_row_off rows in (likewise B) — a block-row range of an operand that was split once, e.g. the parts
+ * of a Cholesky panel that update the next panel's columns and the rest of the trailing matrix separately (engine.fit_emulated).
+ * Offsets are multiples of 64 rows; a_rows_total / b_rows_total = 0 means the whole operand (gpr_ozaki_gemm_nt). */
+int gpr_ozaki_gemm_nt_window(const void* planesA, const double* scaleA, int M, int a_rows_total, int a_row_off, const void* planesB,
+                             const double* scaleB, int N, int b_rows_total, int b_row_off, int K, int slices, int b_lower, double beta,
+                             double* C, long long ldc, int batch, long long c_batch_stride, int a_upper, int c_lower, double alpha,
+                             int b_shared, void* stream);
 
 /* pieces of the emulated-FP64 prediction (opt-in): V_l^T = K* X_l^T with X_l = rows of the explicit inverse L^-1, the product on
  * the INT8 tensor cores (gpr_ozaki_gemm_nt).  Stands in for tc.cholesky_solve(K*^T, L) + the row sums of gpr.py:100-104 and the

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpygpr_b200.so")
 
 TILE = 128
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # name -> (restype, argtypes).  Pointers are passed as integers (tensor.data_ptr()).
 _P, _I, _LL = c_void_p, c_int, c_longlong
@@ -76,6 +76,7 @@ SIGNATURES = {
     "gpr_ozaki_planes_bytes": (c_longlong, [_I, _I, _I]),
     "gpr_ozaki_split": (c_int, [_P, _LL, _I, _I, _I, c_double, _P, _P, _I, _LL, _P]),
     "gpr_ozaki_gemm_nt": (c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, c_double, _P, _LL, _I, _LL, _I, _I, c_double, _I, _P]),
+    "gpr_ozaki_gemm_nt_window": (c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, c_double, _P, _LL, _I, _LL, _I, _I, c_double, _I, _P]),
     "gpr_gemv_sub": (c_int, [_P, _LL, _LL, _I, _I, _I, _P, _LL, _P, _LL, _P]),
     "gpr_triu_rows": (c_int, [_P, _P, _I, _I, _P, _P]),
     "gpr_grad_from_kinv": (c_int, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),

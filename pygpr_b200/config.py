@@ -50,6 +50,8 @@ class Options:
     emulate_fit_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64_FIT", "0"))
     emulate_fit_panel: int = int(os.environ.get("PYGPR_EMULATE_FIT_PANEL", "0"))
     emulate_fit_chunk: int = int(os.environ.get("PYGPR_EMULATE_FIT_CHUNK", "32"))
+    # the FP64 work on the next diagonal block runs on a high-priority side stream under the current panel's trailing update (0 = in line)
+    emulate_fit_lookahead: bool = os.environ.get("PYGPR_EMULATE_FIT_LOOKAHEAD", "1") != "0"
 
 
 options = Options()

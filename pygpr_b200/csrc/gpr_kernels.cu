@@ -1132,7 +1132,7 @@ extern "C" long long gpr_potrf_work_bytes(int B, int npad) {
 
 // Internal streams / events of the two-stream per-column schedule (created once per device; no device memory)
 struct PotrfAux {
-    cudaStream_t chain = nullptr, chain2 = nullptr, bulk = nullptr;
+    cudaStream_t chain = nullptr, chain2 = nullptr, bulk = nullptr, bulk_hi = nullptr;
     cudaEvent_t fork = nullptr, join_chain = nullptr, join_chain2 = nullptr, join_bulk = nullptr, diag[4] = {}, bulk_done[4] = {},
                 first_done[4] = {};
     bool ready = false;
@@ -1150,6 +1150,10 @@ static PotrfAux* potrf_aux() {
         if (cudaStreamCreateWithPriority(&x.chain, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;   // hi = highest priority
         if (cudaStreamCreateWithPriority(&x.chain2, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithPriority(&x.bulk, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+        // a second bulk stream one step above the lowest priority, used when the caller's own stream is a high-priority one: a
+        // factorisation enqueued under someone else's tensor-core-bound launch (engine.fit_emulated's look-ahead) must not queue its
+        // panels behind that launch's thousands of default-priority CTAs
+        if (cudaStreamCreateWithPriority(&x.bulk_hi, cudaStreamNonBlocking, (hi < lo - 1) ? lo - 1 : lo) != cudaSuccess) return nullptr;
         cudaEvent_t* evs[] = {&x.fork, &x.join_chain, &x.join_chain2, &x.join_bulk, &x.diag[0], &x.diag[1], &x.diag[2], &x.diag[3],
                               &x.bulk_done[0], &x.bulk_done[1], &x.bulk_done[2], &x.bulk_done[3],
                               &x.first_done[0], &x.first_done[1], &x.first_done[2], &x.first_done[3]};
@@ -1243,6 +1247,13 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
     // the internal streams and events are per device: one factorisation at a time may be ENQUEUED through them
     std::unique_lock<std::mutex> enqueue_lock(g_potrf_enqueue_mutex, std::defer_lock);
     if (aux) enqueue_lock.lock();
+    cudaStream_t bulk_stream = nullptr;
+    if (aux) {
+        int lo_p = 0, hi_p = 0, st_p = 0;
+        bulk_stream = aux->bulk;
+        if (cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p) == cudaSuccess && cudaStreamGetPriority(st, &st_p) == cudaSuccess && st_p < lo_p)
+            bulk_stream = aux->bulk_hi;   // the caller runs this factorisation on a high-priority stream (under another launch)
+    }
     if (aux) {
         char* p = reinterpret_cast<char*>(slots) + potrf_slot_tiles(B, nt, sms) * TILE * TILE * 8;
         counters_c = reinterpret_cast<int*>(p);
@@ -1253,11 +1264,11 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         CUDA_TRY(cudaEventRecord(aux->fork, st));
         CUDA_TRY(cudaStreamWaitEvent(aux->chain, aux->fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(aux->chain2, aux->fork, 0));
-        CUDA_TRY(cudaStreamWaitEvent(aux->bulk, aux->fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(bulk_stream, aux->fork, 0));
     }
     // sd: diagonal tiles; sf: first panel tile + look-ahead product (runs ALONGSIDE the diagonal tile of its column: only its
     // solve waits, on a flag, for inv(L_jj)); sb: the bulk of the panel
-    cudaStream_t sd = aux ? aux->chain : st, sf = aux ? aux->chain2 : st, sb = aux ? aux->bulk : st;
+    cudaStream_t sd = aux ? aux->chain : st, sf = aux ? aux->chain2 : st, sb = aux ? bulk_stream : st;
     auto launch_panel = [&](cudaStream_t s_, int j, int row0, int ntile_rows, int lookahead, int S, double* sl, int* cnt, int* dflag) {
         dim3 grid((ntile_rows + lookahead) * S, B);
         if (gen)

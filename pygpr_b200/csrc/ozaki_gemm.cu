@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const double* __restrict__ scaleA, const double* __restrict__ scaleB, double* __restrict__ C, long long ldc,
             int M, int N, int kpad, int stages, int b_lower, double beta, int group_m, int tmem_cols,
-            int a_batch_rows, int b_batch_rows, long long c_batch_stride, int a_upper, int c_lower, double alpha) {
+            int a_batch_rows, int b_batch_rows, long long c_batch_stride, int a_upper, int c_lower, double alpha, int a_off, int b_off) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled tiles want (at least) 512 B alignment
@@ -267,9 +267,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     if (b_lower >= 0) nkb = min(nkb, (b_lower + (tn + 1) * BN + BKT - 1) / BKT);   // B[j, k] = 0 for k > j + b_lower
     const int kb0 = a_upper >= 0 ? min(nkb - 1, (a_upper + tm * BM) / BKT) : 0;   // A[i, k] = 0 for k < i + a_upper (rows of an upper factor)
     // batched product: batch entry blockIdx.y owns a_batch_rows / b_batch_rows consecutive (padded) rows of the plane arrays
-    const int a_row0 = blockIdx.y * a_batch_rows + tm * BM, b_row0 = blockIdx.y * b_batch_rows + tn * BN;
-    scaleA += (long long)blockIdx.y * a_batch_rows;
-    scaleB += (long long)blockIdx.y * b_batch_rows;
+    // (a_off / b_off: the product uses a window of rows of every batch entry's operand, starting that many rows in)
+    const int a_row0 = blockIdx.y * a_batch_rows + a_off + tm * BM, b_row0 = blockIdx.y * b_batch_rows + b_off + tn * BN;
+    scaleA += (long long)blockIdx.y * a_batch_rows + a_off;
+    scaleB += (long long)blockIdx.y * b_batch_rows + b_off;
     C += (long long)blockIdx.y * c_batch_stride;
 
     if (threadIdx.x == 0) {
@@ -433,14 +434,27 @@ extern "C" int gpr_ozaki_split(const double* X, long long ld, int rows, int k, i
 extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int M, const void* planesB, const double* scaleB, int N,
                                  int K, int slices, int b_lower, double beta, double* C, long long ldc, int batch,
                                  long long c_batch_stride, int a_upper, int c_lower, double alpha, int b_shared, void* stream) {
+    return gpr_ozaki_gemm_nt_window(planesA, scaleA, M, 0, 0, planesB, scaleB, N, 0, 0, K, slices, b_lower, beta, C, ldc, batch, c_batch_stride,
+                                    a_upper, c_lower, alpha, b_shared, stream);
+}
+
+extern "C" int gpr_ozaki_gemm_nt_window(const void* planesA, const double* scaleA, int M, int a_rows_total, int a_row_off, const void* planesB,
+                                        const double* scaleB, int N, int b_rows_total, int b_row_off, int K, int slices, int b_lower,
+                                        double beta, double* C, long long ldc, int batch, long long c_batch_stride, int a_upper,
+                                        int c_lower, double alpha, int b_shared, void* stream) {
     if (!(planesA && planesB && scaleA && scaleB && C && M > 0 && N > 0 && K > 0 && ldc >= N && slices >= 1 && slices <= oz::MAX_SLICES &&
           batch >= 1 && batch <= 65535 && b_lower >= -1 && a_upper >= -1))
         return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_gemm_nt%s (slices=%lld)", "", slices);
+    if (a_rows_total <= 0) { a_rows_total = oz::round_up(M, oz::BM); a_row_off = 0; }
+    if (b_rows_total <= 0) { b_rows_total = oz::round_up(N, oz::BM); b_row_off = 0; }
+    if (!(a_rows_total % oz::BM == 0 && b_rows_total % oz::BM == 0 && a_row_off >= 0 && b_row_off >= 0 && a_row_off % oz::BN == 0 &&
+          b_row_off % oz::BN == 0 && a_row_off + M <= a_rows_total && b_row_off + N <= b_rows_total))
+        return gpr_internal_fail(GPR_ERR_BAD_ARG, "bad argument: gpr_ozaki_gemm_nt_window%s (row window, offset %lld)", "", a_row_off);
     // int32 headroom of a diagonal: (g+1) products of |q| <= 128 over K terms
     if ((long long)K * slices * 16384LL >= (1LL << 31))
         return gpr_internal_fail(GPR_ERR_UNSUPPORTED, "K too long for exact int32 accumulation%s (K=%lld): split the product", "", K);
     const int kpad = oz::round_up(K, oz::BK);
-    const int rpadA = oz::round_up(M, oz::BM), rpadB = oz::round_up(N, oz::BM);
+    const int rpadA = a_rows_total, rpadB = b_rows_total;     // rows of one batch entry in the plane arrays
     // k-block: 64 B rows.  The 32 B variant (twice the ring depth where 7-8 digit planes leave room for only two 64-wide stages)
     // is kept as an A/B knob: measured slower at every plane count (4096^3, 7 planes: 92 vs 106 TFLOP/s-equivalent; 6 planes:
     // 110 vs 142) — the per-stage handshake and the 32 B TMA rows cost more than the deeper ring hides.
@@ -466,7 +480,7 @@ extern "C" int gpr_ozaki_gemm_nt(const void* planesA, const double* scaleA, int 
     if (e == cudaSuccess)                                                                                                      \
         oz::gemm_kernel<S, BKT><<<dim3(tiles_m * tiles_n, batch), oz::NTHREADS, smem, (cudaStream_t)stream>>>(                  \
             mapA, mapB, scaleA, scaleB, C, ldc, M, N, kpad, stages, b_lower, beta, group_m, tmem_cols, rpadA,                  \
-            b_shared ? 0 : rpadB, c_batch_stride, a_upper, c_lower, alpha);
+            b_shared ? 0 : rpadB, c_batch_stride, a_upper, c_lower, alpha, a_row_off, b_row_off);
 #define OZ_LAUNCH(S)                                                                                                           \
     case S:                                                                                                                    \
         if (bk == 64) { OZ_LAUNCH_BK(S, 64) } else { OZ_LAUNCH_BK(S, 32) }                                                     \

@@ -255,6 +255,17 @@ def fit(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: bool, wan
     return st
 
 
+_side_streams = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One high-priority stream per device for latency chains that should run under a tensor-core-bound launch on the current one."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _side_streams[key]
+
+
 def can_fit_emulated(n: int, shared: Optional[FitState]) -> bool:
     """Shapes fit_emulated handles: any order from 512 up (padded to whole 128-row blocks like engine.fit); a shared communication
     block must itself be a whole number of blocks."""
@@ -316,16 +327,48 @@ def fit_emulated(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: 
         r_start = ng
     nn = npad * npad
 
-    def panel_update(e0, ne, r0, r1, pX, zsrc, z_stride, b_shared):
-        """rows below [r0, r1): P = K[below, r0:r1] X^T, K[below, below] -= P P^T, y[below] -= P z[r0:r1]"""
-        h, hR = r1 - r0, npad - r1
+    def panel_update(e0, ne, r0, r1, r2, pX, zsrc, z_stride, b_shared, ready):
+        """rows below [r0, r1): P = K[below, r0:r1] X^T, K[below, below] -= P P^T, y[below] -= P z[r0:r1].  The trailing update goes in
+        two products: first the columns [r1, r2) of the NEXT panel (after it — and the right-hand side update — the next diagonal
+        block and its part of y are final: `ready` is recorded), then the rest."""
+        h, hR, h2 = r1 - r0, npad - r1, r2 - r1
         win = L[e0, r1:, r0:]                                  # [hR, .] window of the first expert of the chunk; the others nn apart
         pA = ozaki_split(win, slices, batch=ne, batch_stride=nn, rows=hR, k=h)
         ozaki_gemm_nt(pA, pX, out=L[e0:e0 + ne, r1:, r0:r1], batch=ne, b_lower=0, b_shared=b_shared)
         pP = ozaki_split(win, slices, batch=ne, batch_stride=nn, rows=hR, k=h)
-        ozaki_gemm_nt(pP, pP, out=L[e0:e0 + ne, r1:, r1:], batch=ne, beta=1.0, alpha=-1.0, c_lower=True)
+        ozaki_gemm_nt(pP, pP, out=L[e0:e0 + ne, r1:, r1:r2], batch=ne, beta=1.0, alpha=-1.0, c_lower=True, a_win=(0, hR), b_win=(0, h2))
         _lib.call("gpr_gemv_sub", _p(win), npad, nn, ne, hR, h, _p(zsrc), z_stride, _p(yrem[e0:e0 + ne, r1:]), yrem.stride(0), _stream())
         _count(1)
+        ready.record(main)
+        if r2 < npad:
+            ozaki_gemm_nt(pP, pP, out=L[e0:e0 + ne, r2:, r2:], batch=ne, beta=1.0, alpha=-1.0, c_lower=True,
+                          a_win=(h2, hR - h2), b_win=(h2, hR - h2))
+
+    def factor_diag(e0, ne, r0, r1):
+        """FP64: the diagonal block [r0, r1) of the chunk's experts (+ its part of the forward solve), its inverse as digit planes for the
+        panel solve.  Runs on the side stream, under the previous panel's trailing update."""
+        h = r1 - r0
+        D = L[e0:e0 + ne, r0:r1, r0:r1].contiguous()
+        yp = yrem[e0:e0 + ne, r0:r1].contiguous()
+        invd, zp, ld, zzp, inf = potrf_inplace(D, yp)
+        L[e0:e0 + ne, r0:r1, r0:r1] = D
+        invdiag[e0:e0 + ne, r0 // TILE:r1 // TILE] = invd
+        z[e0:e0 + ne, r0:r1] = zp
+        logdet_half[e0:e0 + ne] += ld
+        zz[e0:e0 + ne] += zzp
+        cur = info[e0:e0 + ne]
+        info[e0:e0 + ne] = torch.where((cur == 0) & (inf > 0), inf + r0, cur)
+        pX = None
+        if r1 < npad:
+            X = torch.empty(ne, h, h, dtype=F64, device=dev)
+            scratch = _work("emf_potri", int(lib.gpr_potri_scratch_bytes(ne, h)), dev)
+            _lib.call("gpr_tril_inverse", _p(D), _p(invd), ne, h, _p(X), _p(scratch), _stream())
+            _count(3)
+            pX = ozaki_split(X.view(ne * h, h), slices)
+            for t in (pX.planes, pX.scale):                    # allocated on the side stream, read by the main one
+                t.record_stream(main)
+        zp.record_stream(main)
+        return pX, zp
 
     # experts per chunk: what the free HBM holds of the transient digit planes (two sets of the widest [below x panel] window)
     widest = (npad - r_start) * max(r_start, min(panel, npad - r_start))      # elements of the widest [below x panel] window
@@ -333,29 +376,36 @@ def fit_emulated(x: torch.Tensor, y: torch.Tensor, hp: torch.Tensor, has_noise: 
     per = 2 * slices * widest + hmax * hmax * (16 + slices) + (1 << 20)
     free, _ = torch.cuda.mem_get_info(dev)
     E = int(max(1, min(chunk, B, (free - (2 << 30)) // per)))
+    # Look-ahead over panels: the FP64 work on diagonal block p+1 (a latency chain that occupies a few SMs) runs on a high-priority side
+    # stream while the tensor cores finish panel p's trailing update on the main one.
+    from .config import options
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if options.emulate_fit_lookahead else main
     for e0 in range(0, B, E):
         ne = min(e0 + E, B) - e0
+        ready, done = torch.cuda.Event(), torch.cuda.Event()
         if shared is not None:
-            panel_update(e0, ne, 0, r_start, pXg, z[e0:e0 + ne], z.stride(0), True)
-        for r0 in range(r_start, npad, panel):
-            r1 = min(r0 + panel, npad)
-            h = r1 - r0
-            D = L[e0:e0 + ne, r0:r1, r0:r1].contiguous()
-            yp = yrem[e0:e0 + ne, r0:r1].contiguous()
-            invd, zp, ld, zzp, inf = potrf_inplace(D, yp)      # FP64: the panel's diagonal block (+ its part of the forward solve)
-            L[e0:e0 + ne, r0:r1, r0:r1] = D
-            invdiag[e0:e0 + ne, r0 // TILE:r1 // TILE] = invd
-            z[e0:e0 + ne, r0:r1] = zp
-            logdet_half[e0:e0 + ne] += ld
-            zz[e0:e0 + ne] += zzp
-            cur = info[e0:e0 + ne]
-            info[e0:e0 + ne] = torch.where((cur == 0) & (inf > 0), inf + r0, cur)
-            if r1 < npad:
-                X = torch.empty(ne, h, h, dtype=F64, device=dev)
-                scratch = _work("emf_potri", int(lib.gpr_potri_scratch_bytes(ne, h)), dev)
-                _lib.call("gpr_tril_inverse", _p(D), _p(invd), ne, h, _p(X), _p(scratch), _stream())
-                _count(3)
-                panel_update(e0, ne, r0, r1, ozaki_split(X.view(ne * h, h), slices), zp, zp.stride(0), False)
+            panel_update(e0, ne, 0, r_start, min(r_start + panel, npad), pXg, z[e0:e0 + ne], z.stride(0), True, ready)
+        else:
+            ready.record(main)
+        r0 = r_start
+        r1 = min(r0 + panel, npad)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            pX, zp = factor_diag(e0, ne, r0, r1)
+            done.record(side)
+        while True:
+            main.wait_event(done)
+            if r1 >= npad:
+                break
+            r2 = min(r1 + panel, npad)
+            ready, done = torch.cuda.Event(), torch.cuda.Event()
+            panel_update(e0, ne, r0, r1, r2, pX, zp, zp.stride(0), False, ready)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                pX, zp = factor_diag(e0, ne, r1, r2)
+                done.record(side)
+            r0, r1 = r1, r2
     alpha = None
     if want_alpha:
         alpha = torch.empty(B, npad, dtype=F64, device=dev)
@@ -885,15 +935,21 @@ def ozaki_split(X: torch.Tensor, slices: int, bound: float = 0.0, out: Optional[
 
 def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = None, beta: float = 0.0,
                   b_lower: Optional[int] = None, batch: int = 1, a_upper: Optional[int] = None, c_lower: bool = False,
-                  alpha: float = 1.0, b_shared: bool = False) -> torch.Tensor:
+                  alpha: float = 1.0, b_shared: bool = False, a_win: Optional[Tuple[int, int]] = None,
+                  b_win: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """C = beta*C + A B^T from digit planes, on tcgen05.mma kind::i8 (gpr_ozaki_gemm_nt).
+    a_win / b_win = (first row, rows): the product uses that window of rows of (every batch entry of) the operand
+    (gpr_ozaki_gemm_nt_window; both multiples of 128 here).
 
     b_lower = o: B[j, k] = 0 for k > j + o (True means o = 0), the zero k-blocks are skipped; a_upper = o: A[i, k] = 0 for
     k < i + o (rows of an upper-triangular factor); c_lower: only the tiles touching the lower triangle of C are computed and
     written.  batch > 1: A and B hold `batch` operands stacked along the rows (rows % 128 == 0 each); the result is [batch, M, N]."""
     assert A.k == B.k and A.slices == B.slices and A.rows % batch == 0 and (b_shared or B.rows % batch == 0)
-    M, N = A.rows // batch, (B.rows if b_shared else B.rows // batch)
-    assert batch == 1 or (M % 128 == 0 and N % 128 == 0)
+    Mt, Nt = A.rows // batch, (B.rows if b_shared else B.rows // batch)
+    assert batch == 1 or (Mt % 128 == 0 and Nt % 128 == 0)
+    (a_off, M), (b_off, N) = (a_win or (0, Mt)), (b_win or (0, Nt))
+    windowed = a_win is not None or b_win is not None
+    assert a_off % 128 == 0 and b_off % 128 == 0 and a_off + M <= Mt and b_off + N <= Nt and (not windowed or (M % 128 == 0 and N % 128 == 0))
     shape = (M, N) if batch == 1 else (batch, M, N)
     if out is None:
         out = torch.empty(shape, dtype=F64, device=A.planes.device)
@@ -902,9 +958,15 @@ def ozaki_gemm_nt(A: DigitPlanes, B: DigitPlanes, out: Optional[torch.Tensor] = 
         out = out[0]
     assert tuple(out.shape) == shape and out.stride(-1) == 1 and (batch == 1 or out.stride(0) % 2 == 0)
     off = -1 if b_lower is None or b_lower is False else (0 if b_lower is True else int(b_lower))
-    _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), M, _p(B.planes), _p(B.scale), N, A.k, A.slices,
-              off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0,
-              -1 if a_upper is None else int(a_upper), int(c_lower), float(alpha), int(b_shared and batch > 1), _stream())
+    if windowed:
+        rnd = lambda v: round_up(v, 128)
+        _lib.call("gpr_ozaki_gemm_nt_window", _p(A.planes), _p(A.scale), M, rnd(Mt), a_off, _p(B.planes), _p(B.scale), N, rnd(Nt), b_off,
+                  A.k, A.slices, off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0,
+                  -1 if a_upper is None else int(a_upper), int(c_lower), float(alpha), int(b_shared and batch > 1), _stream())
+    else:
+        _lib.call("gpr_ozaki_gemm_nt", _p(A.planes), _p(A.scale), M, _p(B.planes), _p(B.scale), N, A.k, A.slices,
+                  off, float(beta), _p(out), out.stride(-2), batch, out.stride(0) if batch > 1 else 0,
+                  -1 if a_upper is None else int(a_upper), int(c_lower), float(alpha), int(b_shared and batch > 1), _stream())
     _count(1)
     return out
 
