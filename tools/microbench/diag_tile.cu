@@ -1,7 +1,7 @@
 // Latency of the factorisation + inversion of ONE 128x128 diagonal tile inside a CTA (the serial link of the Cholesky's
 // dependency chain): clocks of potf2 / trtri, old (8x8 register blocks) vs new (32-wide warp panels + DMMA), and the error of
 // both against a host factorisation.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I pygpr_b200/csrc -o diag_tile tools/microbench/diag_tile.cu && ./diag_tile
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I pygpr_b200/csrc -I tools/microbench -o diag_tile tools/microbench/diag_tile.cu && ./diag_tile
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -11,6 +11,7 @@
 
 #include "gpr_core.cuh"
 #include "gpr_diag_tile.cuh"
+#include "diag_tile_round1.cuh"
 
 using namespace gpr;
 
