@@ -142,7 +142,7 @@ __device__ __forceinline__ FeatSmem carve_feat(double* base, int dpad) {
 }
 __host__ __device__ static inline int feat_smem_bytes(int dpad) { return (2 * TILE * feat_sld(dpad) + 2 * TILE) * 8; }
 // dynamic shared memory of a kernel that factorises diagonal tiles: the pipeline stages, overlaid by the 128x128 tile, and
-// behind the tile the larger of the feature tiles (GEN) and the block-major exchange buffer of potf2_blk / trtri_blk
+// behind the tile the larger of the feature tiles (GEN) and the scratch of potf2_tile / trtri_tile (gpr_diag_tile.cuh)
 static inline int diag_smem_bytes(int gen, int dpad) {
     const int behind = (gen && feat_smem_bytes(dpad) > BM_DOUBLES * 8) ? feat_smem_bytes(dpad) : BM_DOUBLES * 8;
     const int need = TILE * XLD * 8 + behind;
@@ -549,7 +549,7 @@ struct GemvHook {  // s[r] += sum_k A[r][k] z[k] on every landed chunk; half-war
 };
 
 // Tail of a diagonal-tile task, shared by the per-column kernel and the dataflow kernel: T = K_jj - acc (- dpart) ->
-// potf2 + trti2 in registers -> L_jj, inv(L_jj), log-determinant / info, forward-solve block z_j.
+// potf2_tile + trtri_tile (gpr_diag_tile.cuh) -> L_jj, inv(L_jj), log-determinant / info, forward-solve block z_j.
 // Scalars that several CTAs update in turn (logdet_half, zz, info) and z go through L2 (__ldcg/__stcg): in the dataflow
 // kernel consecutive block columns of one expert run on different SMs and L1 is not coherent.
 // developer build (-DGPR_DIAG_STAMPS, tools/diag_phases.py): clock stamps of the phases of a diagonal-tile task, expert 0
@@ -1234,7 +1234,7 @@ static int potrf_impl(double* L, int gen, const double* a, const double* nrm, co
         CUDA_TRY(opt_in_smem(potrf_panel_kernel<false>, smem_panel));
     }
     // Per-column schedule.  With a workspace it runs on three internal streams: the diagonal tiles (latency bound: the
-    // register-resident potf2/trti2 is ~70 us per column) and the FIRST panel tile + look-ahead product of each column on two
+    // factorisation + inversion of the tile was ~70 us per column in round 1, ~31 us since gpr_diag_tile.cuh) and the FIRST panel tile + look-ahead product of each column on two
     // high-priority streams — the first tile's partial products run alongside the diagonal tile of its own column and only its
     // solve waits, on a flag, for inv(L_jj) — and the BULK of each panel (row tiles j+2 ...) on a low-priority one that only
     // needs diag(j).  A column then costs max(bulk, diag + solve) instead of diag + first tile + bulk

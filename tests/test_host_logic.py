@@ -247,3 +247,30 @@ def test_ozaki_reference_arithmetic():
         pa, sa = ozaki_ref.split(A, S); pb, sb = ozaki_ref.split(B, S)
         errs.append(np.abs(ozaki_ref.gemm_nt(pa, sa, 40, pb, sb, 24, S) - ref).max() / np.abs(ref).max())
     assert errs[-1] < 1e-13 and all(b < a / 50 for a, b in zip(errs, errs[1:]))
+
+
+def test_emulated_form_heuristics_and_mle_lifetime():
+    """Host logic added in round 2: where the emulated factorisation is taken (engine.fit_emulated_pays), and GRBCM_MLE holds no
+    reference cycle (a dropped instance — and its HBM-sized factor buffer — must go away without a cyclic GC pass)."""
+    import gc
+    import weakref
+    import torch
+    import pygpr_b200 as P
+    from pygpr_b200 import engine
+    assert engine.fit_emulated_pays(1, 16384) and engine.fit_emulated_pays(1, 8192) and not engine.fit_emulated_pays(1, 4096)
+    assert engine.fit_emulated_pays(4, 4096) and not engine.fit_emulated_pays(3, 4096) and not engine.fit_emulated_pays(64, 2048)
+    assert engine.can_fit_emulated(1000, None) and not engine.can_fit_emulated(300, None)
+    xl, yl = torch.rand(3, 20, 2, dtype=torch.float64), torch.rand(3, 20, dtype=torch.float64)
+    xg, yg = torch.rand(10, 2, dtype=torch.float64), torch.rand(10, dtype=torch.float64)
+    model = P.GRBCM(xl, yl, xg, yg, P.Compose([P.Squared_exponential(), P.White_noise()]))
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        mle = P.GRBCM_MLE(model, chunk=2)
+        assert mle.model is mle                               # the duck type optimisers rely on (loss.model.params / set_params)
+        ref = weakref.ref(mle)
+        del mle
+        assert ref() is None
+    finally:
+        if was_enabled:
+            gc.enable()
