@@ -131,6 +131,10 @@ class FitState:
     Linv: Optional[torch.Tensor] = None        # [B, npad, npad] L^-1 (tril_inverse), cached for the GEMM-form prediction
     Kinv: Optional[torch.Tensor] = None        # [B, n, n] K^-1 (kinv), cached for the shared-block gradient
     shared_upper: bool = False                 # the copied leading block also carries the communication expert's L_g^-T
+    # state of the opt-in emulated forms (ensure_inverse_factors / _emulated_experts)
+    upper_is_inverse: bool = False             # the strict block-upper part of L holds L^-T (in place)
+    plane_cache: Optional[dict] = None         # digit planes of the inverse rows per expert chunk, kept while HBM allows
+    sig2_max: Optional[float] = None           # max sig^2 over the experts: the bound of K*'s digit split, read back once
 
     def nlml(self) -> torch.Tensor:
         """NLML = 1/2 y^T alpha + sum log L_ii + n/2 log 2 pi   (loss.py:49-51); y^T alpha = z.z"""
