@@ -35,7 +35,7 @@ class Options:
     # (0 = off, the FP64 DMMA path; 6 = FP64 grade, ~1e-11 on V; 3-4 = the FP32-grade mode).  engine.predict_shared_emulated
     emulate_slices: int = int(os.environ.get("PYGPR_EMULATE_FP64", "0"))
     emulate_chunk: int = int(os.environ.get("PYGPR_EMULATE_CHUNK", "8"))
-    # below this (padded) order the emulated prediction stays off even when opted in: at n = 1000 its staging costs more than the
+    # below this (padded) order the emulated prediction and gradient stay off even when opted in: at n = 1000 its staging costs more than the
     # product it replaces (config 1: 0.38 vs 0.28 ms); from 2048 up it wins.  Tests set 0 to exercise it on small shapes.
     emulate_min_order: int = int(os.environ.get("PYGPR_EMULATE_MIN_ORDER", "2048"))
     # opt-in: K^-1 = L^-T L^-1 of the NLML gradient on the INT8 tensor cores with this many digit planes (0 = off; 7 keeps the

@@ -693,7 +693,8 @@ def lml_grad(st: FitState) -> torch.Tensor:
     """d NLML / d hp [B, P] from a finished fit (destroys the strict block-upper part of st.L)   loss.py:59-128."""
     assert st.alpha is not None
     from .config import options
-    if options.emulate_grad_slices > 0 and st.npad > TILE and (st.shared_from is None or st.shared_from.n % TILE == 0):
+    if (options.emulate_grad_slices > 0 and st.npad > TILE and st.npad >= options.emulate_min_order
+            and (st.shared_from is None or st.shared_from.n % TILE == 0)):
         return lml_grad_emulated(st, options.emulate_grad_slices, options.emulate_chunk)
     P = st.d + 1 + int(st.has_noise)
     grad = torch.empty(st.B, P, dtype=F64, device=st.L.device)
