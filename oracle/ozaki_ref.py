@@ -18,14 +18,25 @@ def round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
-def split(X: np.ndarray, slices: int):
-    """planes [slices, rpad, kpad] int8, scale [rpad] float64 — split_kernel."""
+def digits_by_bias(I: np.ndarray, slices: int) -> np.ndarray:
+    """Balanced radix-256 digits of int64 I (|I| < 2^(8 slices - 2)) WITHOUT the carry loop, as se_cross_planes_kernel forms them:
+    with J = I + sum_t 128 * 256^t the bytes of J are d_t + 128, so the digits are the bytes of J ^ 0x80..80.  Returns
+    [slices, ...] int8, most significant digit first (plane 0), like split()."""
+    bias = np.uint64(sum(0x80 << (8 * t) for t in range(slices)))
+    with np.errstate(over="ignore"):                          # modulo 2^64, like the kernel's unsigned long long
+        W = (np.asarray(I, dtype=np.int64).astype(np.uint64) + bias) ^ bias
+    return np.stack([((W >> np.uint64(8 * (slices - 1 - t))) & np.uint64(0xFF)).astype(np.uint8).view(np.int8) for t in range(slices)])
+
+
+def split(X: np.ndarray, slices: int, bound: float = 0.0):
+    """planes [slices, rpad, kpad] int8, scale [rpad] float64 — split_kernel.  bound > 0: every row is scaled by that bound instead of
+    its own maximum (the caller vouches |x| <= bound; gpr_ozaki_split(bound), gpr_se_cross_planes)."""
     X = np.asarray(X, dtype=np.float64)
     rows, k = X.shape
     rpad, kpad = round_up(rows, BM), round_up(k, BK)
     planes = np.zeros((slices, rpad, kpad), dtype=np.int8)
     scale = np.zeros(rpad, dtype=np.float64)
-    amax = np.abs(X).max(axis=1)
+    amax = np.abs(X).max(axis=1) if not bound > 0.0 else np.full(rows, float(bound))
     for r in range(rows):
         a = amax[r]
         if not (a > 0.0 and np.isfinite(a)):

@@ -415,3 +415,8 @@ def test_fused_cross_kernel_digit_planes_bit_exact(eng, B, n, d, m, slices):
     torch.cuda.synchronize()
     assert torch.equal(planes, two.planes) and torch.equal(scale, two.scale)
     assert int(planes[:, :, n:].abs().sum()) == 0 and int(planes.abs().sum()) > 0
+    # ... and both equal the numpy restatement of the split with a known bound (oracle/ozaki_ref.py)
+    import numpy as np
+    from oracle import ozaki_ref
+    npl, nsc = ozaki_ref.split(Ks.view(B * m, npad).cpu().numpy(), slices, bound=bound)
+    assert np.array_equal(planes.cpu().numpy(), npl) and np.array_equal(scale.cpu().numpy(), nsc)

@@ -274,3 +274,30 @@ def test_emulated_form_heuristics_and_mle_lifetime():
     finally:
         if was_enabled:
             gc.enable()
+
+
+def test_digit_planes_without_the_carry_loop():
+    """The fused K* builder (se_cross_planes_kernel) forms the balanced radix-256 digits as the bytes of (I + 0x80..80) ^ 0x80..80;
+    oracle/ozaki_ref.py restates both forms: they must agree digit for digit, and a known bound must give the planes of split()."""
+    import numpy as np
+    from oracle import ozaki_ref
+    rng = np.random.default_rng(5)
+    for slices in (1, 3, 6, 7, 8):
+        lim = 1 << (8 * slices - 2)
+        I = rng.integers(-lim + 1, lim, size=4000, dtype=np.int64)
+        I[:4] = (0, lim - 1, -lim + 1, -1)
+        fast = ozaki_ref.digits_by_bias(I, slices)
+        J = I.copy()
+        for t in range(slices - 1, -1, -1):                   # the carry loop of oz::split_kernel
+            dgt = (J & 0xFF).astype(np.uint8).view(np.int8)
+            assert np.array_equal(fast[t], dgt)
+            J = (J - dgt.astype(np.int64)) >> 8
+        assert not J.any()
+    X = rng.random((5, 70)) * 1.7                              # 0 <= x < bound
+    planes, scale = ozaki_ref.split(X, 6, bound=1.7)
+    e = 0 + 3                                                  # ilogb(1.7) + 3
+    assert np.all(scale[:5] == np.ldexp(1.0, e - 8)) and np.all(scale[5:] == 0)
+    Iref = np.rint(X * np.ldexp(1.0, 48 - e)).astype(np.int64)
+    assert np.array_equal(planes[:, :5, :70], ozaki_ref.digits_by_bias(Iref, 6))
+    back = sum(planes[t, :5, :70].astype(np.float64) * 256.0 ** -(t + 1) for t in range(6)) * np.ldexp(1.0, e)
+    assert np.max(np.abs(back - X)) <= np.ldexp(1.0, e - 48)
