@@ -301,3 +301,15 @@ def test_digit_planes_without_the_carry_loop():
     assert np.array_equal(planes[:, :5, :70], ozaki_ref.digits_by_bias(Iref, 6))
     back = sum(planes[t, :5, :70].astype(np.float64) * 256.0 ** -(t + 1) for t in range(6)) * np.ldexp(1.0, e)
     assert np.max(np.abs(back - X)) <= np.ldexp(1.0, e - 48)
+
+
+def test_tools_and_entry_points_compile():
+    """The measurement tools are run by hand on the GPU box: keep them at least syntactically alive on every CPU run."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, f) for f in ("bench.py", "__graft_entry__.py")]
+    assert len(files) > 10
+    for f in files:
+        py_compile.compile(f, doraise=True)
