@@ -1050,6 +1050,8 @@ def ensure_inverse_factors(st_g: Optional[FitState], st_l: FitState) -> None:
     prediction multiplies with rows of the explicit inverse.  With a shared communication block (st_g) its L_g^-T is copied into
     the leading block, not recomputed."""
     if getattr(st_l, "upper_is_inverse", False):
+        if st_l.plane_cache is None:                          # L^-T was put in place by tril_inverse: the planes of its rows may be kept too
+            st_l.plane_cache = {}
         return
     gt = 0
     if st_g is not None:
